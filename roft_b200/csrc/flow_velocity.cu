@@ -1,0 +1,686 @@
+// Optical-flow-aided velocity measurement + linear Kalman correction, batched over tracks
+// (north-star part 1).
+//
+// Replaces, for every track at once:
+//   ImageOpticalFlowMeasurement<T>::freeze        src/roft-lib/include/ROFT/ImageOpticalFlowMeasurement.hpp:231-283
+//   SKFCorrection::correctStep                    src/roft-lib/src/SKFCorrection.cpp:37-153
+//   SpatialVelocityModel + bfl::KFPrediction      src/roft-lib/src/SpatialVelocityModel.cpp:15-27
+//   observability gate                            src/roft-lib/src/ROFTFilter.cpp:294-301
+//
+// The reference materialises z (2N) and H (2N x 6) and then runs a SEQUENTIAL 2-row Kalman update per
+// pixel.  For per-pixel independent noise that is algebraically the information-form sum
+//     Lambda = (P+Q)^-1 + sum_j l_j H_j^T R^-1 H_j ,  eta = (P+Q)^-1 x + sum_j l_j H_j^T R^-1 z_j
+// (SURVEY.md F1), so the per-pixel work becomes a streaming reduction.  With x^ = (u-cx)/fx,
+// y^ = (v-cy)/fy, a = 1/d the two rows of H_j are  dt*fx*L1 and dt*fy*L2  with
+//     L1 = [a, 0, -x^a, -x^y^, 1+x^2, -y^]     L2 = [0, a, -y^a, -(1+y^2), x^y^, x^]
+// so the kernel accumulates S1 = sum l L1^T L1, S2 = sum l L2^T L2, g1 = sum l L1^T dx,
+// g2 = sum l L2^T dy in FP32 per thread, tree-reduces with warp shuffles, and hands FP64 block
+// partials to a per-track epilogue that applies the FP64 constants and solves the 6x6 system.
+// No atomics in the accumulation path.
+//
+// Laplacian re-weighting (SKFCorrection.cpp:91-116) needs the median of the innovation norms: pass A
+// streams the frame once and writes the compact list of norms; an exact 3-level radix select finds the
+// middle order statistic(s), one more pass over the norms gives b = mean|n - m|; pass B streams the frame
+// again and accumulates with the weights.
+#include "roftb_internal.cuh"
+
+namespace roftb {
+namespace {
+
+__device__ __forceinline__ float4 get4(const float4* p, bool ok) { return ok ? ld_nc_f4(p) : make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+
+// ---- per-warp-tile counts of selected candidates (only needed when stride > 1 or for ordered output) ----
+__global__ void __launch_bounds__(kThreads) k_mask_count(const uint8_t* __restrict__ seg, long long seg_stride, int thr,
+                                                        int HW, int n_warp_tiles, int32_t* __restrict__ wt_count,
+                                                        const VelCtl* __restrict__ ctl) {
+    const int t = blockIdx.y;
+    if (ctl && !ctl[t].enable) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t thr4 = (uint32_t)thr * 0x01010101u;
+    const uint32_t* mq = reinterpret_cast<const uint32_t*>(seg + (long long)t * seg_stride);
+    const int nq = HW >> 2;
+    for (int wt = blockIdx.x * (kThreads / 32) + warp; wt < n_warp_tiles; wt += gridDim.x * (kThreads / 32)) {
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = wt * 128 + j * 32 + lane;
+            const uint32_t m = q < nq ? ld_nc_u32(mq + q) : 0u;
+            c += __popc(__vcmpgtu4(m, thr4)) >> 3;
+        }
+        c = warp_sum(c);
+        if (lane == 0) wt_count[(long long)t * n_warp_tiles + wt] = c;
+    }
+}
+
+// in-place exclusive scan of each track's warp-tile counts (one block per track)
+__global__ void __launch_bounds__(kThreads) k_wt_scan(int32_t* __restrict__ wt_count, int n_warp_tiles, int32_t* __restrict__ total,
+                                                     const VelCtl* __restrict__ ctl) {
+    const int t = blockIdx.x;
+    if (ctl && !ctl[t].enable) return;
+    __shared__ int sh[kThreads / 32];
+    __shared__ int carry;
+    int32_t* p = wt_count + (long long)t * n_warp_tiles;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_warp_tiles; base += kThreads) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_warp_tiles ? p[i] : 0;
+        int incl = warp_scan_incl(v, lane);
+        if (lane == 31) sh[warp] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += sh[w];
+        const int c = carry;
+        if (i < n_warp_tiles) p[i] = c + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == kThreads - 1) carry = c + woff + incl;
+        __syncthreads();
+    }
+    if (total && threadIdx.x == 0) total[t] = carry;
+}
+
+// ---- the streaming pass ---------------------------------------------------------------------
+// PASS 0 (A): innovation norms -> compact list.   PASS 1 (B): weighted normal-equation accumulation.
+// FAST: float2 flow at full resolution (vector loads); otherwise generic per-pixel flow fetch.
+struct PassArgs {
+    Geom g;
+    FrameTable ft;
+    const uint8_t* seg; long long seg_stride; int thr;
+    const VelCtl* ctl;
+    int tiles_per_block, n_block_tiles, n_warp_tiles;
+    const int32_t* wt_prefix;
+    float* norms; uint32_t* norm_count;
+    const WeightParams* wp; int weight_flow;
+    const double* x_pred; int x_stride;
+    double* partials; int max_blocks;
+    double fx, fy;
+};
+
+template <int PASS, bool FAST>
+__global__ void __launch_bounds__(kThreads) k_flow_pass(PassArgs a) {
+    const int t = blockIdx.y;
+    const VelCtl c = a.ctl[t];
+    if (!c.enable) return;
+    const Geom& g = a.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t thr4 = (uint32_t)a.thr * 0x01010101u;
+    const uint32_t* mq = reinterpret_cast<const uint32_t*>(a.seg + (long long)t * a.seg_stride);
+    const float4* dq = reinterpret_cast<const float4*>(a.ft.depth[c.prev_slot] + (long long)t * a.ft.depth_stride);
+    const char* fbase = reinterpret_cast<const char*>(a.ft.flow[c.cur_slot]) +
+                        (long long)t * a.ft.flow_stride * (g.flow_s16 ? 2 : 4);
+    const float4* fq = reinterpret_cast<const float4*>(fbase);
+    const int nq = g.HW >> 2;
+
+    // predicted velocity (F = I: the predicted mean is the previous corrected mean) and FP32 row scales
+    float x[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = (float)a.x_pred[(long long)t * a.x_stride + i];
+    const float c1 = (float)(a.fx * c.dt), c2 = (float)(a.fy * c.dt);
+    WeightParams wp;
+    wp.use = 0;
+    if (PASS == 1 && a.weight_flow) wp = a.wp[t];
+
+    float acc[kNAcc];
+    if (PASS == 1) {
+#pragma unroll
+        for (int i = 0; i < kNAcc; ++i) acc[i] = 0.f;
+    }
+
+    const int tile_end = min((int)(blockIdx.x + 1) * a.tiles_per_block, a.n_block_tiles);
+    for (int tile = blockIdx.x * a.tiles_per_block; tile < tile_end; ++tile) {
+        const int wt = tile * (kThreads / 32) + warp;
+        if (wt >= a.n_warp_tiles) break;  // warp-uniform
+        uint32_t sel[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = wt * 128 + j * 32 + lane;
+            const uint32_t m = q < nq ? ld_nc_u32(mq + q) : 0u;
+            sel[j] = __vcmpgtu4(m, thr4);
+        }
+        if (g.stride > 1) {
+            // row-major rank of every candidate; keep rank % stride == 0 (hpp:237), BEFORE the gates
+            int r = a.wt_prefix[(long long)t * a.n_warp_tiles + wt];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int cnt = __popc(sel[j]) >> 3;
+                const int incl = warp_scan_incl(cnt, lane);
+                const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                unsigned rank = (unsigned)(r + incl - cnt);
+                uint32_t ns = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if ((sel[j] >> (8 * i)) & 1u) {
+                        if (rank % (unsigned)g.stride == 0u) ns |= 0xffu << (8 * i);
+                        ++rank;
+                    }
+                }
+                sel[j] = ns;
+                r += tot;
+            }
+        }
+        const uint32_t any = sel[0] | sel[1] | sel[2] | sel[3];
+        if (!__any_sync(0xffffffffu, any != 0u)) continue;
+
+        // issue every load of the tile before touching the data (up to 12 x 128-bit in flight per lane)
+        float4 D[4], F0[4], F1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = wt * 128 + j * 32 + lane;
+            const bool on = sel[j] != 0u;
+            D[j] = get4(dq + q, on);
+            if (FAST) {
+                F0[j] = get4(fq + 2 * q, on);
+                F1[j] = get4(fq + 2 * q + 1, on);
+            }
+        }
+
+        float nrm[16];
+        uint32_t vmask = 0;  // bit (4j+i): pixel passed the gates
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (sel[j] == 0u) continue;
+            const int px = (wt * 128 + j * 32 + lane) << 2;
+            const int v = px / g.W;
+            const int u0 = px - v * g.W;
+            const float yh = ((float)v - g.cy) * g.inv_fy;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!((sel[j] >> (8 * i)) & 1u)) continue;
+                const float d = comp(D[j], i);
+                float dx, dy;
+                if (FAST) {
+                    const float4 f = i < 2 ? F0[j] : F1[j];
+                    dx = __fdiv_rn((i & 1) ? f.z : f.x, g.scale);
+                    dy = __fdiv_rn((i & 1) ? f.w : f.y, g.scale);
+                } else {
+                    const int u = u0 + i;
+                    const float2 f = load_flow(fbase, g.flow_s16, (long long)(v / g.grid) * g.Wf + (u / g.grid), g.scale);
+                    dx = f.x;
+                    dy = f.y;
+                }
+                // hpp:252 gates
+                if (!(flow_valid(dx, dy) && d > 0.f && (double)d < g.max_depth)) continue;
+                const float xh = ((float)(u0 + i) - g.cx) * g.inv_fx;
+                const float ia = __fdiv_rn(1.0f, d);
+                const float l1[5] = {ia, -xh * ia, -xh * yh, 1.0f + xh * xh, -yh};
+                const float l2[5] = {ia, -yh * ia, -(1.0f + yh * yh), xh * yh, xh};
+                const float p1 = l1[0] * x[0] + l1[1] * x[2] + l1[2] * x[3] + l1[3] * x[4] + l1[4] * x[5];
+                const float p2 = l2[0] * x[1] + l2[1] * x[2] + l2[2] * x[3] + l2[3] * x[4] + l2[4] * x[5];
+                const float n1 = dx - c1 * p1, n2 = dy - c2 * p2;
+                const float nr = sqrtf(n1 * n1 + n2 * n2);
+                if (PASS == 0) {
+                    nrm[4 * j + i] = nr;
+                    vmask |= 1u << (4 * j + i);
+                } else {
+                    float l = 1.0f;
+                    if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
+                    float w1[5], w2[5];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        w1[k] = l * l1[k];
+                        w2[k] = l * l2[k];
+                    }
+                    int o = 0;
+#pragma unroll
+                    for (int r = 0; r < 5; ++r)
+#pragma unroll
+                        for (int s = r; s < 5; ++s) {
+                            acc[o] = fmaf(w1[r], l1[s], acc[o]);
+                            acc[15 + o] = fmaf(w2[r], l2[s], acc[15 + o]);
+                            ++o;
+                        }
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        acc[30 + k] = fmaf(w1[k], dx, acc[30 + k]);
+                        acc[35 + k] = fmaf(w2[k], dy, acc[35 + k]);
+                    }
+                    acc[40] += 1.0f;
+                }
+            }
+        }
+
+        if (PASS == 0) {
+            // warp-aggregated append of the valid norms (order is irrelevant for the order statistics)
+            int total = 0;
+            uint32_t ball[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                ball[k] = __ballot_sync(0xffffffffu, (vmask >> k) & 1u);
+                total += __popc(ball[k]);
+            }
+            if (total) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(a.norm_count + t, (unsigned)total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                float* out = a.norms + (long long)t * g.HW;
+                const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if ((vmask >> k) & 1u) out[base + __popc(ball[k] & lt)] = nrm[k];
+                    base += __popc(ball[k]);
+                }
+            }
+        }
+    }
+
+    if (PASS == 1) {
+        __shared__ float red[kThreads / 32][kNAcc];
+#pragma unroll
+        for (int i = 0; i < kNAcc; ++i) {
+            const float s = warp_sum(acc[i]);
+            if (lane == 0) red[warp][i] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < kNAcc) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) s += (double)red[w][threadIdx.x];
+            a.partials[((long long)t * a.max_blocks + blockIdx.x) * kNAcc + threadIdx.x] = s;
+        }
+    }
+}
+
+// ---- exact radix select of the upper median + Laplacian parameters ---------------------------
+__global__ void k_sel_init(int n_tracks, const uint32_t* __restrict__ norm_count, SelState* __restrict__ sel,
+                           const VelCtl* __restrict__ ctl) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tracks) return;
+    SelState s;
+    s.prefix = 0;
+    s.n = ctl[t].enable ? norm_count[t] : 0u;
+    s.k = s.n >> 1;
+    s.pad = 0;
+    s.less_cnt = 0;
+    s.less_sum = 0.0;
+    s.total_sum = 0.0;
+    s.less_max_bits = 0;
+    s.pad2 = 0;
+    sel[t] = s;
+}
+
+template <int LEVEL>
+__global__ void __launch_bounds__(kThreads) k_sel_hist(const float* __restrict__ norms, int HW, const SelState* __restrict__ sel,
+                                                      uint32_t* __restrict__ hist) {
+    const int t = blockIdx.y;
+    const uint32_t n = sel[t].n;
+    const uint32_t prefix = sel[t].prefix;
+    const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = blockIdx.x * per;
+    if (lo >= n) return;
+    const uint32_t hi = min(n, lo + per);
+    constexpr int NB = LEVEL == 2 ? 256 : kSelBins;
+    __shared__ uint32_t h[NB];
+    for (int i = threadIdx.x; i < NB; i += kThreads) h[i] = 0;
+    __syncthreads();
+    const uint32_t* keys = reinterpret_cast<const uint32_t*>(norms + (long long)t * HW);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kThreads) {
+        const uint32_t key = keys[i];
+        if (LEVEL == 0) {
+            atomicAdd(&h[key >> 20], 1u);
+        } else if (LEVEL == 1) {
+            if ((key >> 20) == (prefix >> 20)) atomicAdd(&h[(key >> 8) & 0xfffu], 1u);
+        } else {
+            if ((key >> 8) == (prefix >> 8)) atomicAdd(&h[key & 0xffu], 1u);
+        }
+    }
+    __syncthreads();
+    uint32_t* gh = hist + (long long)t * kSelBins;
+    for (int i = threadIdx.x; i < NB; i += kThreads)
+        if (h[i]) atomicAdd(gh + i, h[i]);
+}
+
+template <int LEVEL>
+__global__ void __launch_bounds__(kThreads) k_sel_scan(SelState* __restrict__ sel, uint32_t* __restrict__ hist) {
+    const int t = blockIdx.x;
+    SelState& s = sel[t];
+    if (s.n == 0) return;
+    constexpr int NB = LEVEL == 2 ? 256 : kSelBins;
+    constexpr int PER = NB / kThreads;
+    __shared__ uint32_t sh[kThreads / 32];
+    uint32_t* gh = hist + (long long)t * kSelBins;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t loc[PER];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        loc[i] = gh[threadIdx.x * PER + i];
+        gh[threadIdx.x * PER + i] = 0;
+        sum += loc[i];
+    }
+    const uint32_t incl = (uint32_t)warp_scan_incl((int)sum, lane);
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; ++w) woff += sh[w];
+    uint32_t before = woff + incl - sum;
+    const uint32_t k = s.k;
+    __syncthreads();
+    if (k >= before && k < before + sum) {  // exactly one thread
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            if (k < before + loc[i]) {
+                const uint32_t bin = threadIdx.x * PER + i;
+                s.prefix |= LEVEL == 0 ? bin << 20 : LEVEL == 1 ? bin << 8 : bin;
+                s.k = k - before;
+                break;
+            }
+            before += loc[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_sel_stats(const float* __restrict__ norms, int HW, SelState* __restrict__ sel) {
+    const int t = blockIdx.y;
+    const uint32_t n = sel[t].n;
+    const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+    const uint32_t lo = blockIdx.x * per;
+    if (lo >= n) return;
+    const uint32_t hi = min(n, lo + per);
+    const float v1 = __uint_as_float(sel[t].prefix);
+    const float* p = norms + (long long)t * HW;
+    double tot = 0.0, ls = 0.0;
+    unsigned lc = 0;
+    float lm = 0.f;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += kThreads) {
+        const float v = p[i];
+        tot += (double)v;
+        if (v < v1) {
+            ls += (double)v;
+            ++lc;
+            lm = fmaxf(lm, v);
+        }
+    }
+    tot = warp_sum(tot);
+    ls = warp_sum(ls);
+    lc = (unsigned)warp_sum((int)lc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lm = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, o));
+    __shared__ double s_tot[kThreads / 32], s_ls[kThreads / 32];
+    __shared__ unsigned s_lc[kThreads / 32];
+    __shared__ float s_lm[kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_tot[warp] = tot;
+        s_ls[warp] = ls;
+        s_lc[warp] = lc;
+        s_lm[warp] = lm;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kThreads / 32; ++w) {
+            tot += s_tot[w];
+            ls += s_ls[w];
+            lc += s_lc[w];
+            lm = fmaxf(lm, s_lm[w]);
+        }
+        atomicAdd(&sel[t].total_sum, tot);
+        atomicAdd(&sel[t].less_sum, ls);
+        atomicAdd(&sel[t].less_cnt, (unsigned long long)lc);
+        atomicMax(&sel[t].less_max_bits, __float_as_uint(lm));
+    }
+}
+
+__global__ void k_sel_final(int n_tracks, const SelState* __restrict__ sel, WeightParams* __restrict__ wp) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tracks) return;
+    const SelState s = sel[t];
+    WeightParams w;
+    w.m = 0.f;
+    w.inv_b = 0.f;
+    w.coef = 0.f;
+    w.inv_lmax = 1.f;
+    w.use = 0;
+    w.n = (int32_t)s.n;
+    w.pad[0] = w.pad[1] = 0;
+    if (s.n > 0) {
+        // SKFCorrection.cpp:95-102: median (even: mean of the two middle values), b = mean |n - m|
+        const double n = (double)s.n;
+        const double k1 = (double)(s.n >> 1);
+        const double v1 = (double)__uint_as_float(s.prefix);
+        const double lower = (s.less_cnt == (unsigned long long)(s.n >> 1)) ? (double)__uint_as_float(s.less_max_bits) : v1;
+        const bool even = (s.n & 1u) == 0u;
+        const double m = even ? 0.5 * (lower + v1) : v1;
+        const double s_below = s.less_sum + (k1 - (double)s.less_cnt) * v1;  // sum of the k1 smallest
+        const double s_above = s.total_sum - s_below;
+        const double b = ((s_above - (n - k1) * m) + (k1 * m - s_below)) / n;
+        if (b > 1e-4) {  // SKFCorrection.cpp:106
+            const double dmin = even ? 0.5 * (v1 - lower) : 0.0;
+            const double lmax = fmax(exp(-dmin / b) / (2.0 * b), 1e-6);
+            w.m = (float)m;
+            w.inv_b = (float)(1.0 / b);
+            w.coef = (float)(1.0 / (2.0 * b));
+            w.inv_lmax = (float)(1.0 / lmax);
+            w.use = 1;
+        }
+    }
+    wp[t] = w;
+}
+
+// ---- per-track epilogue: FP64 reduction of the block partials, 6x6 solve, gate, publish ------------
+__device__ void chol6_inverse(const double* A, double* Ainv) {
+    // A symmetric positive definite 6x6 (row-major) -> Ainv. Cholesky A = L L^T, then invert.
+    double L[36];
+    for (int i = 0; i < 36; ++i) L[i] = 0.0;
+    for (int j = 0; j < 6; ++j) {
+        double s = A[j * 6 + j];
+        for (int k = 0; k < j; ++k) s -= L[j * 6 + k] * L[j * 6 + k];
+        const double d = sqrt(s);
+        L[j * 6 + j] = d;
+        for (int i = j + 1; i < 6; ++i) {
+            double v = A[i * 6 + j];
+            for (int k = 0; k < j; ++k) v -= L[i * 6 + k] * L[j * 6 + k];
+            L[i * 6 + j] = v / d;
+        }
+    }
+    // Linv (lower)
+    double Li[36];
+    for (int i = 0; i < 36; ++i) Li[i] = 0.0;
+    for (int c = 0; c < 6; ++c) {
+        Li[c * 6 + c] = 1.0 / L[c * 6 + c];
+        for (int i = c + 1; i < 6; ++i) {
+            double v = 0.0;
+            for (int k = c; k < i; ++k) v -= L[i * 6 + k] * Li[k * 6 + c];
+            Li[i * 6 + c] = v / L[i * 6 + i];
+        }
+    }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+            double v = 0.0;
+            for (int k = (i > j ? i : j); k < 6; ++k) v += Li[k * 6 + i] * Li[k * 6 + j];
+            Ainv[i * 6 + j] = v;
+        }
+}
+
+struct EpiArgs {
+    int n_tracks;
+    const VelCtl* ctl;
+    const double* partials; int max_blocks; int n_blocks;
+    double* v_mean; double* v_cov; const double* q_diag;
+    double r0, r1, fx, fy;
+    double* vel_hist; int hist_ring;
+    int32_t* out_count; double* out_lambda; double* out_eta;
+    uint32_t* norm_count;
+    int update_state;
+};
+
+__global__ void __launch_bounds__(32) k_vel_epilogue(EpiArgs a) {
+    const int t = blockIdx.x;
+    const int lane = threadIdx.x;
+    const VelCtl c = a.ctl[t];
+    __shared__ double sums[kNAcc];
+    if (c.enable) {
+        for (int i = lane; i < kNAcc; i += 32) {
+            double s = 0.0;
+            const double* p = a.partials + (long long)t * a.max_blocks * kNAcc + i;
+            for (int b = 0; b < a.n_blocks; ++b) s += p[(long long)b * kNAcc];
+            sums[i] = s;
+        }
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    if (a.norm_count) a.norm_count[t] = 0;
+    double* x = a.v_mean + (long long)t * 6;
+    double* P = a.v_cov + (long long)t * 36;
+    int count = 0;
+    if (c.enable) {
+        const int i1[5] = {0, 2, 3, 4, 5}, i2[5] = {1, 2, 3, 4, 5};
+        const double k1 = (a.fx * c.dt) * (a.fx * c.dt) / a.r0, k2 = (a.fy * c.dt) * (a.fy * c.dt) / a.r1;
+        const double e1 = (a.fx * c.dt) / a.r0, e2 = (a.fy * c.dt) / a.r1;
+        double Lm[36], eta[6];
+        for (int i = 0; i < 36; ++i) Lm[i] = 0.0;
+        for (int i = 0; i < 6; ++i) eta[i] = 0.0;
+        int o = 0;
+        for (int r = 0; r < 5; ++r)
+            for (int s = r; s < 5; ++s) {
+                const double v1 = k1 * sums[o], v2 = k2 * sums[15 + o];
+                Lm[i1[r] * 6 + i1[s]] += v1;
+                if (r != s) Lm[i1[s] * 6 + i1[r]] += v1;
+                Lm[i2[r] * 6 + i2[s]] += v2;
+                if (r != s) Lm[i2[s] * 6 + i2[r]] += v2;
+                ++o;
+            }
+        for (int k = 0; k < 5; ++k) {
+            eta[i1[k]] += e1 * sums[30 + k];
+            eta[i2[k]] += e2 * sums[35 + k];
+        }
+        count = (int)(sums[40] + 0.5);
+        if (a.out_lambda)
+            for (int i = 0; i < 36; ++i) a.out_lambda[(long long)t * 36 + i] = Lm[i];
+        if (a.out_eta)
+            for (int i = 0; i < 6; ++i) a.out_eta[(long long)t * 6 + i] = eta[i];
+        // ROFTFilter.cpp:294-301: fewer than 3 valid pixels (or an empty measurement, SKFCorrection.cpp:60-68 keeps
+        // the PREDICTED state, which the observability gate then reverts) -> the belief is left untouched.
+        if (a.update_state && count >= 3) {
+            double Pp[36], Pinv[36], Lam[36], Pn[36], rhs[6];
+            for (int i = 0; i < 36; ++i) Pp[i] = P[i];
+            for (int i = 0; i < 6; ++i) Pp[i * 6 + i] += a.q_diag[i];  // KFPrediction: P + Q, F = I
+            chol6_inverse(Pp, Pinv);
+            for (int i = 0; i < 36; ++i) Lam[i] = Pinv[i] + Lm[i];
+            chol6_inverse(Lam, Pn);
+            for (int i = 0; i < 6; ++i) {
+                double v = eta[i];
+                for (int j = 0; j < 6; ++j) v += Pinv[i * 6 + j] * x[j];
+                rhs[i] = v;
+            }
+            double xn[6];
+            for (int i = 0; i < 6; ++i) {
+                double v = 0.0;
+                for (int j = 0; j < 6; ++j) v += Pn[i * 6 + j] * rhs[j];
+                xn[i] = v;
+            }
+            for (int i = 0; i < 6; ++i) x[i] = xn[i];
+            for (int i = 0; i < 36; ++i) P[i] = Pn[i];
+        }
+    } else {
+        if (a.out_lambda)
+            for (int i = 0; i < 36; ++i) a.out_lambda[(long long)t * 36 + i] = 0.0;
+        if (a.out_eta)
+            for (int i = 0; i < 6; ++i) a.out_eta[(long long)t * 6 + i] = 0.0;
+    }
+    if (a.out_count) a.out_count[t] = count;
+    // velocity_->set_twist(v_corr_belief_.mean()) every frame (ROFTFilter.cpp:305)
+    if (a.vel_hist && c.hist_slot >= 0) {
+        double* h = a.vel_hist + ((long long)t * a.hist_ring + c.hist_slot) * 6;
+        for (int i = 0; i < 6; ++i) h[i] = x[i];
+    }
+}
+
+}  // namespace
+
+int launch_mask_rank(const uint8_t* seg, long long seg_stride, int thr, int HW, int n_items, int32_t* wt_count, int32_t* total,
+                     const VelCtl* ctl, cudaStream_t s) {
+    const int n_warp_tiles = (HW + kWarpTilePx - 1) / kWarpTilePx;
+    const int n_block_tiles = (HW + kBlockTilePx - 1) / kBlockTilePx;
+    ROFTB_LAUNCH(k_mask_count, dim3(min(n_block_tiles, 64), n_items), kThreads, 0, s, seg, seg_stride, thr, HW, n_warp_tiles,
+                 wt_count, ctl);
+    ROFTB_LAUNCH(k_wt_scan, n_items, kThreads, 0, s, wt_count, n_warp_tiles, total, ctl);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_wt_scan(int32_t* wt_count, int n_warp_tiles, int n_items, int32_t* total, cudaStream_t s) {
+    ROFTB_LAUNCH(k_wt_scan, n_items, kThreads, 0, s, wt_count, n_warp_tiles, total, (const VelCtl*)nullptr);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
+    const int T = a.n_tracks;
+    const Geom& g = a.g;
+    const int n_warp_tiles = (g.HW + kWarpTilePx - 1) / kWarpTilePx;
+    const int n_block_tiles = (g.HW + kBlockTilePx - 1) / kBlockTilePx;
+    // blocks per track: fill the machine (>= ~6 CTAs per SM in total) but amortise the block reduction
+    int bpt = max(1, (148 * 6 + T - 1) / T);
+    bpt = min(bpt, min(n_block_tiles, a.max_blocks));
+    const int tpb = (n_block_tiles + bpt - 1) / bpt;
+    bpt = (n_block_tiles + tpb - 1) / tpb;
+
+    if (g.stride > 1) launch_mask_rank(a.seg, a.seg_stride, a.thr, g.HW, T, a.wt_count, nullptr, a.ctl, s);
+    PassArgs pa;
+    pa.g = g;
+    pa.ft = a.ft;
+    pa.seg = a.seg;
+    pa.seg_stride = a.seg_stride;
+    pa.thr = a.thr;
+    pa.ctl = a.ctl;
+    pa.tiles_per_block = tpb;
+    pa.n_block_tiles = n_block_tiles;
+    pa.n_warp_tiles = n_warp_tiles;
+    pa.wt_prefix = a.wt_count;
+    pa.norms = a.norms;
+    pa.norm_count = a.norm_count;
+    pa.wp = a.wp;
+    pa.weight_flow = a.weight_flow;
+    pa.x_pred = a.x_pred_override ? a.x_pred_override : a.v_mean;
+    pa.x_stride = 6;
+    pa.partials = a.partials;
+    pa.max_blocks = a.max_blocks;
+    pa.fx = a.fx;
+    pa.fy = a.fy;
+    const bool fast = (!g.flow_s16 && g.grid == 1);
+    if (a.weight_flow) {
+        if (fast)
+            ROFTB_LAUNCH((k_flow_pass<0, true>), dim3(bpt, T), kThreads, 0, s, pa);
+        else
+            ROFTB_LAUNCH((k_flow_pass<0, false>), dim3(bpt, T), kThreads, 0, s, pa);
+        ROFTB_LAUNCH(k_sel_init, (T + 127) / 128, 128, 0, s, T, a.norm_count, a.sel, a.ctl);
+        // enough blocks per track to spread the list, few enough that the per-block histogram flush stays cheap
+        int sb = max(1, min(32, (148 * 4 + T - 1) / T));
+        ROFTB_LAUNCH(k_sel_hist<0>, dim3(sb, T), kThreads, 0, s, a.norms, g.HW, a.sel, a.hist);
+        ROFTB_LAUNCH(k_sel_scan<0>, T, kThreads, 0, s, a.sel, a.hist);
+        ROFTB_LAUNCH(k_sel_hist<1>, dim3(sb, T), kThreads, 0, s, a.norms, g.HW, a.sel, a.hist);
+        ROFTB_LAUNCH(k_sel_scan<1>, T, kThreads, 0, s, a.sel, a.hist);
+        ROFTB_LAUNCH(k_sel_hist<2>, dim3(sb, T), kThreads, 0, s, a.norms, g.HW, a.sel, a.hist);
+        ROFTB_LAUNCH(k_sel_scan<2>, T, kThreads, 0, s, a.sel, a.hist);
+        ROFTB_LAUNCH(k_sel_stats, dim3(sb, T), kThreads, 0, s, a.norms, g.HW, a.sel);
+        ROFTB_LAUNCH(k_sel_final, (T + 127) / 128, 128, 0, s, T, a.sel, a.wp);
+    }
+    if (fast)
+        ROFTB_LAUNCH((k_flow_pass<1, true>), dim3(bpt, T), kThreads, 0, s, pa);
+    else
+        ROFTB_LAUNCH((k_flow_pass<1, false>), dim3(bpt, T), kThreads, 0, s, pa);
+    EpiArgs e;
+    e.n_tracks = T;
+    e.ctl = a.ctl;
+    e.partials = a.partials;
+    e.max_blocks = a.max_blocks;
+    e.n_blocks = bpt;
+    e.v_mean = a.v_mean;
+    e.v_cov = a.v_cov;
+    e.q_diag = a.q_diag;
+    e.r0 = a.r_flow[0];
+    e.r1 = a.r_flow[1];
+    e.fx = a.fx;
+    e.fy = a.fy;
+    e.vel_hist = a.vel_hist;
+    e.hist_ring = a.hist_ring;
+    e.out_count = a.out_count;
+    e.out_lambda = a.out_lambda;
+    e.out_eta = a.out_eta;
+    e.norm_count = a.weight_flow ? a.norm_count : nullptr;
+    e.update_state = a.update_state;
+    ROFTB_LAUNCH(k_vel_epilogue, T, 32, 0, s, e);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace roftb

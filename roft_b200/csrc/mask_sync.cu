@@ -1,0 +1,305 @@
+// Flow-aided mask synchronisation, batched over tracks (north-star part 2).
+//
+// Replaces ImageSegmentationOFAidedSource<T>::step_frame / map + cv::remap
+// (src/roft-lib/include/ROFT/ImageSegmentationOFAidedSource.hpp:128-281) and the cv::threshold of
+// ImageSegmentationMeasurement::freeze (src/roft-lib/src/ImageSegmentationMeasurement.cpp:61-65).
+//
+// The reference builds a float inverse map by forward-scattering every non-zero mask pixel through the
+// buffered flow frames (last writer in row-major source order wins) and then gathers with cv::remap;
+// unmapped destinations sample source pixel (0,0).  Here:
+//   k_mask_stats   non-zero count / min / max of a newly delivered mask (emptiness + single-valuedness)
+//   k_warp_plan    per-track decision of hpp:169-226 that depends on the mask CONTENT (empty new mask)
+//                  and the per-track flow buffer bookkeeping - kept on the device so the host never syncs
+//   k_warp_init    destination plane <- default value (or identity copy), winner plane <- -1
+//   k_warp_scatter integer scatter: single-valued masks store the value byte directly (any writer wins
+//                  the same value); mixed-valued masks resolve collisions with atomicMax(source index)
+//   k_warp_gather  mixed-valued masks only: out(dst) = src(winner(dst))
+// All arithmetic on the chased position is IEEE FP32 add/div with x86 float->int truncation semantics
+// (cvt_int) so the result is bit-exact against the reference + OpenCV.
+#include "roftb_internal.cuh"
+
+namespace roftb {
+
+long long g_launch_count = 0;
+
+namespace {
+
+__device__ __forceinline__ const uint8_t* track_plane(const uint8_t* base, long long stride, int t) {
+    return base + (long long)t * stride;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_mask_stats(const uint8_t* __restrict__ new_mask, long long new_stride,
+                                                        const WarpCtl* __restrict__ ctl, int n16,
+                                                        MaskStat* __restrict__ stat) {
+    const int t = blockIdx.y;
+    if (!ctl[t].has_new) return;
+    const uint4* p = reinterpret_cast<const uint4*>(track_plane(new_mask, new_stride, t));
+    int nnz = 0;
+    uint32_t vmin = 0xffffffffu, vmax = 0u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) {
+        uint4 w = ld_nc_u4(p + i);
+        uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t nz = __vcmpne4(ws[k], 0u);
+            nnz += __popc(nz) >> 3;
+            vmin = __vminu4(vmin, ws[k] | ~nz);
+            vmax = __vmaxu4(vmax, ws[k]);
+        }
+    }
+    int mn = min(min(vmin & 0xff, (vmin >> 8) & 0xff), min((vmin >> 16) & 0xff, vmin >> 24));
+    int mx = max(max(vmax & 0xff, (vmax >> 8) & 0xff), max((vmax >> 16) & 0xff, vmax >> 24));
+    nnz = warp_sum(nnz);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0 && nnz > 0) {
+        atomicAdd(&stat[t].nnz, nnz);
+        atomicMin(&stat[t].vmin, mn);
+        atomicMax(&stat[t].vmax, mx);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_warp_plan(int n_tracks, const WarpCtl* __restrict__ ctl, MaskStat* __restrict__ stat,
+                            WarpPlan* __restrict__ plan, FlowBuf* __restrict__ fbuf, const uint8_t* __restrict__ new_mask,
+                            long long new_stride, const uint8_t* __restrict__ state_src, int HW, int segm_delay) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tracks) return;
+    const WarpCtl c = ctl[t];
+    MaskStat st = stat[t];
+    stat[t] = MaskStat{0, 255, 0, 0};
+    FlowBuf fb = fbuf[t];
+    WarpPlan p;
+    p.mode = kWarpCopyState;
+    p.src_new = 0;
+    p.zero_origin = 0;
+    p.n_flows = 0;
+    for (int i = 0; i < kMaxFlows; ++i) p.flow_slot[i] = 0;
+    p.uniform_val = fb.uniform_val;
+    p.dflt = 0;
+    p.pad[0] = p.pad[1] = 0;
+    if (c.reset) fb.n = 0;
+    const int new_uniform = (st.nnz > 0 && st.vmin == st.vmax) ? st.vmin : 0;
+
+    if (!c.flow_aided) {
+        // plain source: the delivered mask simply replaces the state
+        if (c.has_new) {
+            p.mode = kWarpCopyNew;
+            fb.uniform_val = new_uniform;
+        }
+    } else {
+        bool valid_seg = c.has_new != 0;
+        bool init_now = false;
+        if (valid_seg && c.first_mask) {  // hpp:169-178: initialisation, not treated as a new mask
+            init_now = true;
+            valid_seg = false;
+            fb.uniform_val = new_uniform;
+        }
+        if (valid_seg && st.nnz == 0) {  // hpp:186-197: uninformative mask is skipped
+            valid_seg = false;
+            if (segm_delay <= 0) fb.n = 0;
+        }
+        if (c.flow_valid) {  // hpp:200-209: flow_buffer_.push_back
+            if (fb.n == kMaxFlows) {
+                for (int i = 1; i < kMaxFlows; ++i) fb.slot[i - 1] = fb.slot[i];
+                fb.n = kMaxFlows - 1;
+            }
+            fb.slot[fb.n++] = c.cur_slot;
+        }
+        if (valid_seg) {  // hpp:211-219: new mask through the last D buffered flows
+            int start = 0;
+            if (segm_delay > 0) start = max(0, fb.n - segm_delay);
+            p.mode = kWarpScatter;
+            p.src_new = 1;
+            p.zero_origin = 0;
+            p.n_flows = fb.n - start;
+            for (int i = start; i < fb.n; ++i) p.flow_slot[i - start] = fb.slot[i];
+            fb.n = 0;
+            fb.uniform_val = new_uniform;
+            p.uniform_val = new_uniform;
+            p.dflt = track_plane(new_mask, new_stride, t)[0];
+        } else if (c.flow_valid) {  // hpp:221-226: propagate with the current flow only
+            p.mode = kWarpScatter;
+            p.src_new = init_now ? 1 : 0;
+            p.zero_origin = 1;
+            p.n_flows = 1;
+            p.flow_slot[0] = c.cur_slot;
+            p.uniform_val = fb.uniform_val;
+            p.dflt = 0;
+        } else if (init_now) {
+            p.mode = kWarpCopyNew;
+        }
+    }
+    plan[t] = p;
+    fbuf[t] = fb;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_warp_init(const WarpPlan* __restrict__ plan, const uint8_t* __restrict__ new_mask,
+                                                       long long new_stride, const uint8_t* __restrict__ state_src,
+                                                       uint8_t* __restrict__ state_dst, int32_t* __restrict__ winner,
+                                                       int HW) {
+    const int t = blockIdx.y;
+    const WarpPlan p = plan[t];
+    const int n16 = HW >> 4;
+    uint4* dst = reinterpret_cast<uint4*>(state_dst + (long long)t * HW);
+    if (p.mode == kWarpScatter) {
+        const uint32_t b = (uint32_t)p.dflt * 0x01010101u;
+        const uint4 fill = make_uint4(b, b, b, b);
+        const bool general = (p.uniform_val == 0);
+        int4* win = reinterpret_cast<int4*>(winner + (long long)t * HW);
+        const int4 neg = make_int4(-1, -1, -1, -1);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) {
+            if (!general) {
+                dst[i] = fill;
+            } else {
+                win[4 * i + 0] = neg;
+                win[4 * i + 1] = neg;
+                win[4 * i + 2] = neg;
+                win[4 * i + 3] = neg;
+            }
+        }
+    } else {
+        const uint4* src = reinterpret_cast<const uint4*>(
+            p.mode == kWarpCopyNew ? track_plane(new_mask, new_stride, t) : state_src + (long long)t * HW);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = ld_nc_u4(src + i);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chase one source pixel through the flow chain (hpp:249-278). Returns the destination linear index or -1.
+__device__ __forceinline__ int chase(const Geom& g, const FrameTable& ft, const WarpPlan& p, int t, int u, int v) {
+    float tx = (float)u, ty = (float)v;
+    const float gs = (float)g.grid;
+    for (int j = 0; j < p.n_flows; ++j) {
+        const int ix = cvt_int(tx), iy = cvt_int(ty);
+        if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) return -1;
+        const int fr = cvt_int(__fdiv_rn(ty, gs));
+        const int fc = cvt_int(__fdiv_rn(tx, gs));
+        const int slot = p.flow_slot[j];
+        const char* base = reinterpret_cast<const char*>(ft.flow[slot]) +
+                           (long long)t * ft.flow_stride * (g.flow_s16 ? 2 : 4);
+        const float2 f = load_flow(base, g.flow_s16, (long long)fr * g.Wf + fc, g.scale);
+        tx = __fadd_rn(tx, f.x);
+        ty = __fadd_rn(ty, f.y);
+    }
+    const int ix = cvt_int(tx), iy = cvt_int(ty);
+    if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) return -1;
+    return iy * g.W + ix;
+}
+
+__global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft, const WarpPlan* __restrict__ plan,
+                                                          const uint8_t* __restrict__ new_mask, long long new_stride,
+                                                          const uint8_t* __restrict__ state_src,
+                                                          uint8_t* __restrict__ state_dst, int32_t* __restrict__ winner) {
+    const int t = blockIdx.y;
+    __shared__ WarpPlan sp;
+    if (threadIdx.x == 0) sp = plan[t];
+    __syncthreads();
+    if (sp.mode != kWarpScatter) return;
+    const uint8_t* src = sp.src_new ? track_plane(new_mask, new_stride, t) : state_src + (long long)t * g.HW;
+    uint8_t* dst = state_dst + (long long)t * g.HW;
+    int32_t* win = winner + (long long)t * g.HW;
+    const int nq = g.HW >> 2;
+    const uint8_t uval = (uint8_t)sp.uniform_val;
+    const bool general = (sp.uniform_val == 0);
+    // one quad (4 px, one 32-bit word) per lane per iteration: fully coalesced mask reads
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        uint32_t m = ld_nc_u32(reinterpret_cast<const uint32_t*>(src) + q);
+        if (sp.zero_origin && q == 0) m &= 0xffffff00u;
+        if (m == 0u) continue;
+        const int px = q << 2;
+        const int v = px / g.W;
+        const int u0 = px - v * g.W;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (((m >> (8 * i)) & 0xffu) == 0u) continue;
+            const int d = chase(g, ft, sp, t, u0 + i, v);
+            if (d < 0) continue;
+            if (general)
+                atomicMax(win + d, px + i);
+            else
+                dst[d] = uval;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_warp_gather(const WarpPlan* __restrict__ plan, const uint8_t* __restrict__ new_mask,
+                                                         long long new_stride, const uint8_t* __restrict__ state_src,
+                                                         uint8_t* __restrict__ state_dst, const int32_t* __restrict__ winner,
+                                                         int HW) {
+    const int t = blockIdx.y;
+    const WarpPlan p = plan[t];
+    if (p.mode != kWarpScatter || p.uniform_val != 0) return;
+    const uint8_t* src = p.src_new ? track_plane(new_mask, new_stride, t) : state_src + (long long)t * HW;
+    const int4* win = reinterpret_cast<const int4*>(winner + (long long)t * HW);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(state_dst + (long long)t * HW);
+    const int nq = HW >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const int4 w = win[q];
+        const int ws[4] = {w.x, w.y, w.z, w.w};
+        uint32_t out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            // the zeroed origin of the "no new mask" branch can never be a winner: it is not a source
+            uint32_t b = ws[i] >= 0 ? (uint32_t)src[ws[i]] : (uint32_t)p.dflt;
+            out |= b << (8 * i);
+        }
+        dst[q] = out;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_threshold(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        uint4 w = src[i];
+        // cv::threshold(.., 1, 255, THRESH_BINARY): v > 1 ? 255 : 0
+        w.x = __vcmpgtu4(w.x, 0x01010101u);
+        w.y = __vcmpgtu4(w.y, 0x01010101u);
+        w.z = __vcmpgtu4(w.z, 0x01010101u);
+        w.w = __vcmpgtu4(w.w, 0x01010101u);
+        dst[i] = w;
+    }
+}
+
+}  // namespace
+
+int launch_mask_sync(const MaskSyncArgs& a, cudaStream_t s, bool planned) {
+    const int T = a.n_tracks;
+    const int HW = a.g.HW;
+    const int n16 = HW >> 4;
+    const int nq = HW >> 2;
+    // enough blocks per track to fill the machine at small T, few enough to keep launch tails short at large T
+    int bx = (n16 + kThreads - 1) / kThreads;
+    int target = max(1, (148 * 8 + T - 1) / T);
+    bx = max(1, min(bx, target));
+    if (!planned) {
+        if (a.new_mask) ROFTB_LAUNCH(k_mask_stats, dim3(bx, T), kThreads, 0, s, a.new_mask, a.new_stride, a.ctl, n16, a.stat);
+        ROFTB_LAUNCH(k_warp_plan, (T + 127) / 128, 128, 0, s, T, a.ctl, a.stat, a.plan, a.fbuf, a.new_mask, a.new_stride,
+                     a.state_src, HW, a.segm_delay);
+    }
+    ROFTB_LAUNCH(k_warp_init, dim3(bx, T), kThreads, 0, s, a.plan, a.new_mask, a.new_stride, a.state_src, a.state_dst,
+                 a.winner, HW);
+    int bq = (nq + kThreads - 1) / kThreads;
+    int targetq = max(1, (148 * 16 + T - 1) / T);
+    bq = max(1, min(bq, targetq));
+    ROFTB_LAUNCH(k_warp_scatter, dim3(bq, T), kThreads, 0, s, a.g, a.ft, a.plan, a.new_mask, a.new_stride, a.state_src,
+                 a.state_dst, a.winner);
+    ROFTB_LAUNCH(k_warp_gather, dim3(bq, T), kThreads, 0, s, a.plan, a.new_mask, a.new_stride, a.state_src, a.state_dst,
+                 a.winner, HW);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_threshold(const uint8_t* src, uint8_t* dst, size_t n, cudaStream_t s) {
+    size_t n16 = n >> 4;
+    size_t nb = (n16 + kThreads - 1) / kThreads;
+    int bx = nb > (size_t)(148 * 8) ? 148 * 8 : (int)nb;
+    ROFTB_LAUNCH(k_threshold, max(bx, 1), kThreads, 0, s, reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), n16);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace roftb

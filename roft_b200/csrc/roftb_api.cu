@@ -1,0 +1,919 @@
+// C ABI of libroft_b200.so (include/roft_b200.h): context, the batched ROFTFilter loop and the
+// stateless operators.  Host-side logic here is the part of the reference that is pure control flow:
+//   ROFTFilter::filtering_step sequencing                 src/roft-lib/src/ROFTFilter.cpp:255-367
+//   ImageSegmentationOFAidedSource::step_frame (the content-independent part)   ...OFAidedSource.hpp:128-231
+//   ImageOpticalFlowMeasurement::freeze early-outs        ...ImageOpticalFlowMeasurement.hpp:184-229
+//   CartesianQuaternionMeasurement::freeze mode machine   src/roft-lib/src/CartesianQuaternionMeasurement.cpp:92-348
+// Everything value-dependent (empty masks, observability, the filters) runs on the device, so a step
+// never synchronises with the GPU.
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "roftb_internal.cuh"
+
+using namespace roftb;
+
+namespace {
+
+std::string g_create_error;
+constexpr int kCtlRing = 8;    // in-flight per-step control blocks
+constexpr int kHistRing = 16;  // velocity history ring (> ROFTB_MAX_DELAY + 3)
+
+struct PoseMeasHost {          // CartesianQuaternionMeasurement state (.h:98-140), values replaced by slots
+    std::deque<int> buffer;    // buffer_velocities_ as velocity-history slots
+    bool is_pose = false;
+    bool is_first_velocity_in = false;
+    int last_vel_slot = -1;
+    double last_pose[7] = {0, 0, 0, 1, 0, 0, 0};
+    int mtype = ROFTB_MEAS_NONE;
+    int meas_vel_slot = -1;    // velocity part of the current measurement_
+};
+
+struct TrackHost {
+    bool seg_src_available = false;   // ImageSegmentationOFAidedSource::segmentation_available_
+    bool of_first_frame = true;       // ImageSegmentationOFAidedSource::is_first_frame_
+    bool segmeas_available = false;   // ImageSegmentationMeasurement::segmentation_available_
+    bool fm_first_frame = true;       // ImageOpticalFlowMeasurement::is_first_frame_
+    int prev_slot = -1;               // frame slot of previous_depth_
+    PoseMeasHost pm;
+};
+
+}  // namespace
+
+struct roftb_ctx {
+    roftb_config cfg;
+    Geom g;
+    int T = 0;
+    size_t HW = 0;
+    size_t flow_elems = 0;  // scalar elements per track
+    int dev = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    std::string err;
+    long long launches0 = 0;
+
+    // device state
+    uint8_t* mask_state[2] = {nullptr, nullptr};
+    int mask_cur = 0;
+    int32_t* winner = nullptr;
+    float* norms = nullptr;
+    uint32_t* norm_count = nullptr;
+    uint32_t* hist = nullptr;
+    SelState* sel = nullptr;
+    WeightParams* wp = nullptr;
+    double* partials = nullptr;
+    int max_blocks = 0;
+    int32_t* wt_count = nullptr;
+    int32_t* wt_count2 = nullptr;
+    int n_warp_tiles = 0;
+    MaskStat* stat = nullptr;
+    WarpPlan* plan = nullptr;
+    FlowBuf* fbuf = nullptr;
+    double *v_mean = nullptr, *v_cov = nullptr, *p_mean = nullptr, *p_cov = nullptr, *pb_mean = nullptr, *pb_cov = nullptr;
+    double* vel_hist = nullptr;
+    double* q_diag = nullptr;
+    int32_t* d_count = nullptr;
+    double *d_lambda = nullptr, *d_eta = nullptr;
+    UkfParams ukf_p;
+
+    // per-step control blocks: pinned host ring + one device copy
+    WarpCtl* h_wctl = nullptr; VelCtl* h_vctl = nullptr; UkfOp* h_ops = nullptr; int32_t* h_nops = nullptr;
+    WarpCtl* d_wctl = nullptr; VelCtl* d_vctl = nullptr; UkfOp* d_ops = nullptr; int32_t* d_nops = nullptr;
+    cudaEvent_t ctl_event[kCtlRing];
+    bool ctl_event_used[kCtlRing];
+
+    // frames
+    FrameTable ft;
+    long long frame_idx = 0;
+    std::vector<TrackHost> th;
+    // host-path staging ring (lazily allocated)
+    float* stage_depth = nullptr; void* stage_flow = nullptr; uint8_t* stage_mask = nullptr;
+    cudaEvent_t copy_done = nullptr;
+    uint8_t* thr_tmp = nullptr;
+};
+
+namespace {
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);               \
+            return -1;                                                                    \
+        }                                                                                 \
+    } while (0)
+
+int fail(roftb_ctx* ctx, const char* msg) {
+    ctx->err = msg;
+    return -2;
+}
+
+template <class T>
+cudaError_t dalloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
+    return e;
+}
+
+size_t flow_scalar_bytes(const roftb_ctx* ctx) { return ctx->g.flow_s16 ? 2 : 4; }
+
+int check_geom(const roftb_config& c, std::string& err) {
+    if (c.n_tracks <= 0) { err = "n_tracks must be > 0"; return -2; }
+    if (c.width <= 0 || c.height <= 0 || (c.width % 4) != 0 || ((long long)c.width * c.height) % 16 != 0) {
+        err = "width must be a multiple of 4 and width*height a multiple of 16"; return -2;
+    }
+    if (c.flow_format != ROFTB_FLOW_F32 && c.flow_format != ROFTB_FLOW_S16) { err = "unknown flow_format"; return -2; }
+    if (c.flow_grid <= 0 || c.width / c.flow_grid <= 0 || c.height / c.flow_grid <= 0) { err = "bad flow_grid"; return -2; }
+    if (!(c.flow_scale > 0.f)) { err = "flow_scale must be > 0"; return -2; }
+    if (c.subsampling_radius < 1) { err = "subsampling_radius must be >= 1"; return -2; }
+    if (c.segm_delay > ROFTB_MAX_DELAY || c.pose_delay > ROFTB_MAX_DELAY) { err = "delay exceeds ROFTB_MAX_DELAY"; return -2; }
+    if (!(c.fx > 0) || !(c.fy > 0)) { err = "fx, fy must be > 0"; return -2; }
+    return 0;
+}
+
+void fill_geom(roftb_ctx* ctx) {
+    const roftb_config& c = ctx->cfg;
+    Geom& g = ctx->g;
+    g.W = c.width; g.H = c.height; g.HW = c.width * c.height;
+    g.grid = c.flow_grid;
+    // DatasetImageOpticalFlow.cpp:46: grid = width / cols  =>  cols = ceil-free width / grid for exact multiples
+    g.Wf = c.width / c.flow_grid; g.Hf = c.height / c.flow_grid;
+    g.flow_s16 = c.flow_format == ROFTB_FLOW_S16;
+    g.scale = c.flow_scale;
+    g.cx = (float)c.cx; g.cy = (float)c.cy;
+    g.inv_fx = (float)(1.0 / c.fx); g.inv_fy = (float)(1.0 / c.fy);
+    g.max_depth = c.depth_maximum;
+    g.stride = c.subsampling_radius;
+}
+
+}  // namespace
+
+extern "C" {
+
+int roftb_version(void) { return ROFTB_VERSION; }
+
+void roftb_config_default(roftb_config* c) {
+    // config/config_fast_ycb.cfg
+    memset(c, 0, sizeof(*c));
+    c->n_tracks = 1;
+    c->width = 1280; c->height = 720;
+    c->fx = 1229.4285612615463; c->fy = 1229.4285612615463; c->cx = 640.0; c->cy = 360.0;
+    c->sample_time = 0.033333333333;
+    c->flow_format = ROFTB_FLOW_F32; c->flow_grid = 1; c->flow_scale = 1.0f;
+    c->cov_flow[0] = c->cov_flow[1] = 1.0;
+    c->depth_maximum = 2.0;
+    c->subsampling_radius = 35;
+    c->weight_flow = 1;
+    for (int i = 0; i < 6; ++i) { c->v_sigma[i] = 0.1; c->v_cov0[i] = 1e-3; }
+    for (int i = 0; i < 3; ++i) {
+        c->p_sigma_linear[i] = 1.0; c->p_sigma_angular[i] = 1.0;
+        c->cov_v[i] = 0.1; c->cov_w[i] = 1e-4; c->cov_x[i] = 1e-3; c->cov_q[i] = 1e-4;
+    }
+    for (int i = 0; i < 12; ++i) c->p_cov0[i] = 1e-3;
+    c->ut_alpha = 1.0; c->ut_beta = 2.0; c->ut_kappa = 0.0;
+    c->use_pose = 1; c->use_pose_resync = 1; c->use_velocity = 1; c->flow_aided = 1;
+    c->segm_delay = 6; c->pose_delay = 6;
+    c->device = 0;
+}
+
+const char* roftb_last_error(const roftb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int64_t roftb_kernel_launches(const roftb_ctx* ctx) { return ctx ? (int64_t)(g_launch_count - ctx->launches0) : 0; }
+
+void* roftb_stream(roftb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return -2; }
+    *out = nullptr;
+    std::string err;
+    if (check_geom(*cfg, err)) { g_create_error = err; return -2; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                         " (roft_b200 has no CPU fallback)";
+        return -1;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return -2; }
+    roftb_ctx* ctx = new roftb_ctx();
+    ctx->cfg = *cfg;
+    ctx->T = cfg->n_tracks;
+    ctx->dev = cfg->device;
+    fill_geom(ctx);
+    ctx->HW = (size_t)ctx->g.HW;
+    ctx->flow_elems = (size_t)ctx->g.Wf * ctx->g.Hf * 2;
+    ctx->launches0 = g_launch_count;
+    for (int i = 0; i < kCtlRing; ++i) ctx->ctl_event_used[i] = false;
+    memset(&ctx->ft, 0, sizeof(ctx->ft));
+    ctx->th.assign(ctx->T, TrackHost());
+    const int T = ctx->T;
+    const size_t HW = ctx->HW;
+    ctx->n_warp_tiles = (int)((HW + kWarpTilePx - 1) / kWarpTilePx);
+    const int n_block_tiles = (int)((HW + kBlockTilePx - 1) / kBlockTilePx);
+    ctx->max_blocks = n_block_tiles;
+#define CKC(call)                                                              \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) {                                              \
+            g_create_error = std::string(#call) + ": " + cudaGetErrorString(e__); \
+            roftb_destroy(ctx);                                                \
+            return -1;                                                         \
+        }                                                                      \
+    } while (0)
+    CKC(cudaSetDevice(ctx->dev));
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+    for (int i = 0; i < kCtlRing; ++i) CKC(cudaEventCreateWithFlags(&ctx->ctl_event[i], cudaEventDisableTiming));
+    CKC(dalloc(&ctx->mask_state[0], T * HW));
+    CKC(dalloc(&ctx->mask_state[1], T * HW));
+    CKC(dalloc(&ctx->winner, T * HW));
+    CKC(dalloc(&ctx->norms, T * HW));
+    CKC(dalloc(&ctx->norm_count, (size_t)T));
+    CKC(dalloc(&ctx->hist, (size_t)T * kSelBins));
+    CKC(dalloc(&ctx->sel, (size_t)T));
+    CKC(dalloc(&ctx->wp, (size_t)T));
+    CKC(dalloc(&ctx->partials, (size_t)T * ctx->max_blocks * kNAcc));
+    CKC(dalloc(&ctx->wt_count, (size_t)T * ctx->n_warp_tiles));
+    CKC(dalloc(&ctx->wt_count2, (size_t)T * ctx->n_warp_tiles));
+    CKC(dalloc(&ctx->stat, (size_t)T));
+    CKC(dalloc(&ctx->plan, (size_t)T));
+    CKC(dalloc(&ctx->fbuf, (size_t)T));
+    CKC(dalloc(&ctx->v_mean, (size_t)T * 6));
+    CKC(dalloc(&ctx->v_cov, (size_t)T * 36));
+    CKC(dalloc(&ctx->p_mean, (size_t)T * 13));
+    CKC(dalloc(&ctx->p_cov, (size_t)T * 144));
+    CKC(dalloc(&ctx->pb_mean, (size_t)T * 13));
+    CKC(dalloc(&ctx->pb_cov, (size_t)T * 144));
+    CKC(dalloc(&ctx->vel_hist, (size_t)T * kHistRing * 6));
+    CKC(dalloc(&ctx->q_diag, (size_t)6));
+    CKC(dalloc(&ctx->d_count, (size_t)T));
+    CKC(dalloc(&ctx->d_lambda, (size_t)T * 36));
+    CKC(dalloc(&ctx->d_eta, (size_t)T * 6));
+    CKC(dalloc(&ctx->d_wctl, (size_t)T));
+    CKC(dalloc(&ctx->d_vctl, (size_t)T));
+    CKC(dalloc(&ctx->d_ops, (size_t)T * kMaxUkfOps));
+    CKC(dalloc(&ctx->d_nops, (size_t)T));
+    CKC(cudaMallocHost(&ctx->h_wctl, sizeof(WarpCtl) * T * kCtlRing));
+    CKC(cudaMallocHost(&ctx->h_vctl, sizeof(VelCtl) * T * kCtlRing));
+    CKC(cudaMallocHost(&ctx->h_ops, sizeof(UkfOp) * T * kMaxUkfOps * kCtlRing));
+    CKC(cudaMallocHost(&ctx->h_nops, sizeof(int32_t) * T * kCtlRing));
+    {
+        std::vector<MaskStat> st(T, MaskStat{0, 255, 0, 0});
+        CKC(cudaMemcpy(ctx->stat, st.data(), sizeof(MaskStat) * T, cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(ctx->q_diag, cfg->v_sigma, sizeof(double) * 6, cudaMemcpyHostToDevice));
+    }
+    UkfParams& p = ctx->ukf_p;
+    p.alpha = cfg->ut_alpha; p.beta = cfg->ut_beta; p.kappa = cfg->ut_kappa;
+    for (int i = 0; i < 3; ++i) {
+        p.psd_lin[i] = cfg->p_sigma_linear[i]; p.sigma_ang[i] = cfg->p_sigma_angular[i];
+        p.cov_v[i] = cfg->cov_v[i]; p.cov_w[i] = cfg->cov_w[i]; p.cov_x[i] = cfg->cov_x[i]; p.cov_q[i] = cfg->cov_q[i];
+    }
+#undef CKC
+    if (roftb_filter_init(ctx, nullptr, nullptr)) {
+        g_create_error = ctx->err;
+        roftb_destroy(ctx);
+        return -1;
+    }
+    *out = ctx;
+    return 0;
+}
+
+void roftb_destroy(roftb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->dev);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->winner, ctx->norms, ctx->norm_count, ctx->hist, ctx->sel,
+                     ctx->wp, ctx->partials, ctx->wt_count, ctx->wt_count2, ctx->stat, ctx->plan, ctx->fbuf, ctx->v_mean,
+                     ctx->v_cov, ctx->p_mean, ctx->p_cov, ctx->pb_mean, ctx->pb_cov, ctx->vel_hist, ctx->q_diag,
+                     ctx->d_count, ctx->d_lambda, ctx->d_eta, ctx->d_wctl, ctx->d_vctl, ctx->d_ops, ctx->d_nops,
+                     ctx->stage_depth, ctx->stage_flow, ctx->stage_mask, ctx->thr_tmp};
+    for (void* p : dptrs)
+        if (p) cudaFree(p);
+    if (ctx->h_wctl) cudaFreeHost(ctx->h_wctl);
+    if (ctx->h_vctl) cudaFreeHost(ctx->h_vctl);
+    if (ctx->h_ops) cudaFreeHost(ctx->h_ops);
+    if (ctx->h_nops) cudaFreeHost(ctx->h_nops);
+    for (int i = 0; i < kCtlRing; ++i)
+        if (ctx->ctl_event[i]) cudaEventDestroy(ctx->ctl_event[i]);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int roftb_sync(roftb_ctx* ctx) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mean0) {
+    if (!ctx) return -2;
+    const int T = ctx->T;
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // ROFTFilter::initialization_step (ROFTFilter.cpp:216-237)
+    std::vector<double> pm((size_t)T * 13, 0.0), pc((size_t)T * 144, 0.0), vm((size_t)T * 6, 0.0), vc((size_t)T * 36, 0.0);
+    for (int t = 0; t < T; ++t) {
+        if (p_mean0) memcpy(&pm[(size_t)t * 13], p_mean0 + (size_t)t * 13, sizeof(double) * 13);
+        else pm[(size_t)t * 13 + 9] = 1.0;
+        if (v_mean0) memcpy(&vm[(size_t)t * 6], v_mean0 + (size_t)t * 6, sizeof(double) * 6);
+        for (int i = 0; i < 12; ++i) pc[(size_t)t * 144 + i * 13] = ctx->cfg.p_cov0[i];
+        for (int i = 0; i < 6; ++i) vc[(size_t)t * 36 + i * 7] = ctx->cfg.v_cov0[i];
+    }
+    CK(cudaMemcpy(ctx->p_mean, pm.data(), pm.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->p_cov, pc.data(), pc.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->pb_mean, pm.data(), pm.size() * 8, cudaMemcpyHostToDevice));  // buffered_belief_ = p_corr_belief_
+    CK(cudaMemcpy(ctx->pb_cov, pc.data(), pc.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->v_mean, vm.data(), vm.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->v_cov, vc.data(), vc.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->vel_hist, 0, sizeof(double) * T * kHistRing * 6));
+    CK(cudaMemset(ctx->mask_state[0], 0, (size_t)T * ctx->HW));
+    CK(cudaMemset(ctx->mask_state[1], 0, (size_t)T * ctx->HW));
+    CK(cudaMemset(ctx->fbuf, 0, sizeof(FlowBuf) * T));
+    CK(cudaMemset(ctx->norm_count, 0, sizeof(uint32_t) * T));
+    CK(cudaMemset(ctx->d_count, 0, sizeof(int32_t) * T));
+    ctx->mask_cur = 0;
+    ctx->frame_idx = 0;
+    ctx->th.assign(T, TrackHost());  // segmentation_->reset() etc.
+    return 0;
+}
+
+// Stage host planes of this frame into the device ring; returns the device pointers.
+static int stage_host_frame(roftb_ctx* ctx, const roftb_frame* f, int slot, const float** d_depth, const void** d_flow,
+                            const uint8_t** d_mask) {
+    const size_t T = ctx->T, HW = ctx->HW;
+    const size_t fb = flow_scalar_bytes(ctx);
+    if (!ctx->stage_depth) {
+        CK(cudaMalloc(&ctx->stage_depth, sizeof(float) * T * HW * kFrameRing));
+        CK(cudaMalloc(&ctx->stage_flow, fb * T * ctx->flow_elems * kFrameRing));
+        CK(cudaMalloc(&ctx->stage_mask, T * HW));
+    }
+    float* dd = ctx->stage_depth + (size_t)slot * T * HW;
+    char* df = reinterpret_cast<char*>(ctx->stage_flow) + (size_t)slot * T * ctx->flow_elems * fb;
+    // the slot was last read kFrameRing steps ago on ctx->stream; copies run on the copy stream after that work
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done, 0));
+    for (size_t t = 0; t < T; ++t) {
+        CK(cudaMemcpyAsync(dd + t * HW, f->depth + t * f->depth_track_stride, sizeof(float) * HW, cudaMemcpyHostToDevice,
+                           ctx->copy_stream));
+        if (f->flow)
+            CK(cudaMemcpyAsync(df + t * ctx->flow_elems * fb,
+                               reinterpret_cast<const char*>(f->flow) + t * f->flow_track_stride * fb, ctx->flow_elems * fb,
+                               cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (f->mask && (!f->mask_valid || f->mask_valid[t]))
+            CK(cudaMemcpyAsync(ctx->stage_mask + t * HW, f->mask + t * f->mask_track_stride, HW, cudaMemcpyHostToDevice,
+                               ctx->copy_stream));
+    }
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    // the caller may reuse its host buffers as soon as this call returns
+    CK(cudaEventSynchronize(ev));
+    CK(cudaEventDestroy(ev));
+    *d_depth = dd;
+    *d_flow = f->flow ? df : nullptr;
+    *d_mask = f->mask ? ctx->stage_mask : nullptr;
+    return 0;
+}
+
+int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
+    if (!ctx || !f) return -2;
+    if (!f->depth) return fail(ctx, "roftb_filter_step: depth is required (ROFTFilter.cpp:261-266 tears down without it)");
+    const int T = ctx->T;
+    const roftb_config& cfg = ctx->cfg;
+    CK(cudaSetDevice(ctx->dev));
+    const int slot = (int)(ctx->frame_idx % kFrameRing);
+    const int hist_slot = (int)(ctx->frame_idx % kHistRing);
+    const int cslot = (int)(ctx->frame_idx % kCtlRing);
+
+    const float* d_depth = nullptr;
+    const void* d_flow = nullptr;
+    const uint8_t* d_mask = nullptr;
+    long long depth_stride, flow_stride, mask_stride;
+    if (f->memory == ROFTB_MEM_HOST) {
+        int rc = stage_host_frame(ctx, f, slot, &d_depth, &d_flow, &d_mask);
+        if (rc) return rc;
+        depth_stride = (long long)ctx->HW;
+        flow_stride = (long long)ctx->flow_elems;
+        mask_stride = (long long)ctx->HW;
+    } else {
+        d_depth = f->depth; d_flow = f->flow; d_mask = f->mask;
+        depth_stride = f->depth_track_stride; flow_stride = f->flow_track_stride; mask_stride = f->mask_track_stride;
+        if ((((uintptr_t)d_depth) & 15) || (depth_stride & 3) || (d_flow && ((((uintptr_t)d_flow) & 15) || (flow_stride & 7))) ||
+            (d_mask && ((((uintptr_t)d_mask) & 15) || (mask_stride & 15))))
+            return fail(ctx, "device planes must be 16-byte aligned with 16-byte aligned track strides");
+    }
+    if (ctx->frame_idx > 0 && (ctx->ft.depth_stride != depth_stride || (d_flow && ctx->ft.flow_stride && ctx->ft.flow_stride != flow_stride)))
+        return fail(ctx, "track strides must not change between frames");
+    ctx->ft.depth[slot] = d_depth;
+    ctx->ft.flow[slot] = d_flow;
+    ctx->ft.depth_stride = depth_stride;
+    if (d_flow) ctx->ft.flow_stride = flow_stride;
+
+    // ---- host state machines -> control blocks ------------------------------------------------
+    if (ctx->ctl_event_used[cslot]) CK(cudaEventSynchronize(ctx->ctl_event[cslot]));
+    WarpCtl* wc = ctx->h_wctl + (size_t)cslot * T;
+    VelCtl* vc = ctx->h_vctl + (size_t)cslot * T;
+    UkfOp* ops = ctx->h_ops + (size_t)cslot * T * kMaxUkfOps;
+    int32_t* nops = ctx->h_nops + (size_t)cslot * T;
+    bool any_new_mask = false, any_vel = false;
+    for (int t = 0; t < T; ++t) {
+        TrackHost& h = ctx->th[t];
+        const bool flow_in = d_flow && (!f->flow_valid || f->flow_valid[t]);
+        const bool mask_in = d_mask && (!f->mask_valid || f->mask_valid[t]);
+        const bool pose_in = f->pose && (!f->pose_valid || f->pose_valid[t]);
+        const double dt = f->dt ? f->dt[t] : cfg.sample_time;
+
+        // -- ImageSegmentationOFAidedSource::step_frame (hpp:128-231), content-independent part
+        WarpCtl& w = wc[t];
+        memset(&w, 0, sizeof(w));
+        w.flow_aided = cfg.flow_aided;
+        w.cur_slot = slot;
+        w.has_new = mask_in;
+        if (cfg.flow_aided) {
+            w.first_mask = mask_in && !h.seg_src_available;
+            if (mask_in) h.seg_src_available = true;
+            w.flow_valid = flow_in && !h.of_first_frame;
+            h.of_first_frame = false;
+            // ImageSegmentationMeasurement::freeze (cpp:56-68): new_segmentation_ = segmentation_available_
+            if (h.seg_src_available) h.segmeas_available = true;
+        } else {
+            if (mask_in) h.segmeas_available = true;
+        }
+        any_new_mask |= mask_in;
+
+        // -- ImageOpticalFlowMeasurement::freeze early-outs (hpp:184-229)
+        VelCtl& v = vc[t];
+        v.enable = 0;
+        v.prev_slot = h.prev_slot < 0 ? slot : h.prev_slot;
+        v.cur_slot = slot;
+        v.hist_slot = hist_slot;
+        v.dt = dt;
+        if (h.segmeas_available) {
+            if (!flow_in || h.fm_first_frame) {
+                h.fm_first_frame = false;
+            } else {
+                v.enable = 1;
+            }
+            h.prev_slot = slot;  // previous_depth_ = depth (hpp:222,286)
+        }
+        any_vel |= v.enable != 0;
+
+        // -- pose UKF sequencing (ROFTFilter.cpp:325-367) and CartesianQuaternionMeasurement::freeze
+        PoseMeasHost& pm = h.pm;
+        UkfOp* o = ops + (size_t)t * kMaxUkfOps;
+        int n = 0;
+        auto add_predict = [&]() {
+            memset(&o[n], 0, sizeof(UkfOp));
+            o[n].kind = kOpPredict;
+            o[n].dt = dt;
+            ++n;
+        };
+        auto add_correct = [&](int mtype, int vel_slot) {
+            memset(&o[n], 0, sizeof(UkfOp));
+            o[n].kind = kOpCorrect;
+            o[n].meas_type = mtype;
+            o[n].vel_slot = vel_slot;
+            for (int i = 0; i < 7; ++i) o[n].meas[6 + i] = pm.last_pose[i];
+            ++n;
+        };
+        // Standard freeze (.cpp:176-347)
+        if (cfg.use_velocity) {
+            pm.is_first_velocity_in = true;
+            pm.last_vel_slot = hist_slot;
+        }
+        pm.is_pose = false;
+        if (cfg.use_pose && pose_in) {
+            pm.is_pose = true;
+            memcpy(pm.last_pose, f->pose + (size_t)t * 7, sizeof(double) * 7);
+        }
+        bool valid_freeze = true;
+        if (pm.is_first_velocity_in && pm.is_pose) {
+            pm.mtype = ROFTB_MEAS_POSE_VELOCITY;
+            pm.meas_vel_slot = pm.last_vel_slot;
+            pm.buffer.push_back(pm.last_vel_slot);
+        } else if (pm.is_first_velocity_in) {
+            pm.mtype = ROFTB_MEAS_VELOCITY;
+            pm.meas_vel_slot = pm.last_vel_slot;
+            pm.buffer.push_back(pm.last_vel_slot);
+        } else if (pm.is_pose) {
+            pm.mtype = ROFTB_MEAS_POSE;
+        } else {
+            pm.mtype = ROFTB_MEAS_NONE;
+            valid_freeze = false;
+        }
+        // entries older than pose_delay + 1 are trimmed before any use (.cpp:100-104): cap the host mirror
+        while ((int)pm.buffer.size() > ROFTB_MAX_DELAY + 3) pm.buffer.pop_front();
+        if (!valid_freeze) {
+            add_predict();  // p_corr_belief_ = p_pred_belief_
+        } else if (pm.mtype == ROFTB_MEAS_POSE_VELOCITY && cfg.use_pose_resync) {
+            // ROFTFilter.cpp:331-354: rewind to the buffered belief and replay the buffered velocities
+            memset(&o[n], 0, sizeof(UkfOp));
+            o[n].kind = kOpSwapBuffered;
+            ++n;
+            for (;;) {
+                // PopBufferedMeasurement (.cpp:97-152)
+                if (cfg.pose_delay > 0)
+                    while ((int)pm.buffer.size() > cfg.pose_delay + 1) pm.buffer.pop_front();
+                if (pm.buffer.empty()) {
+                    pm.buffer.push_back(pm.meas_vel_slot);
+                    break;
+                }
+                const int vs = pm.buffer.front();
+                pm.buffer.pop_front();
+                pm.last_vel_slot = vs;
+                pm.meas_vel_slot = vs;
+                if (pm.is_pose) {
+                    pm.mtype = ROFTB_MEAS_POSE_VELOCITY;
+                    pm.is_pose = false;
+                } else {
+                    pm.mtype = ROFTB_MEAS_VELOCITY;
+                }
+                if (n + 2 > kMaxUkfOps) return fail(ctx, "UKF op list overflow");
+                add_predict();
+                add_correct(pm.mtype, vs);
+            }
+        } else {
+            add_predict();
+            add_correct(pm.mtype, pm.mtype == ROFTB_MEAS_POSE ? -1 : pm.last_vel_slot);
+        }
+        nops[t] = n;
+    }
+
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_wctl, wc, sizeof(WarpCtl) * T, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_vctl, vc, sizeof(VelCtl) * T, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_ops, ops, sizeof(UkfOp) * T * kMaxUkfOps, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_nops, nops, sizeof(int32_t) * T, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ctx->ctl_event[cslot], s));
+    ctx->ctl_event_used[cslot] = true;
+
+    // ---- device work: velocity (previous mask/depth, current flow), mask sync, pose UKF ---------
+    const uint8_t* seg_prev = ctx->mask_state[ctx->mask_cur];
+    uint8_t* seg_next = ctx->mask_state[ctx->mask_cur ^ 1];
+    {
+        VelocityArgs a;
+        memset(&a, 0, sizeof(a));
+        a.g = ctx->g; a.ft = ctx->ft; a.n_tracks = T;
+        a.seg = seg_prev; a.seg_stride = (long long)ctx->HW; a.thr = 1;  // cv::threshold(> 1) applied on load
+        a.ctl = ctx->d_vctl; a.weight_flow = cfg.weight_flow;
+        a.wt_count = ctx->wt_count; a.norms = ctx->norms; a.norm_count = ctx->norm_count; a.hist = ctx->hist;
+        a.sel = ctx->sel; a.wp = ctx->wp; a.partials = ctx->partials; a.max_blocks = ctx->max_blocks;
+        a.v_mean = ctx->v_mean; a.v_cov = ctx->v_cov; a.q_diag = ctx->q_diag;
+        a.r_flow[0] = cfg.cov_flow[0]; a.r_flow[1] = cfg.cov_flow[1];
+        a.fx = cfg.fx; a.fy = cfg.fy;
+        a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
+        a.out_count = ctx->d_count; a.out_lambda = ctx->d_lambda; a.out_eta = ctx->d_eta;
+        a.update_state = 1;
+        if (launch_velocity(a, s)) return fail(ctx, "launch_velocity failed");
+    }
+    {
+        MaskSyncArgs a;
+        memset(&a, 0, sizeof(a));
+        a.g = ctx->g; a.ft = ctx->ft; a.n_tracks = T;
+        a.new_mask = any_new_mask ? d_mask : nullptr; a.new_stride = mask_stride;
+        a.state_src = seg_prev; a.state_dst = seg_next; a.winner = ctx->winner;
+        a.ctl = ctx->d_wctl; a.stat = ctx->stat; a.plan = ctx->plan; a.fbuf = ctx->fbuf;
+        a.segm_delay = cfg.segm_delay;
+        if (launch_mask_sync(a, s)) return fail(ctx, "launch_mask_sync failed");
+        ctx->mask_cur ^= 1;
+    }
+    {
+        UkfArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n_tracks = T; a.p = ctx->ukf_p;
+        a.ops = ctx->d_ops; a.n_ops = ctx->d_nops; a.max_ops = kMaxUkfOps;
+        a.mean = ctx->p_mean; a.cov = ctx->p_cov; a.buf_mean = ctx->pb_mean; a.buf_cov = ctx->pb_cov;
+        a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
+        if (launch_ukf(a, s)) return fail(ctx, "launch_ukf failed");
+    }
+    if (f->memory == ROFTB_MEM_HOST) CK(cudaEventRecord(ctx->copy_done, s));
+    (void)any_vel;
+    ctx->frame_idx++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return -1; }
+    return 0;
+}
+
+int roftb_get_state(roftb_ctx* ctx, double* p_mean, double* p_cov, double* v_mean, double* v_cov) {
+    if (!ctx) return -2;
+    const size_t T = ctx->T;
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    if (p_mean) CK(cudaMemcpyAsync(p_mean, ctx->p_mean, T * 13 * 8, cudaMemcpyDeviceToHost, s));
+    if (p_cov) CK(cudaMemcpyAsync(p_cov, ctx->p_cov, T * 144 * 8, cudaMemcpyDeviceToHost, s));
+    if (v_mean) CK(cudaMemcpyAsync(v_mean, ctx->v_mean, T * 6 * 8, cudaMemcpyDeviceToHost, s));
+    if (v_cov) CK(cudaMemcpyAsync(v_cov, ctx->v_cov, T * 36 * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int roftb_get_mask(roftb_ctx* ctx, uint8_t* raw, uint8_t* thresholded) {
+    if (!ctx) return -2;
+    const size_t n = (size_t)ctx->T * ctx->HW;
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    const uint8_t* cur = ctx->mask_state[ctx->mask_cur];
+    if (raw) CK(cudaMemcpyAsync(raw, cur, n, cudaMemcpyDeviceToHost, s));
+    if (thresholded) {
+        if (!ctx->thr_tmp) CK(cudaMalloc(&ctx->thr_tmp, n));
+        if (launch_threshold(cur, ctx->thr_tmp, n, s)) return fail(ctx, "launch_threshold failed");
+        CK(cudaMemcpyAsync(thresholded, ctx->thr_tmp, n, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int roftb_get_velocity_info(roftb_ctx* ctx, int32_t* count, double* lambda, double* eta) {
+    if (!ctx) return -2;
+    const size_t T = ctx->T;
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    if (count) CK(cudaMemcpyAsync(count, ctx->d_count, T * 4, cudaMemcpyDeviceToHost, s));
+    if (lambda) CK(cudaMemcpyAsync(lambda, ctx->d_lambda, T * 36 * 8, cudaMemcpyDeviceToHost, s));
+    if (eta) CK(cudaMemcpyAsync(eta, ctx->d_eta, T * 6 * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// Stateless operators: host buffers in, host buffers out, through temporary device memory.
+// =============================================================================================
+namespace {
+
+struct TmpBuf {
+    std::vector<void*> ptrs;
+    ~TmpBuf() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <class T>
+    T* alloc(size_t n, bool zero = false) {
+        void* p = nullptr;
+        if (cudaMalloc(&p, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+        if (zero) cudaMemset(p, 0, (n ? n : 1) * sizeof(T));
+        ptrs.push_back(p);
+        return reinterpret_cast<T*>(p);
+    }
+    template <class T>
+    T* upload(const T* h, size_t n, cudaStream_t s) {
+        T* d = alloc<T>(n);
+        if (d && h) cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, s);
+        return d;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int roftb_mask_sync(roftb_ctx* ctx, int32_t n_masks, const uint8_t* mask, const void* flows, int32_t n_flows,
+                    int32_t zero_origin, uint8_t* out_raw, uint8_t* out_thr) {
+    if (!ctx || !mask || n_masks <= 0 || n_flows < 0 || n_flows > kMaxFlows || (n_flows > 0 && !flows))
+        return ctx ? fail(ctx, "roftb_mask_sync: bad argument") : -2;
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    const size_t HW = ctx->HW, N = n_masks;
+    const size_t fb = flow_scalar_bytes(ctx);
+    TmpBuf tb;
+    uint8_t* d_mask = tb.upload(mask, N * HW, s);
+    char* d_flows = n_flows ? tb.upload(reinterpret_cast<const char*>(flows), (size_t)n_flows * N * ctx->flow_elems * fb, s) : nullptr;
+    uint8_t* d_out = tb.alloc<uint8_t>(N * HW);
+    uint8_t* d_thr = tb.alloc<uint8_t>(N * HW);
+    int32_t* d_win = tb.alloc<int32_t>(N * HW);
+    std::vector<WarpPlan> plans(N);
+    for (size_t i = 0; i < N; ++i) {
+        // hpp:211-226 with the buffer given explicitly
+        const uint8_t* m = mask + i * HW;
+        WarpPlan& p = plans[i];
+        memset(&p, 0, sizeof(p));
+        p.mode = kWarpScatter;
+        p.src_new = 1;
+        p.zero_origin = zero_origin ? 1 : 0;
+        p.n_flows = n_flows;
+        for (int j = 0; j < n_flows; ++j) p.flow_slot[j] = j;
+        int vmin = 256, vmax = 0;
+        for (size_t k = (zero_origin ? 1 : 0); k < HW; ++k)
+            if (m[k]) { vmin = m[k] < vmin ? m[k] : vmin; vmax = m[k] > vmax ? m[k] : vmax; }
+        p.uniform_val = (vmax > 0 && vmin == vmax) ? vmin : 0;
+        p.dflt = zero_origin ? 0 : m[0];
+    }
+    WarpPlan* d_plan = tb.upload(plans.data(), N, s);
+    if (!d_mask || !d_out || !d_thr || !d_win || !d_plan || (n_flows && !d_flows)) return fail(ctx, "roftb_mask_sync: out of device memory");
+    MaskSyncArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = ctx->g; a.n_tracks = (int)N;
+    for (int j = 0; j < n_flows; ++j) a.ft.flow[j] = d_flows + (size_t)j * N * ctx->flow_elems * fb;
+    a.ft.flow_stride = (long long)ctx->flow_elems;
+    a.new_mask = d_mask; a.new_stride = (long long)HW;
+    a.state_src = d_mask; a.state_dst = d_out; a.winner = d_win; a.plan = d_plan;
+    if (launch_mask_sync(a, s, true)) return fail(ctx, "launch_mask_sync failed");
+    if (out_raw) CK(cudaMemcpyAsync(out_raw, d_out, N * HW, cudaMemcpyDeviceToHost, s));
+    if (out_thr) {
+        if (launch_threshold(d_out, d_thr, N * HW, s)) return fail(ctx, "launch_threshold failed");
+        CK(cudaMemcpyAsync(out_thr, d_thr, N * HW, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+static int velocity_operator(roftb_ctx* ctx, int32_t n, const uint8_t* mask, const float* depth, const void* flow,
+                             const double* x_pred, const double* dt, double* x, double* P, double* lambda, double* eta,
+                             int32_t* count, bool update) {
+    if (!ctx || n <= 0 || !mask || !depth || !flow) return ctx ? fail(ctx, "velocity operator: bad argument") : -2;
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    const size_t HW = ctx->HW, N = n;
+    const size_t fb = flow_scalar_bytes(ctx);
+    TmpBuf tb;
+    uint8_t* d_mask = tb.upload(mask, N * HW, s);
+    float* d_depth = tb.upload(depth, N * HW, s);
+    char* d_flow = tb.upload(reinterpret_cast<const char*>(flow), N * ctx->flow_elems * fb, s);
+    std::vector<VelCtl> ctl(N);
+    for (size_t i = 0; i < N; ++i) {
+        ctl[i].enable = 1; ctl[i].prev_slot = 0; ctl[i].cur_slot = 0; ctl[i].hist_slot = -1;
+        ctl[i].dt = dt ? dt[i] : ctx->cfg.sample_time;
+    }
+    VelCtl* d_ctl = tb.upload(ctl.data(), N, s);
+    std::vector<double> zeros(N * 36, 0.0);
+    double* d_x = tb.upload(x ? x : zeros.data(), N * 6, s);
+    double* d_P = tb.upload(P ? P : zeros.data(), N * 36, s);
+    double* d_xp = x_pred ? tb.upload(x_pred, N * 6, s) : nullptr;
+    const int nwt = ctx->n_warp_tiles;
+    VelocityArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = ctx->g; a.n_tracks = (int)N;
+    a.ft.depth[0] = d_depth; a.ft.flow[0] = d_flow;
+    a.ft.depth_stride = (long long)HW; a.ft.flow_stride = (long long)ctx->flow_elems;
+    a.seg = d_mask; a.seg_stride = (long long)HW; a.thr = 0;  // previous_segmentation_ is used through findNonZero
+    a.ctl = d_ctl; a.weight_flow = ctx->cfg.weight_flow;
+    a.wt_count = tb.alloc<int32_t>(N * nwt);
+    a.norms = tb.alloc<float>(N * HW);
+    a.norm_count = tb.alloc<uint32_t>(N, true);
+    a.hist = tb.alloc<uint32_t>(N * kSelBins, true);
+    a.sel = tb.alloc<SelState>(N, true);
+    a.wp = tb.alloc<WeightParams>(N, true);
+    a.max_blocks = ctx->max_blocks;
+    a.partials = tb.alloc<double>(N * a.max_blocks * kNAcc);
+    a.v_mean = d_x; a.v_cov = d_P; a.q_diag = ctx->q_diag;
+    a.r_flow[0] = ctx->cfg.cov_flow[0]; a.r_flow[1] = ctx->cfg.cov_flow[1];
+    a.fx = ctx->cfg.fx; a.fy = ctx->cfg.fy;
+    a.out_count = tb.alloc<int32_t>(N);
+    a.out_lambda = tb.alloc<double>(N * 36);
+    a.out_eta = tb.alloc<double>(N * 6);
+    a.update_state = update ? 1 : 0;
+    a.x_pred_override = d_xp;
+    if (!d_mask || !d_depth || !d_flow || !d_ctl || !d_x || !d_P || !a.wt_count || !a.norms || !a.norm_count || !a.hist ||
+        !a.sel || !a.wp || !a.partials || !a.out_count || !a.out_lambda || !a.out_eta)
+        return fail(ctx, "velocity operator: out of device memory");
+    if (launch_velocity(a, s)) return fail(ctx, "launch_velocity failed");
+    if (update && x) CK(cudaMemcpyAsync(x, d_x, N * 6 * 8, cudaMemcpyDeviceToHost, s));
+    if (update && P) CK(cudaMemcpyAsync(P, d_P, N * 36 * 8, cudaMemcpyDeviceToHost, s));
+    if (lambda) CK(cudaMemcpyAsync(lambda, a.out_lambda, N * 36 * 8, cudaMemcpyDeviceToHost, s));
+    if (eta) CK(cudaMemcpyAsync(eta, a.out_eta, N * 6 * 8, cudaMemcpyDeviceToHost, s));
+    if (count) CK(cudaMemcpyAsync(count, a.out_count, N * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int roftb_flow_velocity(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, const float* depth, const void* flow,
+                        const double* x_pred, const double* dt, double* lambda, double* eta, int32_t* count) {
+    return velocity_operator(ctx, n_items, mask, depth, flow, x_pred, dt, nullptr, nullptr, lambda, eta, count, false);
+}
+
+int roftb_velocity_kf(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, const float* depth, const void* flow,
+                      const double* dt, double* x, double* P, int32_t* count) {
+    if (!x || !P) return ctx ? fail(ctx, "roftb_velocity_kf: x and P are required") : -2;
+    return velocity_operator(ctx, n_items, mask, depth, flow, nullptr, dt, x, P, nullptr, nullptr, count, true);
+}
+
+static int ukf_operator(roftb_ctx* ctx, int32_t n, double* mean, double* cov, const std::vector<UkfOp>& ops) {
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    const size_t N = n;
+    TmpBuf tb;
+    double* d_mean = tb.upload(mean, N * 13, s);
+    double* d_cov = tb.upload(cov, N * 144, s);
+    UkfOp* d_ops = tb.upload(ops.data(), N, s);
+    std::vector<int32_t> nops(N, 1);
+    int32_t* d_nops = tb.upload(nops.data(), N, s);
+    if (!d_mean || !d_cov || !d_ops || !d_nops) return fail(ctx, "ukf operator: out of device memory");
+    UkfArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_tracks = n; a.p = ctx->ukf_p; a.ops = d_ops; a.n_ops = d_nops; a.max_ops = 1; a.mean = d_mean; a.cov = d_cov;
+    if (launch_ukf(a, s)) return fail(ctx, "launch_ukf failed");
+    CK(cudaMemcpyAsync(mean, d_mean, N * 13 * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(cov, d_cov, N * 144 * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int roftb_ukf_predict(roftb_ctx* ctx, int32_t n_items, double* mean, double* cov, const double* dt) {
+    if (!ctx || n_items <= 0 || !mean || !cov) return ctx ? fail(ctx, "roftb_ukf_predict: bad argument") : -2;
+    std::vector<UkfOp> ops(n_items);
+    for (int i = 0; i < n_items; ++i) {
+        memset(&ops[i], 0, sizeof(UkfOp));
+        ops[i].kind = kOpPredict;
+        ops[i].dt = dt ? dt[i] : ctx->cfg.sample_time;
+    }
+    return ukf_operator(ctx, n_items, mean, cov, ops);
+}
+
+int roftb_ukf_correct(roftb_ctx* ctx, int32_t n_items, double* mean, double* cov, const double* meas, const int32_t* meas_type) {
+    if (!ctx || n_items <= 0 || !mean || !cov || !meas || !meas_type) return ctx ? fail(ctx, "roftb_ukf_correct: bad argument") : -2;
+    std::vector<UkfOp> ops(n_items);
+    for (int i = 0; i < n_items; ++i) {
+        memset(&ops[i], 0, sizeof(UkfOp));
+        ops[i].kind = kOpCorrect;
+        ops[i].meas_type = meas_type[i];
+        ops[i].vel_slot = -1;
+        memcpy(ops[i].meas, meas + (size_t)i * 13, sizeof(double) * 13);
+    }
+    return ukf_operator(ctx, n_items, mean, cov, ops);
+}
+
+static void fill_select(roftb_ctx* ctx, SelectArgs& a, TmpBuf& tb, int32_t n, const uint8_t* mask, const float* depth,
+                        const void* flow, cudaStream_t s) {
+    const size_t HW = ctx->HW, N = n;
+    const size_t fb = flow_scalar_bytes(ctx);
+    memset(&a, 0, sizeof(a));
+    a.g = ctx->g; a.n_items = n;
+    a.mask = tb.upload(mask, N * HW, s); a.mask_stride = (long long)HW; a.thr = 0;
+    a.depth = tb.upload(depth, N * HW, s); a.depth_stride = (long long)HW;
+    a.flow = flow ? tb.upload(reinterpret_cast<const char*>(flow), N * ctx->flow_elems * fb, s) : nullptr;
+    a.flow_stride = (long long)ctx->flow_elems;
+    a.wt_count = tb.alloc<int32_t>(N * ctx->n_warp_tiles);
+    a.wt_count2 = tb.alloc<int32_t>(N * ctx->n_warp_tiles);
+}
+
+int roftb_flow_measurement_export(roftb_ctx* ctx, const uint8_t* mask, const float* depth, const void* flow, double dt,
+                                  int32_t capacity, double* z, double* H, int32_t* n_valid) {
+    if (!ctx || !mask || !depth || !flow || capacity < 0 || !n_valid) return ctx ? fail(ctx, "export: bad argument") : -2;
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    TmpBuf tb;
+    SelectArgs a;
+    fill_select(ctx, a, tb, 1, mask, depth, flow, s);
+    double* d_z = tb.alloc<double>((size_t)capacity * 2);
+    double* d_H = tb.alloc<double>((size_t)capacity * 12);
+    int32_t* d_n = tb.alloc<int32_t>(1, true);
+    if (!a.mask || !a.depth || !a.flow || !a.wt_count || !a.wt_count2 || !d_z || !d_H || !d_n) return fail(ctx, "export: out of device memory");
+    if (launch_export_measurement(a, dt, ctx->cfg.fx, ctx->cfg.fy, ctx->cfg.cx, ctx->cfg.cy, capacity, d_z, d_H, d_n, s)) return fail(ctx, "export launch failed");
+    CK(cudaMemcpyAsync(n_valid, d_n, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int nv = *n_valid < capacity ? *n_valid : capacity;
+    if (z && nv) CK(cudaMemcpy(z, d_z, (size_t)nv * 2 * 8, cudaMemcpyDeviceToHost));
+    if (H && nv) CK(cudaMemcpy(H, d_H, (size_t)nv * 12 * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int roftb_masked_points(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, const float* depth, double max_depth,
+                        int32_t capacity, double* points, int32_t* count) {
+    if (!ctx || n_items <= 0 || !mask || !depth || capacity < 0 || !count) return ctx ? fail(ctx, "masked_points: bad argument") : -2;
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    TmpBuf tb;
+    SelectArgs a;
+    fill_select(ctx, a, tb, n_items, mask, depth, nullptr, s);
+    double* d_pts = tb.alloc<double>((size_t)n_items * capacity * 3);
+    int32_t* d_n = tb.alloc<int32_t>(n_items, true);
+    if (!a.mask || !a.depth || !a.wt_count || !a.wt_count2 || !d_pts || !d_n) return fail(ctx, "masked_points: out of device memory");
+    if (launch_masked_points(a, max_depth, ctx->cfg.fx, ctx->cfg.fy, ctx->cfg.cx, ctx->cfg.cy, capacity, d_pts, d_n, s))
+        return fail(ctx, "masked_points launch failed");
+    CK(cudaMemcpyAsync(count, d_n, (size_t)n_items * 4, cudaMemcpyDeviceToHost, s));
+    if (points && capacity) CK(cudaMemcpyAsync(points, d_pts, (size_t)n_items * capacity * 3 * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int roftb_masked_depth_l1(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, const float* depth, const float* rendered,
+                          int32_t divider, double* err_sum, int32_t* samples) {
+    if (!ctx || n_items <= 0 || !mask || !depth || !rendered || divider <= 0 || !err_sum || !samples)
+        return ctx ? fail(ctx, "masked_depth_l1: bad argument") : -2;
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    TmpBuf tb;
+    SelectArgs a;
+    fill_select(ctx, a, tb, n_items, mask, depth, nullptr, s);
+    const size_t rsz = (size_t)(ctx->g.W / divider) * (ctx->g.H / divider);
+    float* d_r = tb.upload(rendered, (size_t)n_items * rsz, s);
+    double* d_e = tb.alloc<double>(n_items, true);
+    int32_t* d_n = tb.alloc<int32_t>(n_items, true);
+    if (!a.mask || !a.depth || !a.wt_count || !d_r || !d_e || !d_n) return fail(ctx, "masked_depth_l1: out of device memory");
+    if (launch_masked_depth_l1(a, d_r, (long long)rsz, divider, d_e, d_n, s)) return fail(ctx, "masked_depth_l1 launch failed");
+    CK(cudaMemcpyAsync(err_sum, d_e, (size_t)n_items * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(samples, d_n, (size_t)n_items * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // extern "C"

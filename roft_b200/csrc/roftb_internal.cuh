@@ -1,0 +1,281 @@
+// Internal declarations shared by the roft_b200 CUDA translation units (sm_100a).
+// Not part of the public ABI (include/roft_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "roft_b200.h"
+
+namespace roftb {
+
+constexpr int kMaxFlows = ROFTB_MAX_DELAY;   // longest flow chain a mask is warped through
+constexpr int kFrameRing = 16;               // device-side table of recent frames (> kMaxFlows)
+constexpr int kThreads = 256;                // streaming kernels: 8 warps
+constexpr int kWarpTilePx = 512;             // one warp covers 4 sub-tiles of 128 px (one quad per lane each)
+constexpr int kBlockTilePx = kThreads / 32 * kWarpTilePx;  // 4096 px
+// accumulators of the flow->velocity normal equations:
+//   S1 = sum l L1^T L1 over index set {0,2,3,4,5} (15 upper-triangular entries)
+//   S2 = sum l L2^T L2 over index set {1,2,3,4,5} (15)
+//   g1 = sum l L1^T dx (5), g2 = sum l L2^T dy (5), count (1)
+constexpr int kNAcc = 41;
+constexpr int kSelBins = 4096;               // radix-select histogram bins per level
+constexpr int kMaxUkfOps = 2 * (ROFTB_MAX_DELAY + 2) + 2;
+
+// ---- geometry / format of one batch of planes ----------------------------------------------
+struct Geom {
+    int W, H, HW;          // camera frame
+    int Wf, Hf;            // flow frame
+    int grid;              // W / Wf
+    int flow_s16;          // 1: short2 elements, 0: float2
+    float scale;           // flow scaling factor
+    float cx, cy, inv_fx, inv_fy;
+    double max_depth;      // depth gate (compared in double like the reference)
+    int stride;            // subsampling radius (>=1)
+};
+
+// table of the recent frames' device planes (passed to kernels by value)
+struct FrameTable {
+    const void* flow[kFrameRing];
+    const float* depth[kFrameRing];
+    long long flow_stride;   // scalar elements between tracks
+    long long depth_stride;  // elements between tracks
+};
+
+// ---- mask synchronisation -----------------------------------------------------------------
+struct WarpCtl {           // host-built, one per track per step
+    int32_t has_new;       // a (stale) mask is delivered to this track at this frame
+    int32_t first_mask;    // ... and it is the first one ever (initialisation, hpp:169-178)
+    int32_t flow_valid;    // flow available && !is_first_frame (hpp:200-204)
+    int32_t cur_slot;      // frame-ring slot of the current frame
+    int32_t flow_aided;    // 0: plain segmentation source (no warp)
+    int32_t reset;         // 1: forget the buffered flows first (source reset)
+    int32_t pad[2];
+};
+
+struct MaskStat { int32_t nnz, vmin, vmax, pad; };
+
+enum WarpMode : int32_t { kWarpCopyState = 0, kWarpCopyNew = 1, kWarpScatter = 2 };
+
+struct WarpPlan {          // device-resolved by k_warp_plan
+    int32_t mode;
+    int32_t src_new;       // scatter source: 1 = newly delivered mask, 0 = state mask
+    int32_t zero_origin;   // mask_(0,0) = 0 before findNonZero (hpp:224)
+    int32_t n_flows;
+    int32_t flow_slot[kMaxFlows];
+    int32_t uniform_val;   // >0: every non-zero source pixel has this value (byte-store fast path)
+    int32_t dflt;          // value sampled by unmapped destinations = src(0,0) (Q2)
+    int32_t pad[2];
+};
+
+struct FlowBuf {           // per-track device mirror of flow_buffer_ (hpp:82,208,218)
+    int32_t n;
+    int32_t slot[kMaxFlows];
+    int32_t uniform_val;   // single value of the current state mask (0 = mixed / unknown)
+    int32_t pad[2];
+};
+
+// ---- velocity filter ----------------------------------------------------------------------
+struct VelCtl {            // host-built, one per track per step
+    int32_t enable;        // data_in: segmentation available, flow valid, not first frame
+    int32_t prev_slot;     // frame-ring slot holding the previous depth
+    int32_t cur_slot;      // slot of the current flow
+    int32_t hist_slot;     // velocity-history ring slot to publish the twist to
+    double dt;
+};
+
+struct WeightParams {      // Laplacian re-weighting parameters (SKFCorrection.cpp:91-116)
+    float m, inv_b, coef, inv_lmax;
+    int32_t use;           // b > 1e-4
+    int32_t n;             // number of valid measurements
+    int32_t pad[2];
+};
+
+struct SelState {          // radix-select state (upper median = s[n/2])
+    uint32_t prefix;       // key bits fixed so far
+    uint32_t k;            // remaining rank inside the prefix
+    uint32_t n;
+    uint32_t pad;
+    // statistics gathered by the last pass
+    unsigned long long less_cnt;
+    double less_sum;
+    double total_sum;
+    uint32_t less_max_bits;
+    uint32_t pad2;
+};
+
+// ---- pose UKF -----------------------------------------------------------------------------
+enum UkfOpKind : int32_t { kOpPredict = 1, kOpCorrect = 2, kOpSwapBuffered = 3 };
+
+struct UkfOp {
+    int32_t kind;
+    int32_t meas_type;     // ROFTB_MEAS_* for kOpCorrect
+    int32_t vel_slot;      // velocity-history slot providing the (v, w) part, -1: use meas[0..5]
+    int32_t pad;
+    double dt;             // kOpPredict
+    double meas[13];       // (v, w, x, q) - pose part filled by the host
+};
+
+struct UkfParams {
+    double alpha, beta, kappa;
+    double psd_lin[3], sigma_ang[3];
+    double cov_v[3], cov_w[3], cov_x[3], cov_q[3];
+};
+
+// ---- launchers (defined in the .cu files) ---------------------------------------------------
+struct MaskSyncArgs {
+    Geom g;
+    FrameTable ft;
+    int n_tracks;
+    const uint8_t* new_mask; long long new_stride;   // may be null
+    const uint8_t* state_src; uint8_t* state_dst;    // [T][HW]
+    int32_t* winner;                                  // [T][HW]
+    const WarpCtl* ctl;                               // device
+    MaskStat* stat; WarpPlan* plan; FlowBuf* fbuf;    // device
+    int segm_delay;
+};
+// planned = true: a.plan was filled by the caller (operator mode), skip the stats / plan kernels
+int launch_mask_sync(const MaskSyncArgs& a, cudaStream_t s, bool planned = false);
+int launch_threshold(const uint8_t* src, uint8_t* dst, size_t n, cudaStream_t s);
+
+struct VelocityArgs {
+    Geom g;
+    FrameTable ft;
+    int n_tracks;
+    const uint8_t* seg; long long seg_stride; int thr;   // selected iff byte > thr
+    const VelCtl* ctl;                                    // device
+    int weight_flow;
+    // scratch
+    int32_t* wt_count;      // [T][n_warp_tiles] per-warp-tile mask counts / prefixes (stride > 1)
+    float* norms;           // [T][HW]
+    uint32_t* norm_count;   // [T]
+    uint32_t* hist;         // [T][kSelBins]
+    SelState* sel;          // [T]
+    WeightParams* wp;       // [T]
+    double* partials;       // [T][max_blocks][kNAcc]
+    int max_blocks;
+    // state
+    double* v_mean; double* v_cov;     // [T][6], [T][36]
+    const double* q_diag;              // [6] process noise (device)
+    double r_flow[2];
+    double fx, fy;
+    double* vel_hist; int hist_ring;   // [T][ring][6]
+    // diagnostics
+    int32_t* out_count; double* out_lambda; double* out_eta;  // device [T], [T][36], [T][6]
+    int update_state;                  // 0: only compute lambda/eta/count (operator mode)
+    const double* x_pred_override;     // operator mode: [T][6] predicted mean for the norms (else v_mean)
+};
+int launch_velocity(const VelocityArgs& a, cudaStream_t s);
+// per-warp-tile exclusive prefix of the number of pixels with byte > thr (row-major rank base); ctl may be null
+int launch_mask_rank(const uint8_t* seg, long long seg_stride, int thr, int HW, int n_items, int32_t* wt_count, int32_t* total,
+                     const VelCtl* ctl, cudaStream_t s);
+int launch_wt_scan(int32_t* wt_count, int n_warp_tiles, int n_items, int32_t* total, cudaStream_t s);
+
+struct UkfArgs {
+    int n_tracks;
+    UkfParams p;
+    const UkfOp* ops; const int32_t* n_ops; int max_ops;   // device [T][max_ops], [T]
+    double* mean; double* cov;                              // [T][13], [T][144]
+    double* buf_mean; double* buf_cov;                      // buffered belief (may be null)
+    const double* vel_hist; int hist_ring;                  // [T][ring][6] (may be null)
+};
+int launch_ukf(const UkfArgs& a, cudaStream_t s);
+
+struct SelectArgs {        // ordered compaction helpers (export / points / L1)
+    Geom g;
+    int n_items;
+    const uint8_t* mask; long long mask_stride; int thr;
+    const float* depth; long long depth_stride;
+    const void* flow; long long flow_stride;
+    int32_t* wt_count;     // [n][n_warp_tiles]
+    int32_t* wt_count2;    // [n][n_warp_tiles]
+};
+int launch_export_measurement(const SelectArgs& a, double dt, double fx, double fy, double cx, double cy, int capacity,
+                              double* z, double* H, int32_t* n_valid, cudaStream_t s);
+int launch_masked_points(const SelectArgs& a, double max_depth, double fx, double fy, double cx, double cy, int capacity,
+                         double* points, int32_t* count, cudaStream_t s);
+int launch_masked_depth_l1(const SelectArgs& a, const float* rendered, long long rendered_stride, int divider,
+                           double* err_sum, int32_t* samples, cudaStream_t s);
+
+// number of kernel launches issued through ROFTB_LAUNCH (for bench.py "gpu_launches")
+extern long long g_launch_count;
+
+}  // namespace roftb
+
+#define ROFTB_LAUNCH(kernel, grid, block, smem, stream, ...)            \
+    do {                                                                \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);     \
+        ++::roftb::g_launch_count;                                      \
+    } while (0)
+
+// ---- device helpers ---------------------------------------------------------------------------
+namespace roftb {
+
+// C `int(float)` as compiled for x86-64 (cvttss2si): truncation toward zero, NaN / overflow -> INT_MIN.
+__device__ __forceinline__ int cvt_int(float t) {
+    return (fabsf(t) < 2147483648.0f) ? (int)t : (int)0x80000000;
+}
+
+__device__ __forceinline__ uint32_t ld_nc_u32(const uint32_t* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ld_nc_u4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// one flow element (dx, dy) = float(f) / scale in FP32, as ImageOpticalFlowMeasurement.hpp:249-250
+__device__ __forceinline__ float2 load_flow(const void* base, int s16, long long idx, float scale) {
+    float2 f;
+    if (s16) {
+        short2 v = __ldg(reinterpret_cast<const short2*>(base) + idx);
+        f = make_float2((float)v.x, (float)v.y);
+    } else {
+        f = __ldg(reinterpret_cast<const float2*>(base) + idx);
+    }
+    f.x = __fdiv_rn(f.x, scale);
+    f.y = __fdiv_rn(f.y, scale);
+    return f;
+}
+
+// OpticalFlowUtilities.h:19-22
+__device__ __forceinline__ bool flow_valid(float dx, float dy) {
+    return !isnan(dx) && !isnan(dy) && fabsf(dx) < 1e9f && fabsf(dy) < 1e9f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// inclusive scan across the warp
+__device__ __forceinline__ int warp_scan_incl(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+}  // namespace roftb

@@ -1,0 +1,462 @@
+// Batched quaternion UKF over the 13-vector / 12-dof state (v, w, x, q): one warp per track, a small
+// per-track op list (predict / correct / swap-with-buffered-belief) per launch so that the pose
+// re-synchronisation replay of ROFTFilter.cpp:331-354 never returns to the host.
+//
+// Replaces
+//   bfl::UKFPrediction::predictStep through CartesianQuaternionModel::motion
+//        src/roft-lib/src/CartesianQuaternionModel.cpp:86-141           (43 sigma points)
+//   ROFT::UKFCorrection::correctStep   src/roft-lib/src/UKFCorrection.cpp:54-133
+//   CartesianQuaternionMeasurement::{predictedMeasure, innovation}
+//        src/roft-lib/src/CartesianQuaternionMeasurement.cpp:357-487     (37 / 49 sigma points)
+// and the bfl utilities they call (sigma_point, unscented_transform, mean_quaternion, diff_quaternion,
+// sum_quaternion_rotation_vector - UPSTREAM-RECALL).
+//
+// All arithmetic is FP64 (the work is a few KB per track; the kernel is latency-bound and is meant to
+// hide under the streaming kernels).  The covariance square root is the symmetric eigen-decomposition
+// A = U sqrt(S) by cyclic Jacobi with a relative rotation threshold (see DESIGN.md "UKF square root").
+#include "roftb_internal.cuh"
+
+namespace roftb {
+namespace {
+
+constexpr int kMaxSp = 49;
+constexpr double kJacobiRelTol = 1e-14;
+constexpr int kJacobiMaxSweeps = 24;
+
+struct UkfSmem {
+    double A[12][12];    // Jacobi work matrix
+    double V[12][12];    // eigenvectors
+    double AP[12][12];   // sqrt(c) * U sqrt(S) of the state covariance
+    double AN[12][12];   // same for the noise covariance
+    double P[12][12];    // covariance of the belief being processed
+    double mean[13];
+    double Y[kMaxSp][13];
+    double DX[kMaxSp][12];
+    double DY[kMaxSp][12];
+    double ymean[13];
+    double Py[12][24];   // [Py | I] for the Gauss-Jordan inverse
+    double Pxy[12][12];
+    double K[12][12];
+    double KPy[12][12];
+    double innov[12];
+    double Kn[12];
+};
+
+__device__ __forceinline__ void qmul(const double* a, const double* b, double* o) {
+    const double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    const double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    const double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+    const double z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+    o[0] = w; o[1] = x; o[2] = y; o[3] = z;
+}
+
+// rotation_vector_to_quaternion: |r| > 0 ? (cos(|r|/2), sin(|r|/2) r/|r|) : (1,0,0,0)
+__device__ __forceinline__ void rotvec_to_quat(const double* r, double* q) {
+    const double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    if (n > 0.0) {
+        double s, c;
+        sincos(0.5 * n, &s, &c);
+        const double k = s / n;
+        q[0] = c; q[1] = k * r[0]; q[2] = k * r[1]; q[3] = k * r[2];
+    } else {
+        q[0] = 1.0; q[1] = 0.0; q[2] = 0.0; q[3] = 0.0;
+    }
+}
+
+// diff_quaternion(a, b) = log(a (x) conj(b)) as a rotation vector, short way round
+__device__ __forceinline__ void quat_diff(const double* a, const double* b, double* r) {
+    const double bc[4] = {b[0], -b[1], -b[2], -b[3]};
+    double p[4];
+    qmul(a, bc, p);
+    if (p[0] < 0.0) { p[0] = -p[0]; p[1] = -p[1]; p[2] = -p[2]; p[3] = -p[3]; }
+    const double n = sqrt(p[1] * p[1] + p[2] * p[2] + p[3] * p[3]);
+    if (n > 0.0) {
+        const double k = 2.0 * acos(fmin(1.0, fmax(-1.0, p[0]))) / n;
+        r[0] = k * p[1]; r[1] = k * p[2]; r[2] = k * p[3];
+    } else {
+        r[0] = 0.0; r[1] = 0.0; r[2] = 0.0;
+    }
+}
+
+// Cyclic Jacobi on the n x n symmetric matrix in s.A (n <= 12); eigenvectors to s.V. Warp-cooperative.
+__device__ void jacobi_warp(UkfSmem& s, int n, int lane) {
+    for (int i = lane; i < 144; i += 32) s.V[i / 12][i % 12] = (i / 12 == i % 12) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < kJacobiMaxSweeps; ++sweep) {
+        bool rotated = false;
+        for (int p = 0; p < n - 1; ++p) {
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = s.A[p][q], app = s.A[p][p], aqq = s.A[q][q];
+                if (fabs(apq) <= kJacobiRelTol * sqrt(fabs(app * aqq))) continue;  // warp-uniform
+                rotated = true;
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double tt = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(tt * tt + 1.0);
+                const double sn = tt * c;
+                __syncwarp();
+                if (lane < n) {  // columns p, q
+                    const double akp = s.A[lane][p], akq = s.A[lane][q];
+                    s.A[lane][p] = c * akp - sn * akq;
+                    s.A[lane][q] = sn * akp + c * akq;
+                    const double vkp = s.V[lane][p], vkq = s.V[lane][q];
+                    s.V[lane][p] = c * vkp - sn * vkq;
+                    s.V[lane][q] = sn * vkp + c * vkq;
+                }
+                __syncwarp();
+                if (lane < n) {  // rows p, q
+                    const double apk = s.A[p][lane], aqk = s.A[q][lane];
+                    s.A[p][lane] = c * apk - sn * aqk;
+                    s.A[q][lane] = sn * apk + c * aqk;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    s.A[p][q] = 0.0;
+                    s.A[q][p] = 0.0;
+                }
+                __syncwarp();
+            }
+        }
+        if (!rotated) break;
+    }
+}
+
+// out = sc * U sqrt(max(S,0)) for the n x n matrix currently in s.A
+__device__ void cov_sqrt_warp(UkfSmem& s, int n, double sc, double (*out)[12], int lane) {
+    jacobi_warp(s, n, lane);
+    for (int i = lane; i < n * n; i += 32) {
+        const int r = i / n, c = i % n;
+        out[r][c] = sc * s.V[r][c] * sqrt(fmax(s.A[c][c], 0.0));
+    }
+    __syncwarp();
+}
+
+// dominant eigenvector of sum_i w_i q_i q_i^T over the quaternion columns Y[i][qoff..qoff+3]; sign fixed
+// against the first sigma point (see oracle/roft_oracle.py mean_quaternion)
+__device__ void mean_quaternion_warp(UkfSmem& s, int npts, int qoff, double wm0, double wi, double* out, int lane) {
+    if (lane < 10) {  // upper triangle, mirrored so the matrix is exactly symmetric
+        int r = 0, c = lane;
+        while (c >= 4 - r) { c -= 4 - r; ++r; }
+        c += r;
+        double m = 0.0;
+        for (int i = 0; i < npts; ++i) m += (i == 0 ? wm0 : wi) * (s.Y[i][qoff + r] * s.Y[i][qoff + c]);
+        s.A[r][c] = m;
+        s.A[c][r] = m;
+    }
+    __syncwarp();
+    jacobi_warp(s, 4, lane);
+    int best = 0;
+    for (int i = 1; i < 4; ++i)
+        if (s.A[i][i] > s.A[best][best]) best = i;
+    double q[4] = {s.V[0][best], s.V[1][best], s.V[2][best], s.V[3][best]};
+    double dot = 0.0, nn = 0.0;
+    for (int i = 0; i < 4; ++i) {
+        dot += q[i] * s.Y[0][qoff + i];
+        nn += q[i] * q[i];
+    }
+    const double k = (dot < 0.0 ? -1.0 : 1.0) / sqrt(nn);
+    for (int i = 0; i < 4; ++i) out[i] = k * q[i];
+    __syncwarp();
+}
+
+struct UtW { double wm0, wc0, wi, c; };
+__device__ __forceinline__ UtW ut_weights(int n, const UkfParams& p) {
+    UtW w;
+    const double lam = p.alpha * p.alpha * (n + p.kappa) - n;
+    w.wm0 = lam / (n + lam);
+    w.wc0 = lam / (n + lam) + (1.0 - p.alpha * p.alpha + p.beta);
+    w.wi = 1.0 / (2.0 * (n + lam));
+    w.c = n + lam;
+    return w;
+}
+
+// sigma point i of the augmented state: state part (lin[9], q[4]) and noise part nz[k]
+__device__ __forceinline__ void make_sigma_point(const UkfSmem& s, int i, int n, int k, double* lin, double* q, double* nz) {
+    double pert[12];
+    for (int r = 0; r < 12; ++r) pert[r] = 0.0;
+    for (int r = 0; r < k; ++r) nz[r] = 0.0;
+    if (i > 0) {
+        const int col = (i - 1) % n;
+        const double sg = (i - 1) < n ? 1.0 : -1.0;
+        if (col < 12) {
+            for (int r = 0; r < 12; ++r) pert[r] = sg * s.AP[r][col];
+        } else {
+            for (int r = 0; r < k; ++r) nz[r] = sg * s.AN[r][col - 12];
+        }
+    }
+    for (int r = 0; r < 9; ++r) lin[r] = s.mean[r] + pert[r];
+    double dq[4];
+    rotvec_to_quat(&pert[9], dq);
+    qmul(dq, &s.mean[9], q);
+}
+
+// ---- predict ----------------------------------------------------------------------------------
+__device__ void ukf_predict_warp(UkfSmem& s, const UkfParams& p, double T, int lane) {
+    const int k = 9, n = 21, npts = 43;
+    const UtW w = ut_weights(n, p);
+    const double sc = sqrt(w.c);
+    for (int i = lane; i < 144; i += 32) s.A[i / 12][i % 12] = s.P[i / 12][i % 12];
+    __syncwarp();
+    cov_sqrt_warp(s, 12, sc, s.AP, lane);
+    // Q(T), CartesianQuaternionModel.cpp:127-141
+    for (int i = lane; i < 144; i += 32) s.A[i / 12][i % 12] = 0.0;
+    __syncwarp();
+    if (lane < 3) {
+        s.A[lane][lane] = p.psd_lin[lane] * T;
+        s.A[3 + lane][3 + lane] = p.sigma_ang[lane];
+        s.A[6 + lane][6 + lane] = p.psd_lin[lane] * (pow(T, 3.0) / 3.0);
+        s.A[lane][6 + lane] = p.psd_lin[lane] * (pow(T, 2.0) / 2.0);
+        s.A[6 + lane][lane] = p.psd_lin[lane] * (pow(T, 2.0) / 2.0);
+    }
+    __syncwarp();
+    cov_sqrt_warp(s, k, sc, s.AN, lane);
+
+    for (int i = lane; i < npts; i += 32) {
+        double lin[9], q[4], nz[12];
+        make_sigma_point(s, i, n, k, lin, q, nz);
+        // CartesianQuaternionModel::motion (.cpp:86-124)
+        double* y = s.Y[i];
+        for (int r = 0; r < 9; ++r) y[r] = lin[r] + nz[r];
+        for (int r = 0; r < 3; ++r) y[6 + r] += lin[r] * T;
+        const double* wv = &lin[3];
+        const double nw = sqrt(wv[0] * wv[0] + wv[1] * wv[1] + wv[2] * wv[2]) + 2.220446049250313e-16;
+        double sn, cs;
+        sincos(nw * T / 2.0, &sn, &cs);
+        const double kk = sn / nw;
+        const double dq[4] = {cs, kk * wv[0], kk * wv[1], kk * wv[2]};
+        qmul(dq, q, &y[9]);
+    }
+    __syncwarp();
+    if (lane < 9) {
+        double m = 0.0;
+        for (int i = 0; i < npts; ++i) m += (i == 0 ? w.wm0 : w.wi) * s.Y[i][lane];
+        s.ymean[lane] = m;
+    }
+    __syncwarp();
+    double qm[4];
+    mean_quaternion_warp(s, npts, 9, w.wm0, w.wi, qm, lane);
+    if (lane == 0)
+        for (int i = 0; i < 4; ++i) s.ymean[9 + i] = qm[i];
+    __syncwarp();
+    for (int i = lane; i < npts; i += 32) {
+        for (int r = 0; r < 9; ++r) s.DY[i][r] = s.Y[i][r] - s.ymean[r];
+        quat_diff(&s.Y[i][9], &s.ymean[9], &s.DY[i][9]);
+    }
+    __syncwarp();
+    for (int e = lane; e < 144; e += 32) {
+        const int r = e / 12, c = e % 12;
+        double v = 0.0;
+        for (int i = 0; i < npts; ++i) v += (i == 0 ? w.wc0 : w.wi) * s.DY[i][r] * s.DY[i][c];
+        s.P[r][c] = v;
+    }
+    if (lane < 13) s.mean[lane] = s.ymean[lane];
+    __syncwarp();
+}
+
+// ---- correct ----------------------------------------------------------------------------------
+__device__ void ukf_correct_warp(UkfSmem& s, const UkfParams& p, int mtype, const double* meas, int lane) {
+    if (mtype == ROFTB_MEAS_NONE) return;
+    const bool has_v = (mtype == ROFTB_MEAS_VELOCITY || mtype == ROFTB_MEAS_POSE_VELOCITY);
+    const bool has_p = (mtype == ROFTB_MEAS_POSE || mtype == ROFTB_MEAS_POSE_VELOCITY);
+    const int k = (has_v ? 6 : 0) + (has_p ? 6 : 0);  // noise dof = innovation dof
+    const int n = 12 + k, npts = 2 * n + 1;
+    const int nlin = (has_v ? 6 : 0) + (has_p ? 3 : 0);
+    const UtW w = ut_weights(n, p);
+    const double sc = sqrt(w.c);
+    for (int i = lane; i < 144; i += 32) s.A[i / 12][i % 12] = s.P[i / 12][i % 12];
+    __syncwarp();
+    cov_sqrt_warp(s, 12, sc, s.AP, lane);
+    // R = blkdiag(R_velocity, R_pose) (CartesianQuaternionMeasurement.cpp:49-61)
+    for (int i = lane; i < 144; i += 32) s.A[i / 12][i % 12] = 0.0;
+    __syncwarp();
+    if (lane < 3) {
+        int o = 0;
+        if (has_v) {
+            s.A[lane][lane] = p.cov_v[lane];
+            s.A[3 + lane][3 + lane] = p.cov_w[lane];
+            o = 6;
+        }
+        if (has_p) {
+            s.A[o + lane][o + lane] = p.cov_x[lane];
+            s.A[o + 3 + lane][o + 3 + lane] = p.cov_q[lane];
+        }
+    }
+    __syncwarp();
+    cov_sqrt_warp(s, k, sc, s.AN, lane);
+
+    for (int i = lane; i < npts; i += 32) {
+        double lin[9], q[4], nz[12];
+        make_sigma_point(s, i, n, k, lin, q, nz);
+        double* y = s.Y[i];
+        int o = 0;
+        if (has_v) {  // .cpp:384-414 with use_screw_velocity == false: v + w x (-p) + noise, w + noise
+            const double* v = &lin[0];
+            const double* wv = &lin[3];
+            const double px = -lin[6], py = -lin[7], pz = -lin[8];
+            y[0] = v[0] + (wv[1] * pz - wv[2] * py) + nz[0];
+            y[1] = v[1] + (wv[2] * px - wv[0] * pz) + nz[1];
+            y[2] = v[2] + (wv[0] * py - wv[1] * px) + nz[2];
+            y[3] = wv[0] + nz[3];
+            y[4] = wv[1] + nz[4];
+            y[5] = wv[2] + nz[5];
+            o = 6;
+        }
+        if (has_p) {  // .cpp:369-379
+            const int no = has_v ? 6 : 0;
+            for (int r = 0; r < 3; ++r) y[o + r] = lin[6 + r] + nz[no + r];
+            double dq[4];
+            rotvec_to_quat(&nz[no + 3], dq);
+            qmul(dq, q, &y[o + 3]);
+        }
+        for (int r = 0; r < 9; ++r) s.DX[i][r] = lin[r] - s.mean[r];
+        quat_diff(q, &s.mean[9], &s.DX[i][9]);
+    }
+    __syncwarp();
+    if (lane < nlin) {
+        double m = 0.0;
+        for (int i = 0; i < npts; ++i) m += (i == 0 ? w.wm0 : w.wi) * s.Y[i][lane];
+        s.ymean[lane] = m;
+    }
+    __syncwarp();
+    if (has_p) {
+        double qm[4];
+        mean_quaternion_warp(s, npts, nlin, w.wm0, w.wi, qm, lane);
+        if (lane == 0)
+            for (int i = 0; i < 4; ++i) s.ymean[nlin + i] = qm[i];
+        __syncwarp();
+    }
+    for (int i = lane; i < npts; i += 32) {
+        for (int r = 0; r < nlin; ++r) s.DY[i][r] = s.Y[i][r] - s.ymean[r];
+        if (has_p) quat_diff(&s.Y[i][nlin], &s.ymean[nlin], &s.DY[i][nlin]);
+    }
+    // innovation (.cpp:436-487): linear differences; quaternion through diff_quaternion(measured, predicted)
+    if (lane < nlin) {
+        // measurement layout (v, w, x, q): velocity-only uses [0..5], pose-only uses [6..12]
+        const int src = (mtype == ROFTB_MEAS_POSE) ? 6 + lane : lane;
+        s.innov[lane] = meas[src] - s.ymean[lane];
+    }
+    if (has_p && lane == 0) quat_diff(&meas[9], &s.ymean[nlin], &s.innov[nlin]);
+    __syncwarp();
+    const int m = k;
+    for (int e = lane; e < 12 * 24; e += 32) s.Py[e / 24][e % 24] = 0.0;
+    __syncwarp();
+    for (int e = lane; e < m * m; e += 32) {
+        const int r = e / m, c = e % m;
+        double v = 0.0;
+        for (int i = 0; i < npts; ++i) v += (i == 0 ? w.wc0 : w.wi) * s.DY[i][r] * s.DY[i][c];
+        s.Py[r][c] = v;
+        s.Py[r][12 + c] = (r == c) ? 1.0 : 0.0;
+    }
+    for (int e = lane; e < 12 * m; e += 32) {
+        const int r = e / m, c = e % m;
+        double v = 0.0;
+        for (int i = 0; i < npts; ++i) v += (i == 0 ? w.wc0 : w.wi) * s.DX[i][r] * s.DY[i][c];
+        s.Pxy[r][c] = v;
+    }
+    __syncwarp();
+    // keep a copy of Py for the covariance update: KPy is computed from it below, so save into A
+    for (int e = lane; e < m * m; e += 32) s.A[e / m][e % m] = s.Py[e / m][e % m];
+    __syncwarp();
+    // Gauss-Jordan inverse of the SPD matrix Py in [Py | I]
+    for (int col = 0; col < m; ++col) {
+        const double piv = 1.0 / s.Py[col][col];
+        __syncwarp();
+        if (lane < 24) s.Py[col][lane] *= piv;
+        __syncwarp();
+        if (lane < m && lane != col) {
+            const double f = s.Py[lane][col];
+            for (int c = 0; c < 24; ++c) s.Py[lane][c] -= f * s.Py[col][c];
+        }
+        __syncwarp();
+    }
+    // K = Pxy Py^-1 (UKFCorrection.cpp:118)
+    for (int e = lane; e < 12 * m; e += 32) {
+        const int r = e / m, c = e % m;
+        double v = 0.0;
+        for (int j = 0; j < m; ++j) v += s.Pxy[r][j] * s.Py[j][12 + c];
+        s.K[r][c] = v;
+    }
+    __syncwarp();
+    if (lane < 12) {
+        double v = 0.0;
+        for (int j = 0; j < m; ++j) v += s.K[lane][j] * s.innov[j];
+        s.Kn[lane] = v;
+    }
+    for (int e = lane; e < 12 * m; e += 32) {
+        const int r = e / m, c = e % m;
+        double v = 0.0;
+        for (int j = 0; j < m; ++j) v += s.K[r][j] * s.A[j][c];
+        s.KPy[r][c] = v;
+    }
+    __syncwarp();
+    // P <- P - K Py K^T (UKFCorrection.cpp:132); mean update (:125,:128)
+    for (int e = lane; e < 144; e += 32) {
+        const int r = e / 12, c = e % 12;
+        double v = 0.0;
+        for (int j = 0; j < m; ++j) v += s.KPy[r][j] * s.K[c][j];
+        s.P[r][c] -= v;
+    }
+    if (lane == 0) {
+        double dq[4], qn[4];
+        rotvec_to_quat(&s.Kn[9], dq);
+        qmul(dq, &s.mean[9], qn);
+        for (int i = 0; i < 9; ++i) s.mean[i] += s.Kn[i];
+        for (int i = 0; i < 4; ++i) s.mean[9 + i] = qn[i];
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) k_ukf_batch(UkfArgs a) {
+    const int t = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int nops = a.n_ops[t];
+    if (nops <= 0) return;
+    __shared__ UkfSmem s;
+    double* gm = a.mean + (long long)t * 13;
+    double* gc = a.cov + (long long)t * 144;
+    if (lane < 13) s.mean[lane] = gm[lane];
+    for (int i = lane; i < 144; i += 32) s.P[i / 12][i % 12] = gc[i];
+    __syncwarp();
+    __shared__ double meas[13];
+    for (int o = 0; o < nops; ++o) {
+        const UkfOp* op = a.ops + (long long)t * a.max_ops + o;
+        const int kind = op->kind;
+        if (kind == kOpPredict) {
+            ukf_predict_warp(s, a.p, op->dt, lane);
+        } else if (kind == kOpCorrect) {
+            if (lane < 13) {
+                double v = op->meas[lane];
+                if (lane < 6 && op->vel_slot >= 0 && a.vel_hist)
+                    v = a.vel_hist[((long long)t * a.hist_ring + op->vel_slot) * 6 + lane];
+                meas[lane] = v;
+            }
+            __syncwarp();
+            ukf_correct_warp(s, a.p, op->meas_type, meas, lane);
+        } else if (kind == kOpSwapBuffered && a.buf_mean) {
+            // ROFTFilter.cpp:334-340: buffered_belief_ <-> p_corr_belief_
+            double* bm = a.buf_mean + (long long)t * 13;
+            double* bc = a.buf_cov + (long long)t * 144;
+            if (lane < 13) {
+                const double v = bm[lane];
+                bm[lane] = s.mean[lane];
+                s.mean[lane] = v;
+            }
+            for (int i = lane; i < 144; i += 32) {
+                const double v = bc[i];
+                bc[i] = s.P[i / 12][i % 12];
+                s.P[i / 12][i % 12] = v;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane < 13) gm[lane] = s.mean[lane];
+    for (int i = lane; i < 144; i += 32) gc[i] = s.P[i / 12][i % 12];
+}
+
+}  // namespace
+
+int launch_ukf(const UkfArgs& a, cudaStream_t s) {
+    ROFTB_LAUNCH(k_ukf_batch, a.n_tracks, 32, 0, s, a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace roftb

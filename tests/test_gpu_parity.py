@@ -1,0 +1,285 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json): warped / thresholded masks bit-exact; information matrix, information vector,
+velocity and pose within 1e-4 relative; selected-pixel counts identical.
+"""
+import numpy as np
+import pytest
+
+import roft_oracle as o
+from helpers import frame_inputs, quat_close, rel, sequence, small_cfg, to_roftb_config
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from roft_b200 import api as _api
+    _api.load_library()
+    return _api
+
+
+def make_tracker(api, cfg, n=1, fmt="f32"):
+    return api.Tracker(to_roftb_config(cfg, n, fmt))
+
+
+# ------------------------------------------------------------------------------------------------
+# mask synchronisation: bit-exact
+# ------------------------------------------------------------------------------------------------
+def _oracle_warp(mask, flows, cfg, zero_origin):
+    m = mask.copy()
+    if zero_origin:
+        m[0, 0] = 0
+    out = o.remap_exact(m, o.mask_warp_map(m, flows, cfg))
+    return out, o.threshold_mask(out)
+
+
+@pytest.mark.parametrize("fmt", ["f32", "s16"])
+@pytest.mark.parametrize("mixed", [False, True])
+def test_mask_sync_bit_exact(api, fmt, mixed):
+    cfg = small_cfg(flow_grid=1 if fmt == "f32" else 4, flow_scale=1.0 if fmt == "f32" else 32.0, segm_delay=6)
+    seq = sequence(cfg, 3, 8, flow_format=fmt, mixed_mask_values=mixed)
+    trk = make_tracker(api, cfg, 3, fmt)
+    # (a) single-flow propagation with zeroed origin, (b) new mask through 6 buffered flows
+    for zero_origin, flows_idx in ((True, [3]), (False, [1, 2, 3, 4, 5, 6]), (False, [2])):
+        masks = seq.mask[flows_idx[0] - 1].numpy()
+        flows = [seq.flow[i].numpy() for i in flows_idx]
+        raw, thr = trk.mask_sync(masks, flows, zero_origin)
+        for t in range(3):
+            eraw, ethr = _oracle_warp(masks[t], [f[t] for f in flows], cfg, zero_origin)
+            assert np.array_equal(raw[t], eraw), (fmt, mixed, zero_origin, t, int((raw[t] != eraw).sum()))
+            assert np.array_equal(thr[t], ethr)
+
+
+def test_mask_sync_edge_cases(api):
+    cfg = small_cfg(segm_delay=0)
+    H, W = cfg.height, cfg.width
+    rng = np.random.default_rng(0)
+    trk = make_tracker(api, cfg, 1)
+    cases = []
+    # Q2: non-zero origin floods unmapped pixels in the new-mask branch
+    m = np.zeros((H, W), np.uint8); m[40:90, 100:180] = 255; m[0, 0] = 255
+    f = np.full((H, W, 2), 1.5, np.float32)
+    cases.append((m, [f], False))
+    cases.append((m, [f], True))
+    # mixed values {1,2,255}, collisions (contracting flow), out-of-range / NaN / inf / huge flows
+    m2 = rng.choice(np.array([0, 1, 2, 255], np.uint8), size=(H, W), p=[0.5, 0.1, 0.2, 0.2])
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    f2 = np.stack([(W / 2 - xx) * 0.3, (H / 2 - yy) * 0.3], -1).astype(np.float32)
+    f2 += rng.normal(0, 0.7, f2.shape).astype(np.float32)
+    bad = rng.random((H, W))
+    f2[bad < 0.02] = np.nan
+    f2[(bad >= 0.02) & (bad < 0.04)] = np.inf
+    f2[(bad >= 0.04) & (bad < 0.06)] = 1e10
+    f2[(bad >= 0.06) & (bad < 0.08)] = -3e9
+    f3 = rng.normal(0, 30.0, f2.shape).astype(np.float32)  # large displacements leave the frame
+    f4 = rng.uniform(-0.99, 0.99, f2.shape).astype(np.float32)  # t in (-1, 0) truncates to 0
+    cases.append((m2, [f2], False))
+    cases.append((m2, [f2, f3, f4], False))
+    cases.append((m2, [f4], True))
+    cases.append((m2, [], False))  # empty chain: identity map, unmapped -> src(0,0)
+    cases.append((np.zeros((H, W), np.uint8), [f2], False))  # empty mask
+    full = np.full((H, W), 7, np.uint8)
+    cases.append((full, [f4, f4], False))
+    for m, flows, zo in cases:
+        raw, thr = trk.mask_sync(m[None], [f[None] for f in flows], zo)
+        eraw, ethr = _oracle_warp(m, flows, cfg, zo)
+        assert np.array_equal(raw[0], eraw), int((raw[0] != eraw).sum())
+        assert np.array_equal(thr[0], ethr)
+
+
+# ------------------------------------------------------------------------------------------------
+# flow -> velocity measurement and Kalman correction
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fmt,stride,weight", [("f32", 1, True), ("f32", 35, True), ("f32", 7, False), ("s16", 1, True), ("s16", 5, True)])
+def test_flow_velocity_normal_equations(api, fmt, stride, weight):
+    cfg = small_cfg(flow_grid=1 if fmt == "f32" else 4, flow_scale=1.0 if fmt == "f32" else 32.0,
+                    subsampling_radius=float(stride), weight_flow=weight)
+    seq = sequence(cfg, 3, 3, flow_format=fmt)
+    trk = make_tracker(api, cfg, 3, fmt)
+    masks = o.threshold_mask(seq.mask[1].numpy().reshape(-1, cfg.width)).reshape(3, cfg.height, cfg.width)
+    depth = seq.depth[1].numpy(); flow = seq.flow[2].numpy()
+    xp = np.array([[0.02, -0.3, 0.05, -0.5, 0.2, -0.3]] * 3) * np.array([[1.0], [0.0], [-2.0]])
+    dt = np.array([cfg.sample_time, 0.05, 0.02])
+    lam, eta, cnt = trk.flow_velocity(masks, depth, flow, xp, dt)
+    R = np.diag(cfg.cov_flow)
+    for t in range(3):
+        z, H, _ = o.flow_velocity_measurement(masks[t], depth[t], flow[t], cfg, dt[t])
+        assert cnt[t] == z.shape[0] // 2
+        _, _, Lm, em = o.skf_correct_information(xp[t], np.eye(6), z, H, R, weight)
+        assert rel(lam[t], Lm) < TOL, (t, rel(lam[t], Lm))
+        assert rel(eta[t], em) < TOL, (t, rel(eta[t], em))
+
+
+@pytest.mark.parametrize("stride", [1, 35])
+def test_velocity_kf_matches_sequential_reference(api, stride):
+    """Information-form GPU result vs the SEQUENTIAL per-pixel Kalman loop of SKFCorrection.cpp:129-149."""
+    cfg = small_cfg(subsampling_radius=float(stride))
+    seq = sequence(cfg, 2, 3)
+    trk = make_tracker(api, cfg, 2)
+    masks = seq.mask[1].numpy(); depth = seq.depth[1].numpy(); flow = seq.flow[2].numpy()
+    x0 = np.array([[0.0] * 6, [0.05, -0.2, 0.0, -0.8, 0.1, 0.3]])
+    P0 = np.stack([np.diag(cfg.v_cov0), np.diag(cfg.v_cov0) * 3.0])
+    x, P, cnt = trk.velocity_kf(masks, depth, flow, x0, P0)
+    Q = np.diag(list(cfg.v_sigma_linear) + list(cfg.v_sigma_angular))
+    for t in range(2):
+        z, H, _ = o.flow_velocity_measurement(masks[t], depth[t], flow[t], cfg, cfg.sample_time)
+        xp, Pp = o.kf_predict(x0[t], P0[t], Q)
+        xe, Pe = o.skf_correct(xp, Pp, z, H, np.diag(cfg.cov_flow), cfg.weight_flow)
+        assert cnt[t] == z.shape[0] // 2
+        assert rel(x[t], xe) < TOL and rel(P[t], Pe) < TOL, (rel(x[t], xe), rel(P[t], Pe))
+
+
+def test_velocity_observability_gate_and_empty(api):
+    cfg = small_cfg(subsampling_radius=1.0)
+    H, W = cfg.height, cfg.width
+    trk = make_tracker(api, cfg, 3)
+    mask = np.zeros((3, H, W), np.uint8)
+    mask[1, 10, 10:12] = 255         # 2 valid pixels < 3: unobservable
+    mask[2, 20, 20:40] = 255         # enough pixels but all gated out by depth
+    depth = np.full((3, H, W), 0.7, np.float32); depth[2] = 3.0
+    flow = np.zeros((3, H, W, 2), np.float32)
+    x0 = np.tile(np.arange(6.0), (3, 1)); P0 = np.tile(np.eye(6) * 0.01, (3, 1, 1))
+    x, P, cnt = trk.velocity_kf(mask, depth, flow, x0, P0)
+    assert list(cnt) == [0, 2, 0]
+    assert np.array_equal(x, x0) and np.array_equal(P, P0)  # belief untouched (ROFTFilter.cpp:294-301)
+
+
+def test_measurement_export_exact(api):
+    cfg = small_cfg(subsampling_radius=3.0)
+    seq = sequence(cfg, 1, 3)
+    trk = make_tracker(api, cfg, 1)
+    m = seq.mask[1, 0].numpy(); d = seq.depth[1, 0].numpy(); f = seq.flow[2, 0].numpy()
+    z, H, n = trk.flow_measurement_export(m, d, f, cfg.sample_time)
+    ze, He, _ = o.flow_velocity_measurement(m, d, f, cfg, cfg.sample_time)
+    assert n == ze.shape[0] // 2
+    assert np.array_equal(z, ze)  # FP32 quotients widened: exact
+    assert np.allclose(H, He, rtol=1e-14, atol=0)
+
+
+def test_masked_points_and_depth_l1(api):
+    cfg = small_cfg()
+    seq = sequence(cfg, 2, 2)
+    trk = make_tracker(api, cfg, 2)
+    m = seq.mask[1].numpy(); d = seq.depth[1].numpy()
+    pts, cnt = trk.masked_points(m, d, max_depth=10.0)
+    for t in range(2):
+        e = o.masked_points(m[t], d[t], cfg, 10.0)
+        assert cnt[t] == e.shape[0]
+        assert np.allclose(pts[t, :cnt[t]], e, rtol=1e-14, atol=0)
+    div = 4
+    rng = np.random.default_rng(1)
+    rend = np.where(rng.random((2, cfg.height // div, cfg.width // div)) < 0.7, 0.6 + 0.1 * rng.random((2, cfg.height // div, cfg.width // div)), 0.0).astype(np.float32)
+    err, n = trk.masked_depth_l1(m, d, rend, div)
+    for t in range(2):
+        ee, en = o.masked_depth_l1(m[t], d[t], rend[t], div)
+        assert n[t] == en
+        assert abs(err[t] - ee) <= 1e-9 * max(1.0, abs(ee))
+
+
+# ------------------------------------------------------------------------------------------------
+# pose UKF
+# ------------------------------------------------------------------------------------------------
+def _rand_belief(rng, n):
+    mean = np.zeros((n, 13)); cov = np.zeros((n, 12, 12))
+    for i in range(n):
+        mean[i, :9] = rng.normal(0, 0.3, 9); mean[i, 6:9] += [0, 0, 0.7]
+        q = rng.normal(size=4); mean[i, 9:] = q / np.linalg.norm(q)
+        B = rng.normal(size=(12, 12)) * 0.02
+        cov[i] = B @ B.T + np.diag(rng.uniform(1e-4, 2e-3, 12))
+    return mean, cov
+
+
+def test_ukf_predict_and_correct(api):
+    cfg = small_cfg()
+    rng = np.random.default_rng(5)
+    n = 6
+    trk = make_tracker(api, cfg, 1)
+    mean, cov = _rand_belief(rng, n)
+    mean[0] = 0; mean[0, 9] = 1; cov[0] = np.diag(cfg.p_cov0)   # the exactly-degenerate initial belief
+    dt = rng.uniform(0.02, 0.05, n)
+    pm, pc = trk.ukf_predict(mean, cov, dt)
+    for i in range(n):
+        em, ec = o.ukf_predict(mean[i], cov[i], cfg, dt[i])
+        assert rel(pm[i, :9], em[:9]) < TOL and quat_close(pm[i, 9:], em[9:]) < TOL
+        assert rel(pc[i], ec) < TOL, rel(pc[i], ec)
+    for mtype in (o.MEAS_VELOCITY, o.MEAS_POSE, o.MEAS_POSE_VELOCITY):
+        meas = np.zeros((n, 13))
+        meas[:, :9] = mean[:, :9] + rng.normal(0, 0.05, (n, 9))
+        meas[:, :3] = mean[:, :3] + np.cross(mean[:, 3:6], -mean[:, 6:9]) + rng.normal(0, 0.05, (n, 3))
+        dq = o.rotation_vector_to_quaternion(rng.normal(0, 0.05, (n, 3)))
+        meas[:, 9:] = o.quat_mul(dq, mean[:, 9:])
+        meas[1, 9:] *= -1  # measured quaternion on the other hemisphere
+        cm, cc = trk.ukf_correct(pm, pc, meas, np.full(n, mtype, np.int32))
+        for i in range(n):
+            mv = {o.MEAS_VELOCITY: meas[i, :6], o.MEAS_POSE: meas[i, 6:], o.MEAS_POSE_VELOCITY: meas[i]}[mtype]
+            em, ec = o.ukf_correct(pm[i], pc[i], mv, mtype, cfg)
+            assert rel(cm[i, :9], em[:9]) < TOL, (mtype, i, rel(cm[i, :9], em[:9]))
+            assert quat_close(cm[i, 9:], em[9:]) < TOL
+            assert rel(cc[i], ec) < TOL, (mtype, i, rel(cc[i], ec))
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole filter loop
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fmt,stride,resync", [("f32", 5, True), ("s16", 3, True), ("f32", 1, False)])
+def test_filter_loop_matches_oracle(api, fmt, stride, resync):
+    cfg = small_cfg(flow_grid=1 if fmt == "f32" else 4, flow_scale=1.0 if fmt == "f32" else 32.0,
+                    subsampling_radius=float(stride), use_pose_resync=resync, segm_delay=4, pose_delay=4)
+    T, F = 3, 22
+    seq = sequence(cfg, T, F, flow_format=fmt)
+    x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
+    trk = make_tracker(api, cfg, T, fmt)
+    trk.init(x0)
+    oracles = [o.RoftFilterOracle(cfg, x0[t]) for t in range(T)]
+    for k in range(F):
+        frs = [frame_inputs(seq, cfg, k, t) for t in range(T)]
+        has_mask = frs[0].mask is not None
+        mask = np.stack([f.mask for f in frs]) if has_mask else None
+        pose = np.stack([f.pose if f.pose is not None else np.zeros(7) for f in frs])
+        pv = np.array([f.pose is not None for f in frs], np.uint8)
+        flow = np.stack([f.flow for f in frs]) if k > 0 else None
+        trk.step(np.stack([f.depth for f in frs]), flow, mask, pose=pose, pose_valid=pv)
+        pm, vm = trk.state()
+        raw, thr = trk.mask()
+        cnt, lam, eta = trk.velocity_info()
+        for t in range(T):
+            ep, ev = oracles[t].step(frs[t])
+            orc = oracles[t]
+            if orc.seg_source.mask is not None:
+                assert np.array_equal(raw[t], orc.seg_source.mask), (k, t)
+                assert np.array_equal(thr[t], orc.seg), (k, t)
+            assert cnt[t] == orc.last_n_valid, (k, t, cnt[t], orc.last_n_valid)
+            assert rel(vm[t], ev) < TOL or np.linalg.norm(vm[t] - ev) < 1e-9, (k, t, rel(vm[t], ev))
+            assert rel(pm[t, :9], ep[:9]) < TOL, (k, t, rel(pm[t, :9], ep[:9]))
+            assert quat_close(pm[t, 9:], ep[9:]) < TOL, (k, t)
+
+
+def test_full_resolution_properties(api):
+    """1280x720 (BASELINE size): oracle parity on one frame + size-independent properties."""
+    cfg = o.RoftConfig(subsampling_radius=1.0)
+    seq = sequence(cfg, 2, 3, target_coverage=0.4)
+    trk = make_tracker(api, cfg, 2)
+    m = seq.mask[1].numpy(); d = seq.depth[1].numpy(); f = seq.flow[2].numpy()
+    xp = np.tile(np.array([0.02, -0.3, 0.05, -0.5, 0.2, -0.3]), (2, 1))
+    lam, eta, cnt = trk.flow_velocity(m, d, f, xp)
+    for t in range(2):
+        z, H, _ = o.flow_velocity_measurement(m[t], d[t], f[t], cfg, cfg.sample_time)
+        _, _, Lm, em = o.skf_correct_information(xp[t], np.eye(6), z, H, np.diag(cfg.cov_flow), True)
+        assert cnt[t] == z.shape[0] // 2
+        assert rel(lam[t], Lm) < TOL and rel(eta[t], em) < TOL
+        assert np.allclose(lam[t], lam[t].T)  # symmetric
+        assert np.all(np.linalg.eigvalsh(lam[t]) > 0)  # positive definite
+    raw, thr = trk.mask_sync(m, [f], True)
+    for t in range(2):
+        eraw, ethr = _oracle_warp(m[t], [f[t]], cfg, True)
+        assert np.array_equal(raw[t], eraw) and np.array_equal(thr[t], ethr)
+    # zero flow: warp is the identity on the mask (idempotence), thresholding is idempotent
+    raw0, thr0 = trk.mask_sync(m, [np.zeros_like(f)], True)
+    m0 = m.copy(); m0[:, 0, 0] = 0
+    assert np.array_equal(raw0, m0)
+    assert np.array_equal(o.threshold_mask(thr0.reshape(-1, cfg.width)).reshape(thr0.shape), thr0)
