@@ -74,6 +74,8 @@ typedef struct roftb_config {
     int32_t pose_delay;              /* same for pose_dataset                                      */
     int32_t device;                  /* CUDA device ordinal                                        */
     int32_t use_cuda_graph;          /* reserved                                                   */
+    int32_t accum_fp64;              /* 1 (default): per-pixel Jacobian terms and normal-equation sums in
+                                        FP64; 0: FP32 terms (agreement then scales with cond(Lambda)*1e-7/sqrt(N)) */
 } roftb_config;
 
 /* One camera frame for all tracks = what the reference's sources deliver at one
@@ -108,6 +110,12 @@ int roftb_version(void);
 int64_t roftb_kernel_launches(const roftb_ctx* ctx);
 /* CUDA stream the kernels are enqueued on (cudaStream_t as void*), for event timing */
 void* roftb_stream(roftb_ctx* ctx);
+/* Device-side phase timing of roftb_filter_step with CUDA events on that stream.  Reads the averages
+ * (ms per step since profiling was enabled) of the 7 phases {candidate rank, flow pass A (innovation
+ * norms), median select, flow pass B (normal equations), 6x6 epilogue, mask sync, pose UKF} into
+ * ms_per_step[7] / steps (either may be NULL), then enables (1) or disables (0) profiling; enabling
+ * resets the averages. */
+int roftb_profile(roftb_ctx* ctx, int32_t enable, double* ms_per_step, int64_t* steps);
 
 /* ---- the filter loop: ROFTFilter::initialization_step / filtering_step ----------------- */
 /* ROFTFilter.cpp:216-237.  p_mean0: host [n_tracks][13] or NULL (zeros, q = identity);

@@ -24,7 +24,7 @@ MAX_DELAY = 8
 
 EXPORTED_SYMBOLS = [
     "roftb_config_default", "roftb_create", "roftb_destroy", "roftb_last_error", "roftb_sync", "roftb_version",
-    "roftb_kernel_launches", "roftb_stream", "roftb_filter_init", "roftb_filter_step", "roftb_get_state",
+    "roftb_kernel_launches", "roftb_stream", "roftb_profile", "roftb_filter_init", "roftb_filter_step", "roftb_get_state",
     "roftb_get_mask", "roftb_get_velocity_info", "roftb_mask_sync", "roftb_flow_velocity", "roftb_velocity_kf",
     "roftb_flow_measurement_export", "roftb_masked_points", "roftb_masked_depth_l1", "roftb_ukf_predict",
     "roftb_ukf_correct",
@@ -45,7 +45,7 @@ class RoftbConfig(C.Structure):
         ("ut_alpha", C.c_double), ("ut_beta", C.c_double), ("ut_kappa", C.c_double),
         ("use_pose", C.c_int32), ("use_pose_resync", C.c_int32), ("use_velocity", C.c_int32), ("flow_aided", C.c_int32),
         ("segm_delay", C.c_int32), ("pose_delay", C.c_int32),
-        ("device", C.c_int32), ("use_cuda_graph", C.c_int32),
+        ("device", C.c_int32), ("use_cuda_graph", C.c_int32), ("accum_fp64", C.c_int32),
     ]
 
 
@@ -85,6 +85,7 @@ def load_library() -> C.CDLL:
     lib.roftb_kernel_launches.restype = C.c_int64
     lib.roftb_stream.argtypes = [C.c_void_p]
     lib.roftb_stream.restype = C.c_void_p
+    lib.roftb_profile.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.roftb_filter_init.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.roftb_filter_step.argtypes = [C.c_void_p, C.POINTER(RoftbFrame)]
     lib.roftb_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 4
@@ -242,6 +243,14 @@ class Tracker:
 
     def sync(self):
         self._check(self._lib.roftb_sync(self._h), "roftb_sync")
+
+    PHASES = ("rank", "flow_pass_a", "median_select", "flow_pass_b", "epilogue", "mask_sync", "ukf")
+
+    def profile(self, enable: bool):
+        """Read the per-phase device times (ms per step) gathered so far, then enable/disable profiling."""
+        ms = np.zeros(7); n = C.c_int64(0)
+        self._check(self._lib.roftb_profile(self._h, int(enable), _ptr(ms), C.addressof(n)), "roftb_profile")
+        return dict(zip(self.PHASES, ms.tolist())), n.value
 
     @property
     def kernel_launches(self) -> int:

@@ -96,9 +96,12 @@ struct PassArgs {
     const double* x_pred; int x_stride;
     double* partials; int max_blocks;
     double fx, fy;
+    double cxd, cyd, inv_fxd, inv_fyd;   // FP64 intrinsics: pixel -> normalised coordinates without systematic rounding
 };
 
-template <int PASS, bool FAST>
+// AT = accumulation type of pass B: float (per-pixel terms and partial sums in FP32) or double (per-pixel terms
+// and sums in FP64: forward error ~ cond(Lambda) * 1e-16 instead of cond * 1e-7 / sqrt(N)).
+template <int PASS, bool FAST, typename AT>
 __global__ void __launch_bounds__(kThreads) k_flow_pass(PassArgs a) {
     const int t = blockIdx.y;
     const VelCtl c = a.ctl[t];
@@ -122,10 +125,10 @@ __global__ void __launch_bounds__(kThreads) k_flow_pass(PassArgs a) {
     wp.use = 0;
     if (PASS == 1 && a.weight_flow) wp = a.wp[t];
 
-    float acc[kNAcc];
+    AT acc[kNAcc];
     if (PASS == 1) {
 #pragma unroll
-        for (int i = 0; i < kNAcc; ++i) acc[i] = 0.f;
+        for (int i = 0; i < kNAcc; ++i) acc[i] = (AT)0;
     }
 
     const int tile_end = min((int)(blockIdx.x + 1) * a.tiles_per_block, a.n_block_tiles);
@@ -184,7 +187,10 @@ __global__ void __launch_bounds__(kThreads) k_flow_pass(PassArgs a) {
             const int px = (wt * 128 + j * 32 + lane) << 2;
             const int v = px / g.W;
             const int u0 = px - v * g.W;
-            const float yh = ((float)v - g.cy) * g.inv_fy;
+            // normalised coordinates from FP64 intrinsics (a rounded 1/fx would bias every pixel the same way)
+            const double yhd = ((double)v - a.cyd) * a.inv_fyd;
+            const double xh0d = ((double)u0 - a.cxd) * a.inv_fxd;
+            const float yh = (float)yhd;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (!((sel[j] >> (8 * i)) & 1u)) continue;
@@ -202,7 +208,8 @@ __global__ void __launch_bounds__(kThreads) k_flow_pass(PassArgs a) {
                 }
                 // hpp:252 gates
                 if (!(flow_valid(dx, dy) && d > 0.f && (double)d < g.max_depth)) continue;
-                const float xh = ((float)(u0 + i) - g.cx) * g.inv_fx;
+                const double xhd = fma((double)i, a.inv_fxd, xh0d);
+                const float xh = (float)xhd;
                 const float ia = __fdiv_rn(1.0f, d);
                 const float l1[5] = {ia, -xh * ia, -xh * yh, 1.0f + xh * xh, -yh};
                 const float l2[5] = {ia, -yh * ia, -(1.0f + yh * yh), xh * yh, xh};
@@ -216,27 +223,41 @@ __global__ void __launch_bounds__(kThreads) k_flow_pass(PassArgs a) {
                 } else {
                     float l = 1.0f;
                     if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
-                    float w1[5], w2[5];
+                    AT e1[5], e2[5];
+                    if (sizeof(AT) == 8) {
+                        // FP64 per-pixel terms: 1/d refined from the FP32 reciprocal by one Newton step
+                        double r = (double)ia;
+                        r = r * (2.0 - (double)d * r);
+                        e1[0] = (AT)r; e1[1] = (AT)(-xhd * r); e1[2] = (AT)(-xhd * yhd); e1[3] = (AT)(1.0 + xhd * xhd); e1[4] = (AT)(-yhd);
+                        e2[0] = (AT)r; e2[1] = (AT)(-yhd * r); e2[2] = (AT)(-(1.0 + yhd * yhd)); e2[3] = (AT)(xhd * yhd); e2[4] = (AT)xhd;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            e1[k] = (AT)l1[k];
+                            e2[k] = (AT)l2[k];
+                        }
+                    }
+                    AT w1[5], w2[5];
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
-                        w1[k] = l * l1[k];
-                        w2[k] = l * l2[k];
+                        w1[k] = (AT)l * e1[k];
+                        w2[k] = (AT)l * e2[k];
                     }
                     int o = 0;
 #pragma unroll
                     for (int r = 0; r < 5; ++r)
 #pragma unroll
                         for (int s = r; s < 5; ++s) {
-                            acc[o] = fmaf(w1[r], l1[s], acc[o]);
-                            acc[15 + o] = fmaf(w2[r], l2[s], acc[15 + o]);
+                            acc[o] = fma(w1[r], e1[s], acc[o]);
+                            acc[15 + o] = fma(w2[r], e2[s], acc[15 + o]);
                             ++o;
                         }
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
-                        acc[30 + k] = fmaf(w1[k], dx, acc[30 + k]);
-                        acc[35 + k] = fmaf(w2[k], dy, acc[35 + k]);
+                        acc[30 + k] = fma(w1[k], (AT)dx, acc[30 + k]);
+                        acc[35 + k] = fma(w2[k], (AT)dy, acc[35 + k]);
                     }
-                    acc[40] += 1.0f;
+                    acc[40] += (AT)1;
                 }
             }
         }
@@ -266,10 +287,10 @@ __global__ void __launch_bounds__(kThreads) k_flow_pass(PassArgs a) {
     }
 
     if (PASS == 1) {
-        __shared__ float red[kThreads / 32][kNAcc];
+        __shared__ AT red[kThreads / 32][kNAcc];
 #pragma unroll
         for (int i = 0; i < kNAcc; ++i) {
-            const float s = warp_sum(acc[i]);
+            const AT s = warp_sum(acc[i]);
             if (lane == 0) red[warp][i] = s;
         }
         __syncthreads();
@@ -459,38 +480,32 @@ __global__ void k_sel_final(int n_tracks, const SelState* __restrict__ sel, Weig
 }
 
 // ---- per-track epilogue: FP64 reduction of the block partials, 6x6 solve, gate, publish ------------
-__device__ void chol6_inverse(const double* A, double* Ainv) {
-    // A symmetric positive definite 6x6 (row-major) -> Ainv. Cholesky A = L L^T, then invert.
-    double L[36];
-    for (int i = 0; i < 36; ++i) L[i] = 0.0;
-    for (int j = 0; j < 6; ++j) {
-        double s = A[j * 6 + j];
-        for (int k = 0; k < j; ++k) s -= L[j * 6 + k] * L[j * 6 + k];
-        const double d = sqrt(s);
-        L[j * 6 + j] = d;
-        for (int i = j + 1; i < 6; ++i) {
-            double v = A[i * 6 + j];
-            for (int k = 0; k < j; ++k) v -= L[i * 6 + k] * L[j * 6 + k];
-            L[i * 6 + j] = v / d;
-        }
-    }
-    // Linv (lower)
-    double Li[36];
-    for (int i = 0; i < 36; ++i) Li[i] = 0.0;
-    for (int c = 0; c < 6; ++c) {
-        Li[c * 6 + c] = 1.0 / L[c * 6 + c];
-        for (int i = c + 1; i < 6; ++i) {
-            double v = 0.0;
-            for (int k = c; k < i; ++k) v -= L[i * 6 + k] * Li[k * 6 + c];
-            Li[i * 6 + c] = v / L[i * 6 + i];
-        }
-    }
+// In-place Gauss-Jordan inverse of a symmetric positive definite 6x6 matrix held in shared memory
+// (no pivoting needed for SPD input). Executed by one thread.
+__device__ __noinline__ void spd6_inverse(double (*A)[6], double (*Ainv)[6]) {
+#pragma unroll 1
     for (int i = 0; i < 6; ++i)
+#pragma unroll 1
+        for (int j = 0; j < 6; ++j) Ainv[i][j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int col = 0; col < 6; ++col) {
+        const double piv = 1.0 / A[col][col];
+#pragma unroll 1
         for (int j = 0; j < 6; ++j) {
-            double v = 0.0;
-            for (int k = (i > j ? i : j); k < 6; ++k) v += Li[k * 6 + i] * Li[k * 6 + j];
-            Ainv[i * 6 + j] = v;
+            A[col][j] *= piv;
+            Ainv[col][j] *= piv;
         }
+#pragma unroll 1
+        for (int r = 0; r < 6; ++r) {
+            if (r == col) continue;
+            const double f = A[r][col];
+#pragma unroll 1
+            for (int j = 0; j < 6; ++j) {
+                A[r][j] -= f * A[col][j];
+                Ainv[r][j] -= f * Ainv[col][j];
+            }
+        }
+    }
 }
 
 struct EpiArgs {
@@ -553,25 +568,27 @@ __global__ void __launch_bounds__(32) k_vel_epilogue(EpiArgs a) {
         // ROFTFilter.cpp:294-301: fewer than 3 valid pixels (or an empty measurement, SKFCorrection.cpp:60-68 keeps
         // the PREDICTED state, which the observability gate then reverts) -> the belief is left untouched.
         if (a.update_state && count >= 3) {
-            double Pp[36], Pinv[36], Lam[36], Pn[36], rhs[6];
-            for (int i = 0; i < 36; ++i) Pp[i] = P[i];
-            for (int i = 0; i < 6; ++i) Pp[i * 6 + i] += a.q_diag[i];  // KFPrediction: P + Q, F = I
-            chol6_inverse(Pp, Pinv);
-            for (int i = 0; i < 36; ++i) Lam[i] = Pinv[i] + Lm[i];
-            chol6_inverse(Lam, Pn);
+            __shared__ double sW[6][6], sPinv[6][6], sPn[6][6];
+            for (int i = 0; i < 36; ++i) sW[i / 6][i % 6] = P[i];
+            for (int i = 0; i < 6; ++i) sW[i][i] += a.q_diag[i];  // KFPrediction: P + Q, F = I
+            spd6_inverse(sW, sPinv);
+            for (int i = 0; i < 36; ++i) sW[i / 6][i % 6] = sPinv[i / 6][i % 6] + Lm[i];
+            spd6_inverse(sW, sPn);
+            double rhs[6], xn[6];
             for (int i = 0; i < 6; ++i) {
                 double v = eta[i];
-                for (int j = 0; j < 6; ++j) v += Pinv[i * 6 + j] * x[j];
+                for (int j = 0; j < 6; ++j) v += sPinv[i][j] * x[j];
                 rhs[i] = v;
             }
-            double xn[6];
             for (int i = 0; i < 6; ++i) {
                 double v = 0.0;
-                for (int j = 0; j < 6; ++j) v += Pn[i * 6 + j] * rhs[j];
+                for (int j = 0; j < 6; ++j) v += sPn[i][j] * rhs[j];
                 xn[i] = v;
             }
             for (int i = 0; i < 6; ++i) x[i] = xn[i];
-            for (int i = 0; i < 36; ++i) P[i] = Pn[i];
+            // symmetrise the information-form covariance (exactly symmetric in exact arithmetic)
+            for (int i = 0; i < 6; ++i)
+                for (int j = 0; j < 6; ++j) P[i * 6 + j] = 0.5 * (sPn[i][j] + sPn[j][i]);
         }
     } else {
         if (a.out_lambda)
@@ -615,7 +632,9 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     const int tpb = (n_block_tiles + bpt - 1) / bpt;
     bpt = (n_block_tiles + tpb - 1) / tpb;
 
+    if (a.prof) cudaEventRecord(a.prof[0], s);
     if (g.stride > 1) launch_mask_rank(a.seg, a.seg_stride, a.thr, g.HW, T, a.wt_count, nullptr, a.ctl, s);
+    if (a.prof) cudaEventRecord(a.prof[1], s);
     PassArgs pa;
     pa.g = g;
     pa.ft = a.ft;
@@ -637,12 +656,17 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     pa.max_blocks = a.max_blocks;
     pa.fx = a.fx;
     pa.fy = a.fy;
+    pa.cxd = a.cx;
+    pa.cyd = a.cy;
+    pa.inv_fxd = 1.0 / a.fx;
+    pa.inv_fyd = 1.0 / a.fy;
     const bool fast = (!g.flow_s16 && g.grid == 1);
     if (a.weight_flow) {
         if (fast)
-            ROFTB_LAUNCH((k_flow_pass<0, true>), dim3(bpt, T), kThreads, 0, s, pa);
+            ROFTB_LAUNCH((k_flow_pass<0, true, float>), dim3(bpt, T), kThreads, 0, s, pa);
         else
-            ROFTB_LAUNCH((k_flow_pass<0, false>), dim3(bpt, T), kThreads, 0, s, pa);
+            ROFTB_LAUNCH((k_flow_pass<0, false, float>), dim3(bpt, T), kThreads, 0, s, pa);
+        if (a.prof) cudaEventRecord(a.prof[2], s);
         ROFTB_LAUNCH(k_sel_init, (T + 127) / 128, 128, 0, s, T, a.norm_count, a.sel, a.ctl);
         // enough blocks per track to spread the list, few enough that the per-block histogram flush stays cheap
         int sb = max(1, min(32, (148 * 4 + T - 1) / T));
@@ -654,11 +678,22 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
         ROFTB_LAUNCH(k_sel_scan<2>, T, kThreads, 0, s, a.sel, a.hist);
         ROFTB_LAUNCH(k_sel_stats, dim3(sb, T), kThreads, 0, s, a.norms, g.HW, a.sel);
         ROFTB_LAUNCH(k_sel_final, (T + 127) / 128, 128, 0, s, T, a.sel, a.wp);
+    } else if (a.prof) {
+        cudaEventRecord(a.prof[2], s);
     }
-    if (fast)
-        ROFTB_LAUNCH((k_flow_pass<1, true>), dim3(bpt, T), kThreads, 0, s, pa);
-    else
-        ROFTB_LAUNCH((k_flow_pass<1, false>), dim3(bpt, T), kThreads, 0, s, pa);
+    if (a.prof) cudaEventRecord(a.prof[3], s);
+    if (a.accum_fp64) {
+        if (fast)
+            ROFTB_LAUNCH((k_flow_pass<1, true, double>), dim3(bpt, T), kThreads, 0, s, pa);
+        else
+            ROFTB_LAUNCH((k_flow_pass<1, false, double>), dim3(bpt, T), kThreads, 0, s, pa);
+    } else {
+        if (fast)
+            ROFTB_LAUNCH((k_flow_pass<1, true, float>), dim3(bpt, T), kThreads, 0, s, pa);
+        else
+            ROFTB_LAUNCH((k_flow_pass<1, false, float>), dim3(bpt, T), kThreads, 0, s, pa);
+    }
+    if (a.prof) cudaEventRecord(a.prof[4], s);
     EpiArgs e;
     e.n_tracks = T;
     e.ctl = a.ctl;
@@ -680,6 +715,7 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     e.norm_count = a.weight_flow ? a.norm_count : nullptr;
     e.update_state = a.update_state;
     ROFTB_LAUNCH(k_vel_epilogue, T, 32, 0, s, e);
+    if (a.prof) cudaEventRecord(a.prof[5], s);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -92,6 +92,13 @@ struct roftb_ctx {
     float* stage_depth = nullptr; void* stage_flow = nullptr; uint8_t* stage_mask = nullptr;
     cudaEvent_t copy_done = nullptr;
     uint8_t* thr_tmp = nullptr;
+
+    // optional per-phase device timing (bench.py roofline): 8 events per in-flight step
+    bool prof_on = false;
+    cudaEvent_t prof_ev[kCtlRing][8];
+    bool prof_used[kCtlRing];
+    double prof_ms[7];
+    long long prof_steps = 0;
 };
 
 namespace {
@@ -176,6 +183,7 @@ void roftb_config_default(roftb_config* c) {
     c->use_pose = 1; c->use_pose_resync = 1; c->use_velocity = 1; c->flow_aided = 1;
     c->segm_delay = 6; c->pose_delay = 6;
     c->device = 0;
+    c->accum_fp64 = 1;
 }
 
 const char* roftb_last_error(const roftb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -205,7 +213,12 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     ctx->HW = (size_t)ctx->g.HW;
     ctx->flow_elems = (size_t)ctx->g.Wf * ctx->g.Hf * 2;
     ctx->launches0 = g_launch_count;
-    for (int i = 0; i < kCtlRing; ++i) ctx->ctl_event_used[i] = false;
+    for (int i = 0; i < kCtlRing; ++i) {
+        ctx->ctl_event_used[i] = false;
+        ctx->prof_used[i] = false;
+        for (int j = 0; j < 8; ++j) ctx->prof_ev[i][j] = nullptr;
+    }
+    for (int j = 0; j < 7; ++j) ctx->prof_ms[j] = 0.0;
     memset(&ctx->ft, 0, sizeof(ctx->ft));
     ctx->th.assign(ctx->T, TrackHost());
     const int T = ctx->T;
@@ -227,6 +240,8 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
     for (int i = 0; i < kCtlRing; ++i) CKC(cudaEventCreateWithFlags(&ctx->ctl_event[i], cudaEventDisableTiming));
+    for (int i = 0; i < kCtlRing; ++i)
+        for (int j = 0; j < 8; ++j) CKC(cudaEventCreate(&ctx->prof_ev[i][j]));
     CKC(dalloc(&ctx->mask_state[0], T * HW));
     CKC(dalloc(&ctx->mask_state[1], T * HW));
     CKC(dalloc(&ctx->winner, T * HW));
@@ -299,6 +314,9 @@ void roftb_destroy(roftb_ctx* ctx) {
     if (ctx->h_nops) cudaFreeHost(ctx->h_nops);
     for (int i = 0; i < kCtlRing; ++i)
         if (ctx->ctl_event[i]) cudaEventDestroy(ctx->ctl_event[i]);
+    for (int i = 0; i < kCtlRing; ++i)
+        for (int j = 0; j < 8; ++j)
+            if (ctx->prof_ev[i][j]) cudaEventDestroy(ctx->prof_ev[i][j]);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -310,6 +328,32 @@ int roftb_sync(roftb_ctx* ctx) {
     CK(cudaSetDevice(ctx->dev));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+static void prof_collect(roftb_ctx* ctx, int slot) {
+    if (!ctx->prof_used[slot]) return;
+    cudaEventSynchronize(ctx->prof_ev[slot][7]);
+    for (int j = 0; j < 7; ++j) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof_ev[slot][j], ctx->prof_ev[slot][j + 1]) == cudaSuccess) ctx->prof_ms[j] += ms;
+    }
+    ctx->prof_steps++;
+    ctx->prof_used[slot] = false;
+}
+
+int roftb_profile(roftb_ctx* ctx, int32_t enable, double* ms_per_step, int64_t* steps) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->dev));
+    for (int i = 0; i < kCtlRing; ++i) prof_collect(ctx, i);
+    if (ms_per_step)
+        for (int j = 0; j < 7; ++j) ms_per_step[j] = ctx->prof_steps ? ctx->prof_ms[j] / (double)ctx->prof_steps : 0.0;
+    if (steps) *steps = ctx->prof_steps;
+    if (enable != (ctx->prof_on ? 1 : 0) || enable) {
+        for (int j = 0; j < 7; ++j) ctx->prof_ms[j] = 0.0;
+        ctx->prof_steps = 0;
+    }
+    ctx->prof_on = enable != 0;
     return 0;
 }
 
@@ -569,10 +613,15 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
         a.sel = ctx->sel; a.wp = ctx->wp; a.partials = ctx->partials; a.max_blocks = ctx->max_blocks;
         a.v_mean = ctx->v_mean; a.v_cov = ctx->v_cov; a.q_diag = ctx->q_diag;
         a.r_flow[0] = cfg.cov_flow[0]; a.r_flow[1] = cfg.cov_flow[1];
-        a.fx = cfg.fx; a.fy = cfg.fy;
+        a.fx = cfg.fx; a.fy = cfg.fy; a.cx = cfg.cx; a.cy = cfg.cy;
+        a.accum_fp64 = cfg.accum_fp64;
         a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
         a.out_count = ctx->d_count; a.out_lambda = ctx->d_lambda; a.out_eta = ctx->d_eta;
         a.update_state = 1;
+        if (ctx->prof_on) {
+            prof_collect(ctx, cslot);
+            a.prof = ctx->prof_ev[cslot];
+        }
         if (launch_velocity(a, s)) return fail(ctx, "launch_velocity failed");
     }
     {
@@ -585,6 +634,7 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
         a.segm_delay = cfg.segm_delay;
         if (launch_mask_sync(a, s)) return fail(ctx, "launch_mask_sync failed");
         ctx->mask_cur ^= 1;
+        if (ctx->prof_on) CK(cudaEventRecord(ctx->prof_ev[cslot][6], s));
     }
     {
         UkfArgs a;
@@ -594,6 +644,10 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
         a.mean = ctx->p_mean; a.cov = ctx->p_cov; a.buf_mean = ctx->pb_mean; a.buf_cov = ctx->pb_cov;
         a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
         if (launch_ukf(a, s)) return fail(ctx, "launch_ukf failed");
+        if (ctx->prof_on) {
+            CK(cudaEventRecord(ctx->prof_ev[cslot][7], s));
+            ctx->prof_used[cslot] = true;
+        }
     }
     if (f->memory == ROFTB_MEM_HOST) CK(cudaEventRecord(ctx->copy_done, s));
     (void)any_vel;
@@ -766,7 +820,8 @@ static int velocity_operator(roftb_ctx* ctx, int32_t n, const uint8_t* mask, con
     a.partials = tb.alloc<double>(N * a.max_blocks * kNAcc);
     a.v_mean = d_x; a.v_cov = d_P; a.q_diag = ctx->q_diag;
     a.r_flow[0] = ctx->cfg.cov_flow[0]; a.r_flow[1] = ctx->cfg.cov_flow[1];
-    a.fx = ctx->cfg.fx; a.fy = ctx->cfg.fy;
+    a.fx = ctx->cfg.fx; a.fy = ctx->cfg.fy; a.cx = ctx->cfg.cx; a.cy = ctx->cfg.cy;
+    a.accum_fp64 = ctx->cfg.accum_fp64;
     a.out_count = tb.alloc<int32_t>(N);
     a.out_lambda = tb.alloc<double>(N * 36);
     a.out_eta = tb.alloc<double>(N * 6);

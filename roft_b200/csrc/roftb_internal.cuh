@@ -158,10 +158,13 @@ struct VelocityArgs {
     double* v_mean; double* v_cov;     // [T][6], [T][36]
     const double* q_diag;              // [6] process noise (device)
     double r_flow[2];
-    double fx, fy;
+    double fx, fy, cx, cy;
+    int accum_fp64;                    // pass B per-pixel terms and sums in FP64 (else FP32)
     double* vel_hist; int hist_ring;   // [T][ring][6]
     // diagnostics
     int32_t* out_count; double* out_lambda; double* out_eta;  // device [T], [T][36], [T][6]
+    cudaEvent_t* prof;                 // optional: 6 events recorded at the phase boundaries (start, rank, pass A,
+                                       // select, pass B, epilogue)
     int update_state;                  // 0: only compute lambda/eta/count (operator mode)
     const double* x_pred_override;     // operator mode: [T][6] predicted mean for the norms (else v_mean)
 };
