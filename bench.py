@@ -194,6 +194,7 @@ def run_own(args):
     ev0.record(ext)
     for _ in range(args.steps):
         do_step(step); step += 1
+    trk.join()
     ev1.record(ext)
     barrier()
     wall = time.perf_counter() - t0

@@ -105,6 +105,9 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out);
 void roftb_destroy(roftb_ctx* ctx);
 const char* roftb_last_error(const roftb_ctx* ctx); /* ctx may be NULL: last create() error */
 int roftb_sync(roftb_ctx* ctx);                     /* wait for all enqueued work           */
+/* Non-blocking: make the main stream (roftb_stream) wait for everything enqueued so far on the library's
+ * internal streams, so that an event recorded on roftb_stream afterwards covers the whole step. */
+int roftb_join(roftb_ctx* ctx);
 int roftb_version(void);
 /* number of this library's kernel launches since create (bench.py "gpu_launches") */
 int64_t roftb_kernel_launches(const roftb_ctx* ctx);

@@ -23,7 +23,7 @@ MEAS_NONE, MEAS_VELOCITY, MEAS_POSE, MEAS_POSE_VELOCITY = 0, 1, 2, 3
 MAX_DELAY = 8
 
 EXPORTED_SYMBOLS = [
-    "roftb_config_default", "roftb_create", "roftb_destroy", "roftb_last_error", "roftb_sync", "roftb_version",
+    "roftb_config_default", "roftb_create", "roftb_destroy", "roftb_last_error", "roftb_sync", "roftb_join", "roftb_version",
     "roftb_kernel_launches", "roftb_stream", "roftb_profile", "roftb_filter_init", "roftb_filter_step", "roftb_get_state",
     "roftb_get_mask", "roftb_get_velocity_info", "roftb_mask_sync", "roftb_flow_velocity", "roftb_velocity_kf",
     "roftb_flow_measurement_export", "roftb_masked_points", "roftb_masked_depth_l1", "roftb_ukf_predict",
@@ -81,6 +81,7 @@ def load_library() -> C.CDLL:
     lib.roftb_config_default.argtypes = [C.POINTER(RoftbConfig)]
     lib.roftb_config_default.restype = None
     lib.roftb_sync.argtypes = [C.c_void_p]
+    lib.roftb_join.argtypes = [C.c_void_p]
     lib.roftb_kernel_launches.argtypes = [C.c_void_p]
     lib.roftb_kernel_launches.restype = C.c_int64
     lib.roftb_stream.argtypes = [C.c_void_p]
@@ -243,6 +244,10 @@ class Tracker:
 
     def sync(self):
         self._check(self._lib.roftb_sync(self._h), "roftb_sync")
+
+    def join(self):
+        """Make the main stream wait for the internal streams (call before recording an end-of-region event)."""
+        self._check(self._lib.roftb_join(self._h), "roftb_join")
 
     PHASES = ("rank", "flow_pass_a", "median_select", "flow_pass_b", "epilogue", "mask_sync", "ukf")
 

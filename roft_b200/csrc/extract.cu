@@ -85,7 +85,7 @@ __device__ __forceinline__ uint32_t eval_tile(const ExtractArgs& a, int t, int w
             bool ok;
             if (MODE == kModeExport) {
                 const char* fbase = reinterpret_cast<const char*>(a.flow) + (long long)t * a.flow_stride * (g.flow_s16 ? 2 : 4);
-                const float2 f = load_flow(fbase, g.flow_s16, (long long)(v / g.grid) * g.Wf + ((u0 + i) / g.grid), g.scale);
+                const float2 f = load_flow(fbase, (long long)(v / g.grid) * g.Wf + ((u0 + i) / g.grid), g);
                 fxv[4 * j + i] = f.x;
                 fyv[4 * j + i] = f.y;
                 ok = flow_valid(f.x, f.y) && d > 0.f && (double)d < a.max_depth;

@@ -81,6 +81,71 @@ __global__ void __launch_bounds__(kThreads) k_wt_scan(int32_t* __restrict__ wt_c
     if (total && threadIdx.x == 0) total[t] = carry;
 }
 
+// ---- worklist of non-empty warp tiles ------------------------------------------------------------
+// Masks cover a compact fraction of the frame, so every streaming kernel iterates over the list of
+// non-empty warp tiles of its track instead of the whole plane: no time is spent on empty tiles and
+// the work is evenly spread over the blocks of a track regardless of where the object is.
+// k_tile_count packs, per warp tile, (#bytes > 0) | (#bytes > thr) << 16.
+__global__ void __launch_bounds__(kThreads) k_tile_count(const uint8_t* __restrict__ plane, long long stride, int thr, int HW,
+                                                        int n_warp_tiles, int32_t* __restrict__ wt_count,
+                                                        const int32_t* __restrict__ active, int active_stride) {
+    const int t = blockIdx.y;
+    if (active && !active[(long long)t * active_stride]) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t thr4 = (uint32_t)thr * 0x01010101u;
+    const uint32_t* mq = reinterpret_cast<const uint32_t*>(plane + (long long)t * stride);
+    const int nq = HW >> 2;
+    for (int wt = blockIdx.x * (kThreads / 32) + warp; wt < n_warp_tiles; wt += gridDim.x * (kThreads / 32)) {
+        int c0 = 0, c1 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = wt * 128 + j * 32 + lane;
+            const uint32_t m = q < nq ? ld_nc_u32(mq + q) : 0u;
+            c0 += __popc(__vcmpne4(m, 0u)) >> 3;
+            c1 += __popc(__vcmpgtu4(m, thr4)) >> 3;
+        }
+        c0 = warp_sum(c0);
+        c1 = warp_sum(c1);
+        if (lane == 0) wt_count[(long long)t * n_warp_tiles + wt] = c0 | (c1 << 16);
+    }
+}
+
+// one block per track: wt_count <- exclusive prefix of the (> thr) counts (row-major rank base), wt_list <- ids of
+// the warp tiles holding any non-zero byte (ascending), wt_n <- their number
+__global__ void __launch_bounds__(kThreads) k_tile_compact(int32_t* __restrict__ wt_count, int32_t* __restrict__ wt_list,
+                                                          int32_t* __restrict__ wt_n, int n_warp_tiles,
+                                                          const int32_t* __restrict__ active, int active_stride) {
+    const int t = blockIdx.x;
+    if (active && !active[(long long)t * active_stride]) return;
+    __shared__ int sh_r[kThreads / 32], sh_l[kThreads / 32];
+    __shared__ int carry_r, carry_l;
+    int32_t* cnt = wt_count + (long long)t * n_warp_tiles;
+    int32_t* list = wt_list + (long long)t * n_warp_tiles;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { carry_r = 0; carry_l = 0; }
+    __syncthreads();
+    for (int base = 0; base < n_warp_tiles; base += kThreads) {
+        const int i = base + threadIdx.x;
+        const int packed = i < n_warp_tiles ? cnt[i] : 0;
+        const int vr = packed >> 16;
+        const int vl = (packed & 0xffff) ? 1 : 0;
+        const int ir = warp_scan_incl(vr, lane), il = warp_scan_incl(vl, lane);
+        if (lane == 31) { sh_r[warp] = ir; sh_l[warp] = il; }
+        __syncthreads();
+        int wr = 0, wl = 0;
+        for (int w = 0; w < warp; ++w) { wr += sh_r[w]; wl += sh_l[w]; }
+        const int cr = carry_r, cl = carry_l;
+        if (i < n_warp_tiles) {
+            cnt[i] = cr + wr + ir - vr;
+            if (vl) list[cl + wl + il - 1] = i;
+        }
+        __syncthreads();
+        if (threadIdx.x == kThreads - 1) { carry_r = cr + wr + ir; carry_l = cl + wl + il; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) wt_n[t] = carry_l;
+}
+
 // ---- the streaming pass ---------------------------------------------------------------------
 // PASS 0 (A): innovation norms -> compact list.   PASS 1 (B): weighted normal-equation accumulation.
 // FAST: float2 flow at full resolution (vector loads); otherwise generic per-pixel flow fetch.
@@ -89,8 +154,10 @@ struct PassArgs {
     FrameTable ft;
     const uint8_t* seg; long long seg_stride; int thr;
     const VelCtl* ctl;
-    int tiles_per_block, n_block_tiles, n_warp_tiles;
-    const int32_t* wt_prefix;
+    int n_warp_tiles;
+    const int32_t* wt_prefix;   // [T][n_warp_tiles] row-major rank base of each warp tile
+    const int32_t* wt_list;     // [T][n_warp_tiles] non-empty warp tiles
+    const int32_t* wt_n;        // [T]
     float* norms; uint32_t* norm_count;
     const WeightParams* wp; int weight_flow;
     const double* x_pred; int x_stride;
@@ -102,7 +169,7 @@ struct PassArgs {
 // AT = accumulation type of pass B: float (per-pixel terms and partial sums in FP32) or double (per-pixel terms
 // and sums in FP64: forward error ~ cond(Lambda) * 1e-16 instead of cond * 1e-7 / sqrt(N)).
 template <int PASS, bool FAST, typename AT>
-__global__ void __launch_bounds__(kThreads) k_flow_pass(PassArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) k_flow_pass(PassArgs a) {
     const int t = blockIdx.y;
     const VelCtl c = a.ctl[t];
     if (!c.enable) return;
@@ -131,10 +198,10 @@ __global__ void __launch_bounds__(kThreads) k_flow_pass(PassArgs a) {
         for (int i = 0; i < kNAcc; ++i) acc[i] = (AT)0;
     }
 
-    const int tile_end = min((int)(blockIdx.x + 1) * a.tiles_per_block, a.n_block_tiles);
-    for (int tile = blockIdx.x * a.tiles_per_block; tile < tile_end; ++tile) {
-        const int wt = tile * (kThreads / 32) + warp;
-        if (wt >= a.n_warp_tiles) break;  // warp-uniform
+    const int n_list = a.wt_n[t];
+    const int32_t* list = a.wt_list + (long long)t * a.n_warp_tiles;
+    for (int li = blockIdx.x * (kThreads / 32) + warp; li < n_list; li += gridDim.x * (kThreads / 32)) {
+        const int wt = list[li];  // warp-uniform
         uint32_t sel[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -166,98 +233,104 @@ __global__ void __launch_bounds__(kThreads) k_flow_pass(PassArgs a) {
         const uint32_t any = sel[0] | sel[1] | sel[2] | sel[3];
         if (!__any_sync(0xffffffffu, any != 0u)) continue;
 
-        // issue every load of the tile before touching the data (up to 12 x 128-bit in flight per lane)
-        float4 D[4], F0[4], F1[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int q = wt * 128 + j * 32 + lane;
-            const bool on = sel[j] != 0u;
-            D[j] = get4(dq + q, on);
-            if (FAST) {
-                F0[j] = get4(fq + 2 * q, on);
-                F1[j] = get4(fq + 2 * q + 1, on);
-            }
-        }
-
         float nrm[16];
         uint32_t vmask = 0;  // bit (4j+i): pixel passed the gates
+        // loads are issued a batch of quads at a time, all before the data is touched (FP32: 12 x 128-bit in
+        // flight per lane; the FP64 accumulation variant halves the batch to stay within 128 registers)
+        constexpr int QB = (PASS == 1 && sizeof(AT) == 8) ? 2 : 4;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (sel[j] == 0u) continue;
-            const int px = (wt * 128 + j * 32 + lane) << 2;
-            const int v = px / g.W;
-            const int u0 = px - v * g.W;
-            // normalised coordinates from FP64 intrinsics (a rounded 1/fx would bias every pixel the same way)
-            const double yhd = ((double)v - a.cyd) * a.inv_fyd;
-            const double xh0d = ((double)u0 - a.cxd) * a.inv_fxd;
-            const float yh = (float)yhd;
+        for (int jb = 0; jb < 4; jb += QB) {
+            float4 D[QB], F0[QB], F1[QB];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (!((sel[j] >> (8 * i)) & 1u)) continue;
-                const float d = comp(D[j], i);
-                float dx, dy;
+            for (int jj = 0; jj < QB; ++jj) {
+                const int q = wt * 128 + (jb + jj) * 32 + lane;
+                const bool on = sel[jb + jj] != 0u;
+                D[jj] = get4(dq + q, on);
                 if (FAST) {
-                    const float4 f = i < 2 ? F0[j] : F1[j];
-                    dx = __fdiv_rn((i & 1) ? f.z : f.x, g.scale);
-                    dy = __fdiv_rn((i & 1) ? f.w : f.y, g.scale);
-                } else {
-                    const int u = u0 + i;
-                    const float2 f = load_flow(fbase, g.flow_s16, (long long)(v / g.grid) * g.Wf + (u / g.grid), g.scale);
-                    dx = f.x;
-                    dy = f.y;
+                    F0[jj] = get4(fq + 2 * q, on);
+                    F1[jj] = get4(fq + 2 * q + 1, on);
                 }
-                // hpp:252 gates
-                if (!(flow_valid(dx, dy) && d > 0.f && (double)d < g.max_depth)) continue;
-                const double xhd = fma((double)i, a.inv_fxd, xh0d);
-                const float xh = (float)xhd;
-                const float ia = __fdiv_rn(1.0f, d);
-                const float l1[5] = {ia, -xh * ia, -xh * yh, 1.0f + xh * xh, -yh};
-                const float l2[5] = {ia, -yh * ia, -(1.0f + yh * yh), xh * yh, xh};
-                const float p1 = l1[0] * x[0] + l1[1] * x[2] + l1[2] * x[3] + l1[3] * x[4] + l1[4] * x[5];
-                const float p2 = l2[0] * x[1] + l2[1] * x[2] + l2[2] * x[3] + l2[3] * x[4] + l2[4] * x[5];
-                const float n1 = dx - c1 * p1, n2 = dy - c2 * p2;
-                const float nr = sqrtf(n1 * n1 + n2 * n2);
-                if (PASS == 0) {
-                    nrm[4 * j + i] = nr;
-                    vmask |= 1u << (4 * j + i);
-                } else {
-                    float l = 1.0f;
-                    if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
-                    AT e1[5], e2[5];
-                    if (sizeof(AT) == 8) {
-                        // FP64 per-pixel terms: 1/d refined from the FP32 reciprocal by one Newton step
-                        double r = (double)ia;
-                        r = r * (2.0 - (double)d * r);
-                        e1[0] = (AT)r; e1[1] = (AT)(-xhd * r); e1[2] = (AT)(-xhd * yhd); e1[3] = (AT)(1.0 + xhd * xhd); e1[4] = (AT)(-yhd);
-                        e2[0] = (AT)r; e2[1] = (AT)(-yhd * r); e2[2] = (AT)(-(1.0 + yhd * yhd)); e2[3] = (AT)(xhd * yhd); e2[4] = (AT)xhd;
+            }
+#pragma unroll
+            for (int jj = 0; jj < QB; ++jj) {
+                const int j = jb + jj;
+                if (sel[j] == 0u) continue;
+                const int px = (wt * 128 + j * 32 + lane) << 2;
+                const int v = px / g.W;
+                const int u0 = px - v * g.W;
+                // normalised coordinates from FP64 intrinsics (a rounded 1/fx would bias every pixel the same way)
+                const double yhd = ((double)v - a.cyd) * a.inv_fyd;
+                const double xh0d = ((double)u0 - a.cxd) * a.inv_fxd;
+                const float yh = (float)yhd;
+                const float xh0 = (float)xh0d;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!((sel[j] >> (8 * i)) & 1u)) continue;
+                    const float d = comp(D[jj], i);
+                    float dx, dy;
+                    if (FAST) {
+                        const float4 f = i < 2 ? F0[jj] : F1[jj];
+                        dx = div_scale((i & 1) ? f.z : f.x, g);
+                        dy = div_scale((i & 1) ? f.w : f.y, g);
                     } else {
+                        const int u = u0 + i;
+                        const float2 f = load_flow(fbase, (long long)(v / g.grid) * g.Wf + (u / g.grid), g);
+                        dx = f.x;
+                        dy = f.y;
+                    }
+                    // hpp:252 gates
+                    if (!(flow_valid(dx, dy) && d > 0.f && d < g.max_depth_f)) continue;
+                    const float xh = fmaf((float)i, g.inv_fx, xh0);
+                    const float ia = rcp_approx(d);
+                    const float l1[5] = {ia, -xh * ia, -xh * yh, 1.0f + xh * xh, -yh};
+                    const float l2[5] = {ia, -yh * ia, -(1.0f + yh * yh), xh * yh, xh};
+                    const float p1 = l1[0] * x[0] + l1[1] * x[2] + l1[2] * x[3] + l1[3] * x[4] + l1[4] * x[5];
+                    const float p2 = l2[0] * x[1] + l2[1] * x[2] + l2[2] * x[3] + l2[3] * x[4] + l2[4] * x[5];
+                    const float n1 = dx - c1 * p1, n2 = dy - c2 * p2;
+                    const float nr = sqrt_approx(n1 * n1 + n2 * n2);
+                    if (PASS == 0) {
+                        nrm[4 * j + i] = nr;
+                        vmask |= 1u << (4 * j + i);
+                    } else {
+                        float l = 1.0f;
+                        if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
+                        AT e1[5], e2[5];
+                        if (sizeof(AT) == 8) {
+                            // FP64 per-pixel terms: 1/d refined from the FP32 reciprocal by one Newton step
+                            const double xhd = fma((double)i, a.inv_fxd, xh0d);
+                            double r = (double)ia;
+                            r = r * (2.0 - (double)d * r);
+                            e1[0] = (AT)r; e1[1] = (AT)(-xhd * r); e1[2] = (AT)(-xhd * yhd); e1[3] = (AT)(1.0 + xhd * xhd); e1[4] = (AT)(-yhd);
+                            e2[0] = (AT)r; e2[1] = (AT)(-yhd * r); e2[2] = (AT)(-(1.0 + yhd * yhd)); e2[3] = (AT)(xhd * yhd); e2[4] = (AT)xhd;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) {
+                                e1[k] = (AT)l1[k];
+                                e2[k] = (AT)l2[k];
+                            }
+                        }
+                        AT w1[5], w2[5];
 #pragma unroll
                         for (int k = 0; k < 5; ++k) {
-                            e1[k] = (AT)l1[k];
-                            e2[k] = (AT)l2[k];
+                            w1[k] = (AT)l * e1[k];
+                            w2[k] = (AT)l * e2[k];
                         }
-                    }
-                    AT w1[5], w2[5];
+                        int o = 0;
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        w1[k] = (AT)l * e1[k];
-                        w2[k] = (AT)l * e2[k];
-                    }
-                    int o = 0;
+                        for (int r = 0; r < 5; ++r)
 #pragma unroll
-                    for (int r = 0; r < 5; ++r)
+                            for (int s = r; s < 5; ++s) {
+                                acc[o] = fma(w1[r], e1[s], acc[o]);
+                                acc[15 + o] = fma(w2[r], e2[s], acc[15 + o]);
+                                ++o;
+                            }
 #pragma unroll
-                        for (int s = r; s < 5; ++s) {
-                            acc[o] = fma(w1[r], e1[s], acc[o]);
-                            acc[15 + o] = fma(w2[r], e2[s], acc[15 + o]);
-                            ++o;
+                        for (int k = 0; k < 5; ++k) {
+                            acc[30 + k] = fma(w1[k], (AT)dx, acc[30 + k]);
+                            acc[35 + k] = fma(w2[k], (AT)dy, acc[35 + k]);
                         }
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        acc[30 + k] = fma(w1[k], (AT)dx, acc[30 + k]);
-                        acc[35 + k] = fma(w2[k], (AT)dy, acc[35 + k]);
+                        acc[40] += (AT)1;
                     }
-                    acc[40] += (AT)1;
                 }
             }
         }
@@ -621,19 +694,28 @@ int launch_wt_scan(int32_t* wt_count, int n_warp_tiles, int n_items, int32_t* to
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+int launch_tile_list(const uint8_t* plane, long long stride, int thr, int HW, int n_items, int32_t* wt_count, int32_t* wt_list,
+                     int32_t* wt_n, const int32_t* active, int active_stride, cudaStream_t s) {
+    const int n_warp_tiles = (HW + kWarpTilePx - 1) / kWarpTilePx;
+    const int n_block_tiles = (HW + kBlockTilePx - 1) / kBlockTilePx;
+    const int bx = max(1, min(n_block_tiles, (148 * 8 + n_items - 1) / n_items));
+    ROFTB_LAUNCH(k_tile_count, dim3(bx, n_items), kThreads, 0, s, plane, stride, thr, HW, n_warp_tiles, wt_count, active,
+                 active_stride);
+    ROFTB_LAUNCH(k_tile_compact, n_items, kThreads, 0, s, wt_count, wt_list, wt_n, n_warp_tiles, active, active_stride);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     const int T = a.n_tracks;
     const Geom& g = a.g;
     const int n_warp_tiles = (g.HW + kWarpTilePx - 1) / kWarpTilePx;
     const int n_block_tiles = (g.HW + kBlockTilePx - 1) / kBlockTilePx;
-    // blocks per track: fill the machine (>= ~6 CTAs per SM in total) but amortise the block reduction
-    int bpt = max(1, (148 * 6 + T - 1) / T);
+    // blocks per track: several waves over the machine in total; each warp walks the track's tile list with
+    // a stride of (blocks x warps)
+    int bpt = max(1, (148 * 16 + T - 1) / T);
     bpt = min(bpt, min(n_block_tiles, a.max_blocks));
-    const int tpb = (n_block_tiles + bpt - 1) / bpt;
-    bpt = (n_block_tiles + tpb - 1) / tpb;
 
     if (a.prof) cudaEventRecord(a.prof[0], s);
-    if (g.stride > 1) launch_mask_rank(a.seg, a.seg_stride, a.thr, g.HW, T, a.wt_count, nullptr, a.ctl, s);
     if (a.prof) cudaEventRecord(a.prof[1], s);
     PassArgs pa;
     pa.g = g;
@@ -642,10 +724,10 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     pa.seg_stride = a.seg_stride;
     pa.thr = a.thr;
     pa.ctl = a.ctl;
-    pa.tiles_per_block = tpb;
-    pa.n_block_tiles = n_block_tiles;
     pa.n_warp_tiles = n_warp_tiles;
     pa.wt_prefix = a.wt_count;
+    pa.wt_list = a.wt_list;
+    pa.wt_n = a.wt_n;
     pa.norms = a.norms;
     pa.norm_count = a.norm_count;
     pa.wp = a.wp;

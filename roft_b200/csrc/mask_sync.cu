@@ -174,16 +174,15 @@ __global__ void __launch_bounds__(kThreads) k_warp_init(const WarpPlan* __restri
 // Chase one source pixel through the flow chain (hpp:249-278). Returns the destination linear index or -1.
 __device__ __forceinline__ int chase(const Geom& g, const FrameTable& ft, const WarpPlan& p, int t, int u, int v) {
     float tx = (float)u, ty = (float)v;
-    const float gs = (float)g.grid;
     for (int j = 0; j < p.n_flows; ++j) {
         const int ix = cvt_int(tx), iy = cvt_int(ty);
         if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) return -1;
-        const int fr = cvt_int(__fdiv_rn(ty, gs));
-        const int fc = cvt_int(__fdiv_rn(tx, gs));
+        const int fr = cvt_int(div_grid(ty, g));
+        const int fc = cvt_int(div_grid(tx, g));
         const int slot = p.flow_slot[j];
         const char* base = reinterpret_cast<const char*>(ft.flow[slot]) +
                            (long long)t * ft.flow_stride * (g.flow_s16 ? 2 : 4);
-        const float2 f = load_flow(base, g.flow_s16, (long long)fr * g.Wf + fc, g.scale);
+        const float2 f = load_flow(base, (long long)fr * g.Wf + fc, g);
         tx = __fadd_rn(tx, f.x);
         ty = __fadd_rn(ty, f.y);
     }
@@ -195,7 +194,10 @@ __device__ __forceinline__ int chase(const Geom& g, const FrameTable& ft, const 
 __global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft, const WarpPlan* __restrict__ plan,
                                                           const uint8_t* __restrict__ new_mask, long long new_stride,
                                                           const uint8_t* __restrict__ state_src,
-                                                          uint8_t* __restrict__ state_dst, int32_t* __restrict__ winner) {
+                                                          uint8_t* __restrict__ state_dst, int32_t* __restrict__ winner,
+                                                          const int32_t* __restrict__ s_list, const int32_t* __restrict__ s_n,
+                                                          const int32_t* __restrict__ n_list, const int32_t* __restrict__ n_n,
+                                                          int n_warp_tiles) {
     const int t = blockIdx.y;
     __shared__ WarpPlan sp;
     if (threadIdx.x == 0) sp = plan[t];
@@ -207,23 +209,35 @@ __global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft
     const int nq = g.HW >> 2;
     const uint8_t uval = (uint8_t)sp.uniform_val;
     const bool general = (sp.uniform_val == 0);
-    // one quad (4 px, one 32-bit word) per lane per iteration: fully coalesced mask reads
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
-        uint32_t m = ld_nc_u32(reinterpret_cast<const uint32_t*>(src) + q);
-        if (sp.zero_origin && q == 0) m &= 0xffffff00u;
-        if (m == 0u) continue;
-        const int px = q << 2;
-        const int v = px / g.W;
-        const int u0 = px - v * g.W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // walk the worklist of non-empty warp tiles of the source plane; one quad (4 px) per lane per sub-tile
+    const int32_t* list = (sp.src_new ? n_list : s_list) + (long long)t * n_warp_tiles;
+    const int n_list_items = (sp.src_new ? n_n : s_n)[t];
+    for (int li = blockIdx.x * (kThreads / 32) + warp; li < n_list_items; li += gridDim.x * (kThreads / 32)) {
+        const int wt = list[li];
+        uint32_t m[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (((m >> (8 * i)) & 0xffu) == 0u) continue;
-            const int d = chase(g, ft, sp, t, u0 + i, v);
-            if (d < 0) continue;
-            if (general)
-                atomicMax(win + d, px + i);
-            else
-                dst[d] = uval;
+        for (int j = 0; j < 4; ++j) {
+            const int q = wt * 128 + j * 32 + lane;
+            m[j] = q < nq ? ld_nc_u32(reinterpret_cast<const uint32_t*>(src) + q) : 0u;
+            if (sp.zero_origin && q == 0) m[j] &= 0xffffff00u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (m[j] == 0u) continue;
+            const int px = (wt * 128 + j * 32 + lane) << 2;
+            const int v = px / g.W;
+            const int u0 = px - v * g.W;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (((m[j] >> (8 * i)) & 0xffu) == 0u) continue;
+                const int d = chase(g, ft, sp, t, u0 + i, v);
+                if (d < 0) continue;
+                if (general)
+                    atomicMax(win + d, px + i);
+                else
+                    dst[d] = uval;
+            }
         }
     }
 }
@@ -287,8 +301,9 @@ int launch_mask_sync(const MaskSyncArgs& a, cudaStream_t s, bool planned) {
     int bq = (nq + kThreads - 1) / kThreads;
     int targetq = max(1, (148 * 16 + T - 1) / T);
     bq = max(1, min(bq, targetq));
-    ROFTB_LAUNCH(k_warp_scatter, dim3(bq, T), kThreads, 0, s, a.g, a.ft, a.plan, a.new_mask, a.new_stride, a.state_src,
-                 a.state_dst, a.winner);
+    int bs = max(1, min((a.n_warp_tiles + 7) / 8, (148 * 16 + T - 1) / T));
+    ROFTB_LAUNCH(k_warp_scatter, dim3(bs, T), kThreads, 0, s, a.g, a.ft, a.plan, a.new_mask, a.new_stride, a.state_src,
+                 a.state_dst, a.winner, a.s_list, a.s_n, a.n_list, a.n_n, a.n_warp_tiles);
     ROFTB_LAUNCH(k_warp_gather, dim3(bq, T), kThreads, 0, s, a.plan, a.new_mask, a.new_stride, a.state_src, a.state_dst,
                  a.winner, HW);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

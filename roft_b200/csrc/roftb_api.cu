@@ -6,6 +6,7 @@
 //   CartesianQuaternionMeasurement::freeze mode machine   src/roft-lib/src/CartesianQuaternionMeasurement.cpp:92-348
 // Everything value-dependent (empty masks, observability, the filters) runs on the device, so a step
 // never synchronises with the GPU.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <deque>
@@ -50,7 +51,9 @@ struct roftb_ctx {
     size_t HW = 0;
     size_t flow_elems = 0;  // scalar elements per track
     int dev = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr;
+    cudaEvent_t vel_event[8], ukf_event[8], join_event = nullptr;
+    bool ukf_event_used[8];
     std::string err;
     long long launches0 = 0;
 
@@ -65,7 +68,12 @@ struct roftb_ctx {
     WeightParams* wp = nullptr;
     double* partials = nullptr;
     int max_blocks = 0;
-    int32_t* wt_count = nullptr;
+    int32_t* wt_count = nullptr;    // state-mask worklist: rank base, list, length
+    int32_t* wt_list = nullptr;
+    int32_t* wt_n = nullptr;
+    int32_t* nl_count = nullptr;    // newly delivered mask worklist
+    int32_t* nl_list = nullptr;
+    int32_t* nl_n = nullptr;
     int32_t* wt_count2 = nullptr;
     int n_warp_tiles = 0;
     MaskStat* stat = nullptr;
@@ -95,7 +103,7 @@ struct roftb_ctx {
 
     // optional per-phase device timing (bench.py roofline): 8 events per in-flight step
     bool prof_on = false;
-    cudaEvent_t prof_ev[kCtlRing][8];
+    cudaEvent_t prof_ev[kCtlRing][9];
     bool prof_used[kCtlRing];
     double prof_ms[7];
     long long prof_steps = 0;
@@ -149,9 +157,20 @@ void fill_geom(roftb_ctx* ctx) {
     g.Wf = c.width / c.flow_grid; g.Hf = c.height / c.flow_grid;
     g.flow_s16 = c.flow_format == ROFTB_FLOW_S16;
     g.scale = c.flow_scale;
+    g.inv_scale = 1.0f / c.flow_scale;
+    auto mode_of = [](float v) {
+        if (v == 1.0f) return 0;
+        int e = 0;
+        return std::frexp(v, &e) == 0.5f ? 1 : 2;  // power of two
+    };
+    g.scale_mode = mode_of(c.flow_scale);
+    g.inv_grid = 1.0f / (float)c.flow_grid;
+    g.grid_mode = mode_of((float)c.flow_grid);
     g.cx = (float)c.cx; g.cy = (float)c.cy;
     g.inv_fx = (float)(1.0 / c.fx); g.inv_fy = (float)(1.0 / c.fy);
     g.max_depth = c.depth_maximum;
+    g.max_depth_f = (float)c.depth_maximum;
+    if ((double)g.max_depth_f < c.depth_maximum) g.max_depth_f = std::nextafterf(g.max_depth_f, INFINITY);
     g.stride = c.subsampling_radius;
 }
 
@@ -216,7 +235,10 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     for (int i = 0; i < kCtlRing; ++i) {
         ctx->ctl_event_used[i] = false;
         ctx->prof_used[i] = false;
-        for (int j = 0; j < 8; ++j) ctx->prof_ev[i][j] = nullptr;
+        ctx->ukf_event_used[i] = false;
+        ctx->vel_event[i] = nullptr;
+        ctx->ukf_event[i] = nullptr;
+        for (int j = 0; j < 9; ++j) ctx->prof_ev[i][j] = nullptr;
     }
     for (int j = 0; j < 7; ++j) ctx->prof_ms[j] = 0.0;
     memset(&ctx->ft, 0, sizeof(ctx->ft));
@@ -238,10 +260,16 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(cudaSetDevice(ctx->dev));
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->ukf_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->join_event, cudaEventDisableTiming));
+    for (int i = 0; i < kCtlRing; ++i) {
+        CKC(cudaEventCreateWithFlags(&ctx->vel_event[i], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&ctx->ukf_event[i], cudaEventDisableTiming));
+    }
     CKC(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
     for (int i = 0; i < kCtlRing; ++i) CKC(cudaEventCreateWithFlags(&ctx->ctl_event[i], cudaEventDisableTiming));
     for (int i = 0; i < kCtlRing; ++i)
-        for (int j = 0; j < 8; ++j) CKC(cudaEventCreate(&ctx->prof_ev[i][j]));
+        for (int j = 0; j < 9; ++j) CKC(cudaEventCreate(&ctx->prof_ev[i][j]));
     CKC(dalloc(&ctx->mask_state[0], T * HW));
     CKC(dalloc(&ctx->mask_state[1], T * HW));
     CKC(dalloc(&ctx->winner, T * HW));
@@ -253,6 +281,11 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(dalloc(&ctx->partials, (size_t)T * ctx->max_blocks * kNAcc));
     CKC(dalloc(&ctx->wt_count, (size_t)T * ctx->n_warp_tiles));
     CKC(dalloc(&ctx->wt_count2, (size_t)T * ctx->n_warp_tiles));
+    CKC(dalloc(&ctx->wt_list, (size_t)T * ctx->n_warp_tiles));
+    CKC(dalloc(&ctx->wt_n, (size_t)T));
+    CKC(dalloc(&ctx->nl_count, (size_t)T * ctx->n_warp_tiles));
+    CKC(dalloc(&ctx->nl_list, (size_t)T * ctx->n_warp_tiles));
+    CKC(dalloc(&ctx->nl_n, (size_t)T));
     CKC(dalloc(&ctx->stat, (size_t)T));
     CKC(dalloc(&ctx->plan, (size_t)T));
     CKC(dalloc(&ctx->fbuf, (size_t)T));
@@ -269,8 +302,8 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(dalloc(&ctx->d_eta, (size_t)T * 6));
     CKC(dalloc(&ctx->d_wctl, (size_t)T));
     CKC(dalloc(&ctx->d_vctl, (size_t)T));
-    CKC(dalloc(&ctx->d_ops, (size_t)T * kMaxUkfOps));
-    CKC(dalloc(&ctx->d_nops, (size_t)T));
+    CKC(dalloc(&ctx->d_ops, (size_t)T * kMaxUkfOps * kCtlRing));
+    CKC(dalloc(&ctx->d_nops, (size_t)T * kCtlRing));
     CKC(cudaMallocHost(&ctx->h_wctl, sizeof(WarpCtl) * T * kCtlRing));
     CKC(cudaMallocHost(&ctx->h_vctl, sizeof(VelCtl) * T * kCtlRing));
     CKC(cudaMallocHost(&ctx->h_ops, sizeof(UkfOp) * T * kMaxUkfOps * kCtlRing));
@@ -302,7 +335,7 @@ void roftb_destroy(roftb_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->winner, ctx->norms, ctx->norm_count, ctx->hist, ctx->sel,
-                     ctx->wp, ctx->partials, ctx->wt_count, ctx->wt_count2, ctx->stat, ctx->plan, ctx->fbuf, ctx->v_mean,
+                     ctx->wp, ctx->partials, ctx->wt_count, ctx->wt_count2, ctx->wt_list, ctx->wt_n, ctx->nl_count, ctx->nl_list, ctx->nl_n, ctx->stat, ctx->plan, ctx->fbuf, ctx->v_mean,
                      ctx->v_cov, ctx->p_mean, ctx->p_cov, ctx->pb_mean, ctx->pb_cov, ctx->vel_hist, ctx->q_diag,
                      ctx->d_count, ctx->d_lambda, ctx->d_eta, ctx->d_wctl, ctx->d_vctl, ctx->d_ops, ctx->d_nops,
                      ctx->stage_depth, ctx->stage_flow, ctx->stage_mask, ctx->thr_tmp};
@@ -315,8 +348,14 @@ void roftb_destroy(roftb_ctx* ctx) {
     for (int i = 0; i < kCtlRing; ++i)
         if (ctx->ctl_event[i]) cudaEventDestroy(ctx->ctl_event[i]);
     for (int i = 0; i < kCtlRing; ++i)
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 9; ++j)
             if (ctx->prof_ev[i][j]) cudaEventDestroy(ctx->prof_ev[i][j]);
+    for (int i = 0; i < kCtlRing; ++i) {
+        if (ctx->vel_event[i]) cudaEventDestroy(ctx->vel_event[i]);
+        if (ctx->ukf_event[i]) cudaEventDestroy(ctx->ukf_event[i]);
+    }
+    if (ctx->join_event) cudaEventDestroy(ctx->join_event);
+    if (ctx->ukf_stream) { cudaStreamSynchronize(ctx->ukf_stream); cudaStreamDestroy(ctx->ukf_stream); }
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -328,15 +367,26 @@ int roftb_sync(roftb_ctx* ctx) {
     CK(cudaSetDevice(ctx->dev));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->ukf_stream));
+    return 0;
+}
+
+int roftb_join(roftb_ctx* ctx) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaEventRecord(ctx->join_event, ctx->ukf_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->join_event, 0));
     return 0;
 }
 
 static void prof_collect(roftb_ctx* ctx, int slot) {
     if (!ctx->prof_used[slot]) return;
-    cudaEventSynchronize(ctx->prof_ev[slot][7]);
+    cudaEventSynchronize(ctx->prof_ev[slot][6]);
+    cudaEventSynchronize(ctx->prof_ev[slot][8]);
     for (int j = 0; j < 7; ++j) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ctx->prof_ev[slot][j], ctx->prof_ev[slot][j + 1]) == cudaSuccess) ctx->prof_ms[j] += ms;
+        const int e0 = j < 6 ? j : 7, e1 = j < 6 ? j + 1 : 8;
+        if (cudaEventElapsedTime(&ms, ctx->prof_ev[slot][e0], ctx->prof_ev[slot][e1]) == cudaSuccess) ctx->prof_ms[j] += ms;
     }
     ctx->prof_steps++;
     ctx->prof_used[slot] = false;
@@ -363,6 +413,7 @@ int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mea
     const int T = ctx->T;
     CK(cudaSetDevice(ctx->dev));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->ukf_stream));
     // ROFTFilter::initialization_step (ROFTFilter.cpp:216-237)
     std::vector<double> pm((size_t)T * 13, 0.0), pc((size_t)T * 144, 0.0), vm((size_t)T * 6, 0.0), vc((size_t)T * 36, 0.0);
     for (int t = 0; t < T; ++t) {
@@ -464,6 +515,7 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
 
     // ---- host state machines -> control blocks ------------------------------------------------
     if (ctx->ctl_event_used[cslot]) CK(cudaEventSynchronize(ctx->ctl_event[cslot]));
+    if (ctx->ukf_event_used[cslot]) CK(cudaEventSynchronize(ctx->ukf_event[cslot]));
     WarpCtl* wc = ctx->h_wctl + (size_t)cslot * T;
     VelCtl* vc = ctx->h_vctl + (size_t)cslot * T;
     UkfOp* ops = ctx->h_ops + (size_t)cslot * T * kMaxUkfOps;
@@ -595,21 +647,35 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
     cudaStream_t s = ctx->stream;
     CK(cudaMemcpyAsync(ctx->d_wctl, wc, sizeof(WarpCtl) * T, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_vctl, vc, sizeof(VelCtl) * T, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_ops, ops, sizeof(UkfOp) * T * kMaxUkfOps, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_nops, nops, sizeof(int32_t) * T, cudaMemcpyHostToDevice, s));
+    UkfOp* d_ops = ctx->d_ops + (size_t)cslot * T * kMaxUkfOps;
+    int32_t* d_nops = ctx->d_nops + (size_t)cslot * T;
+    CK(cudaMemcpyAsync(d_ops, ops, sizeof(UkfOp) * T * kMaxUkfOps, cudaMemcpyHostToDevice, ctx->ukf_stream));
+    CK(cudaMemcpyAsync(d_nops, nops, sizeof(int32_t) * T, cudaMemcpyHostToDevice, ctx->ukf_stream));
     CK(cudaEventRecord(ctx->ctl_event[cslot], s));
+    // the pose UKF trails on its own stream; keep it within 4 steps of the streaming kernels (velocity-history ring)
+    {
+        const int lag = (cslot + kCtlRing - 4) % kCtlRing;
+        if (ctx->ukf_event_used[lag]) CK(cudaStreamWaitEvent(s, ctx->ukf_event[lag], 0));
+    }
     ctx->ctl_event_used[cslot] = true;
 
     // ---- device work: velocity (previous mask/depth, current flow), mask sync, pose UKF ---------
     const uint8_t* seg_prev = ctx->mask_state[ctx->mask_cur];
     uint8_t* seg_next = ctx->mask_state[ctx->mask_cur ^ 1];
+    // worklists of non-empty warp tiles: the state mask (velocity pass + propagation scatter) and the new mask
+    if (launch_tile_list(seg_prev, (long long)ctx->HW, 1, ctx->g.HW, T, ctx->wt_count, ctx->wt_list, ctx->wt_n, nullptr, 0, s))
+        return fail(ctx, "launch_tile_list failed");
+    if (any_new_mask &&
+        launch_tile_list(d_mask, mask_stride, 0, ctx->g.HW, T, ctx->nl_count, ctx->nl_list, ctx->nl_n,
+                         reinterpret_cast<const int32_t*>(ctx->d_wctl), (int)(sizeof(WarpCtl) / 4), s))
+        return fail(ctx, "launch_tile_list failed");
     {
         VelocityArgs a;
         memset(&a, 0, sizeof(a));
         a.g = ctx->g; a.ft = ctx->ft; a.n_tracks = T;
         a.seg = seg_prev; a.seg_stride = (long long)ctx->HW; a.thr = 1;  // cv::threshold(> 1) applied on load
         a.ctl = ctx->d_vctl; a.weight_flow = cfg.weight_flow;
-        a.wt_count = ctx->wt_count; a.norms = ctx->norms; a.norm_count = ctx->norm_count; a.hist = ctx->hist;
+        a.wt_count = ctx->wt_count; a.wt_list = ctx->wt_list; a.wt_n = ctx->wt_n; a.norms = ctx->norms; a.norm_count = ctx->norm_count; a.hist = ctx->hist;
         a.sel = ctx->sel; a.wp = ctx->wp; a.partials = ctx->partials; a.max_blocks = ctx->max_blocks;
         a.v_mean = ctx->v_mean; a.v_cov = ctx->v_cov; a.q_diag = ctx->q_diag;
         a.r_flow[0] = cfg.cov_flow[0]; a.r_flow[1] = cfg.cov_flow[1];
@@ -623,6 +689,26 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
             a.prof = ctx->prof_ev[cslot];
         }
         if (launch_velocity(a, s)) return fail(ctx, "launch_velocity failed");
+        CK(cudaEventRecord(ctx->vel_event[cslot], s));
+    }
+    {
+        // pose UKF on its own stream: it only needs this step's twist (vel_hist) and the host-built op list
+        cudaStream_t us = ctx->ukf_stream;
+        CK(cudaStreamWaitEvent(us, ctx->vel_event[cslot], 0));
+        UkfArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n_tracks = T; a.p = ctx->ukf_p;
+        a.ops = d_ops; a.n_ops = d_nops; a.max_ops = kMaxUkfOps;
+        a.mean = ctx->p_mean; a.cov = ctx->p_cov; a.buf_mean = ctx->pb_mean; a.buf_cov = ctx->pb_cov;
+        a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
+        if (ctx->prof_on) CK(cudaEventRecord(ctx->prof_ev[cslot][7], us));
+        if (launch_ukf(a, us)) return fail(ctx, "launch_ukf failed");
+        if (ctx->prof_on) {
+            CK(cudaEventRecord(ctx->prof_ev[cslot][8], us));
+            ctx->prof_used[cslot] = true;
+        }
+        CK(cudaEventRecord(ctx->ukf_event[cslot], us));
+        ctx->ukf_event_used[cslot] = true;
     }
     {
         MaskSyncArgs a;
@@ -632,22 +718,10 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
         a.state_src = seg_prev; a.state_dst = seg_next; a.winner = ctx->winner;
         a.ctl = ctx->d_wctl; a.stat = ctx->stat; a.plan = ctx->plan; a.fbuf = ctx->fbuf;
         a.segm_delay = cfg.segm_delay;
+        a.s_list = ctx->wt_list; a.s_n = ctx->wt_n; a.n_list = ctx->nl_list; a.n_n = ctx->nl_n; a.n_warp_tiles = ctx->n_warp_tiles;
         if (launch_mask_sync(a, s)) return fail(ctx, "launch_mask_sync failed");
         ctx->mask_cur ^= 1;
         if (ctx->prof_on) CK(cudaEventRecord(ctx->prof_ev[cslot][6], s));
-    }
-    {
-        UkfArgs a;
-        memset(&a, 0, sizeof(a));
-        a.n_tracks = T; a.p = ctx->ukf_p;
-        a.ops = ctx->d_ops; a.n_ops = ctx->d_nops; a.max_ops = kMaxUkfOps;
-        a.mean = ctx->p_mean; a.cov = ctx->p_cov; a.buf_mean = ctx->pb_mean; a.buf_cov = ctx->pb_cov;
-        a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
-        if (launch_ukf(a, s)) return fail(ctx, "launch_ukf failed");
-        if (ctx->prof_on) {
-            CK(cudaEventRecord(ctx->prof_ev[cslot][7], s));
-            ctx->prof_used[cslot] = true;
-        }
     }
     if (f->memory == ROFTB_MEM_HOST) CK(cudaEventRecord(ctx->copy_done, s));
     (void)any_vel;
@@ -662,6 +736,8 @@ int roftb_get_state(roftb_ctx* ctx, double* p_mean, double* p_cov, double* v_mea
     const size_t T = ctx->T;
     CK(cudaSetDevice(ctx->dev));
     cudaStream_t s = ctx->stream;
+    CK(cudaEventRecord(ctx->join_event, ctx->ukf_stream));
+    CK(cudaStreamWaitEvent(s, ctx->join_event, 0));
     if (p_mean) CK(cudaMemcpyAsync(p_mean, ctx->p_mean, T * 13 * 8, cudaMemcpyDeviceToHost, s));
     if (p_cov) CK(cudaMemcpyAsync(p_cov, ctx->p_cov, T * 144 * 8, cudaMemcpyDeviceToHost, s));
     if (v_mean) CK(cudaMemcpyAsync(v_mean, ctx->v_mean, T * 6 * 8, cudaMemcpyDeviceToHost, s));
@@ -770,6 +846,15 @@ int roftb_mask_sync(roftb_ctx* ctx, int32_t n_masks, const uint8_t* mask, const 
     a.ft.flow_stride = (long long)ctx->flow_elems;
     a.new_mask = d_mask; a.new_stride = (long long)HW;
     a.state_src = d_mask; a.state_dst = d_out; a.winner = d_win; a.plan = d_plan;
+    {
+        const int nwt = ctx->n_warp_tiles;
+        int32_t* cnt = tb.alloc<int32_t>(N * nwt);
+        int32_t* lst = tb.alloc<int32_t>(N * nwt);
+        int32_t* ln = tb.alloc<int32_t>(N);
+        if (!cnt || !lst || !ln) return fail(ctx, "roftb_mask_sync: out of device memory");
+        if (launch_tile_list(d_mask, (long long)HW, 0, ctx->g.HW, (int)N, cnt, lst, ln, nullptr, 0, s)) return fail(ctx, "launch_tile_list failed");
+        a.s_list = lst; a.s_n = ln; a.n_list = lst; a.n_n = ln; a.n_warp_tiles = nwt;
+    }
     if (launch_mask_sync(a, s, true)) return fail(ctx, "launch_mask_sync failed");
     if (out_raw) CK(cudaMemcpyAsync(out_raw, d_out, N * HW, cudaMemcpyDeviceToHost, s));
     if (out_thr) {
@@ -811,6 +896,8 @@ static int velocity_operator(roftb_ctx* ctx, int32_t n, const uint8_t* mask, con
     a.seg = d_mask; a.seg_stride = (long long)HW; a.thr = 0;  // previous_segmentation_ is used through findNonZero
     a.ctl = d_ctl; a.weight_flow = ctx->cfg.weight_flow;
     a.wt_count = tb.alloc<int32_t>(N * nwt);
+    a.wt_list = tb.alloc<int32_t>(N * nwt);
+    a.wt_n = tb.alloc<int32_t>(N);
     a.norms = tb.alloc<float>(N * HW);
     a.norm_count = tb.alloc<uint32_t>(N, true);
     a.hist = tb.alloc<uint32_t>(N * kSelBins, true);
@@ -830,6 +917,9 @@ static int velocity_operator(roftb_ctx* ctx, int32_t n, const uint8_t* mask, con
     if (!d_mask || !d_depth || !d_flow || !d_ctl || !d_x || !d_P || !a.wt_count || !a.norms || !a.norm_count || !a.hist ||
         !a.sel || !a.wp || !a.partials || !a.out_count || !a.out_lambda || !a.out_eta)
         return fail(ctx, "velocity operator: out of device memory");
+    if (!a.wt_list || !a.wt_n) return fail(ctx, "velocity operator: out of device memory");
+    if (launch_tile_list(d_mask, (long long)HW, 0, ctx->g.HW, (int)N, a.wt_count, a.wt_list, a.wt_n, nullptr, 0, s))
+        return fail(ctx, "launch_tile_list failed");
     if (launch_velocity(a, s)) return fail(ctx, "launch_velocity failed");
     if (update && x) CK(cudaMemcpyAsync(x, d_x, N * 6 * 8, cudaMemcpyDeviceToHost, s));
     if (update && P) CK(cudaMemcpyAsync(P, d_P, N * 36 * 8, cudaMemcpyDeviceToHost, s));

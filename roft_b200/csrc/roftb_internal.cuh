@@ -29,8 +29,13 @@ struct Geom {
     int grid;              // W / Wf
     int flow_s16;          // 1: short2 elements, 0: float2
     float scale;           // flow scaling factor
+    float inv_scale;       // 1 / scale
+    int scale_mode;        // 0: scale == 1 (identity), 1: power of two (x * inv_scale is exact), 2: IEEE division
+    float inv_grid;        // 1 / grid
+    int grid_mode;         // same three cases for the division of the chased position by the grid size
     float cx, cy, inv_fx, inv_fy;
     double max_depth;      // depth gate (compared in double like the reference)
+    float max_depth_f;     // smallest float >= max_depth: (double)d < max_depth  <=>  d < max_depth_f
     int stride;            // subsampling radius (>=1)
 };
 
@@ -133,6 +138,10 @@ struct MaskSyncArgs {
     const WarpCtl* ctl;                               // device
     MaskStat* stat; WarpPlan* plan; FlowBuf* fbuf;    // device
     int segm_delay;
+    // worklists (launch_tile_list) of the state mask and of the newly delivered mask
+    const int32_t* s_list; const int32_t* s_n;
+    const int32_t* n_list; const int32_t* n_n;
+    int n_warp_tiles;
 };
 // planned = true: a.plan was filled by the caller (operator mode), skip the stats / plan kernels
 int launch_mask_sync(const MaskSyncArgs& a, cudaStream_t s, bool planned = false);
@@ -146,7 +155,9 @@ struct VelocityArgs {
     const VelCtl* ctl;                                    // device
     int weight_flow;
     // scratch
-    int32_t* wt_count;      // [T][n_warp_tiles] per-warp-tile mask counts / prefixes (stride > 1)
+    int32_t* wt_count;      // [T][n_warp_tiles] row-major rank base of each warp tile   } built by
+    int32_t* wt_list;       // [T][n_warp_tiles] non-empty warp tiles of the mask        } launch_tile_list
+    int32_t* wt_n;          // [T] their number                                          }
     float* norms;           // [T][HW]
     uint32_t* norm_count;   // [T]
     uint32_t* hist;         // [T][kSelBins]
@@ -169,6 +180,10 @@ struct VelocityArgs {
     const double* x_pred_override;     // operator mode: [T][6] predicted mean for the norms (else v_mean)
 };
 int launch_velocity(const VelocityArgs& a, cudaStream_t s);
+// worklist of the non-empty warp tiles of a byte plane (+ rank base of the bytes > thr); active: optional per-item
+// flags, item i is processed iff active[i * active_stride] != 0
+int launch_tile_list(const uint8_t* plane, long long stride, int thr, int HW, int n_items, int32_t* wt_count, int32_t* wt_list,
+                     int32_t* wt_n, const int32_t* active, int active_stride, cudaStream_t s);
 // per-warp-tile exclusive prefix of the number of pixels with byte > thr (row-major rank base); ctl may be null
 int launch_mask_rank(const uint8_t* seg, long long seg_stride, int thr, int HW, int n_items, int32_t* wt_count, int32_t* total,
                      const VelCtl* ctl, cudaStream_t s);
@@ -237,23 +252,41 @@ __device__ __forceinline__ uint4 ld_nc_u4(const uint4* p) {
     return r;
 }
 
-// one flow element (dx, dy) = float(f) / scale in FP32, as ImageOpticalFlowMeasurement.hpp:249-250
-__device__ __forceinline__ float2 load_flow(const void* base, int s16, long long idx, float scale) {
+// x / scale in IEEE FP32 (ImageOpticalFlowMeasurement.hpp:249-250): identity for scale 1, an exact multiplication
+// for a power-of-two scale (NVOF's 32), a correctly rounded division otherwise - bit-identical in all three cases
+__device__ __forceinline__ float div_scale(float x, const Geom& g) {
+    return g.scale_mode == 0 ? x : g.scale_mode == 1 ? x * g.inv_scale : __fdiv_rn(x, g.scale);
+}
+__device__ __forceinline__ float div_grid(float x, const Geom& g) {
+    return g.grid_mode == 0 ? x : g.grid_mode == 1 ? x * g.inv_grid : __fdiv_rn(x, (float)g.grid);
+}
+
+// one flow element (dx, dy) = float(f) / scale in FP32
+__device__ __forceinline__ float2 load_flow(const void* base, long long idx, const Geom& g) {
     float2 f;
-    if (s16) {
+    if (g.flow_s16) {
         short2 v = __ldg(reinterpret_cast<const short2*>(base) + idx);
         f = make_float2((float)v.x, (float)v.y);
     } else {
         f = __ldg(reinterpret_cast<const float2*>(base) + idx);
     }
-    f.x = __fdiv_rn(f.x, scale);
-    f.y = __fdiv_rn(f.y, scale);
+    f.x = div_scale(f.x, g);
+    f.y = div_scale(f.y, g);
     return f;
 }
 
-// OpticalFlowUtilities.h:19-22
-__device__ __forceinline__ bool flow_valid(float dx, float dy) {
-    return !isnan(dx) && !isnan(dy) && fabsf(dx) < 1e9f && fabsf(dy) < 1e9f;
+// OpticalFlowUtilities.h:19-22 (a NaN fails the magnitude test, so the isnan tests are implied)
+__device__ __forceinline__ bool flow_valid(float dx, float dy) { return fabsf(dx) < 1e9f && fabsf(dy) < 1e9f; }
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
