@@ -131,7 +131,7 @@ __device__ void cov_sqrt_warp(UkfSmem& s, int n, double sc, double (*out)[12], i
 }
 
 // dominant eigenvector of sum_i w_i q_i q_i^T over the quaternion columns Y[i][qoff..qoff+3]; sign fixed
-// against the first sigma point (see oracle/roft_oracle.py mean_quaternion)
+// against the first sigma point (DESIGN.md "UKF conventions")
 __device__ void mean_quaternion_warp(UkfSmem& s, int npts, int qoff, double wm0, double wi, double* out, int lane) {
     if (lane < 10) {  // upper triangle, mirrored so the matrix is exactly symmetric
         int r = 0, c = lane;

@@ -147,7 +147,15 @@ def make_sequence(n_tracks: int, n_frames: int, width: int = 1280, height: int =
                 pose_valid[f, t] = False
                 pose[f, t] = 0.0
 
-    gen = torch.Generator(device=dev).manual_seed(seed * 7919 + first_track_id)
+    # one noise generator per GLOBAL track id: a track's images do not depend on the partition / chunking
+    gens = [torch.Generator(device=dev).manual_seed(seed * 7919 + first_track_id + t) for t in range(T)]
+
+    def randn(c0, c1, shape):
+        return torch.stack([torch.randn(shape, generator=gens[t], device=dev, dtype=torch.float32) for t in range(c0, c1)])
+
+    def rand(c0, c1, shape):
+        return torch.stack([torch.rand(shape, generator=gens[t], device=dev, dtype=torch.float32) for t in range(c0, c1)])
+
     for c0 in range(0, T, track_chunk):
         c1 = min(T, c0 + track_chunk)
         hc = half[c0:c1].to(dev)
@@ -188,14 +196,13 @@ def make_sequence(n_tracks: int, n_frames: int, width: int = 1280, height: int =
                 if flow_noise > 0:
                     # optical-flow error is spatially smooth: coarse-grid noise, bilinearly upsampled,
                     # plus a small i.i.d. component
-                    cg = torch.randn((fl.shape[0], 2, max(2, H // 16), max(2, W // 16)), generator=gen, device=dev,
-                                     dtype=torch.float32)
+                    cg = randn(c0, c1, (2, max(2, H // 16), max(2, W // 16)))
                     sm = torch.nn.functional.interpolate(cg, size=(H, W), mode="bilinear", align_corners=True)
                     fl = fl + flow_noise * sm.permute(0, 2, 3, 1)
-                    fl = fl + (0.1 * flow_noise) * torch.randn(fl.shape, generator=gen, device=dev, dtype=torch.float32)
+                    fl = fl + (0.1 * flow_noise) * randn(c0, c1, tuple(fl.shape[1:]))
                 if grid == 1:
                     if corrupt:
-                        r = torch.rand(fl.shape[:-1], generator=gen, device=dev)
+                        r = rand(c0, c1, tuple(fl.shape[1:-1]))
                         fl = torch.where((r < 0.005).unsqueeze(-1), torch.full_like(fl, float("nan")), fl)
                         fl = torch.where(((r >= 0.005) & (r < 0.01)).unsqueeze(-1), torch.full_like(fl, 1e10), fl)
                     flow[f, c0:c1] = fl
@@ -203,7 +210,7 @@ def make_sequence(n_tracks: int, n_frames: int, width: int = 1280, height: int =
                     blk = fl.reshape(-1, Hf, grid, Wf, grid, 2).mean(dim=(2, 4))
                     flow[f, c0:c1] = torch.round(blk * scale).clamp(-32768, 32767).to(torch.int16)
             if corrupt:
-                r = torch.rand(d.shape, generator=gen, device=dev)
+                r = rand(c0, c1, tuple(d.shape[1:]))
                 dn = torch.where(r < 0.02, torch.zeros_like(d), d)
                 dn = torch.where((r >= 0.02) & (r < 0.03), torch.full_like(d, 3.0), dn)
             else:
