@@ -252,7 +252,7 @@ def run_own(args):
         return
 
     peak, peak_kind = measured_peak_gbs()
-    dom = max(("flow_pass_a", "flow_pass_b", "mask_sync"), key=lambda k: phases[k])
+    dom = max(("flow_pass_a", "flow_pass_b", "mask_scatter"), key=lambda k: phases[k])
     dom_ms = phases[dom]
     achieved = T * BYTES_PER_TRACK_FRAME / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None
     step_bytes_gbs = T * BYTES_PER_TRACK_FRAME / (ms_per_step * 1e-3) / 1e9

@@ -114,8 +114,9 @@ int64_t roftb_kernel_launches(const roftb_ctx* ctx);
 /* CUDA stream the kernels are enqueued on (cudaStream_t as void*), for event timing */
 void* roftb_stream(roftb_ctx* ctx);
 /* Device-side phase timing of roftb_filter_step with CUDA events on that stream.  Reads the averages
- * (ms per step since profiling was enabled) of the 7 phases {candidate rank, flow pass A (innovation
- * norms), median select, flow pass B (normal equations), 6x6 epilogue, mask sync, pose UKF} into
+ * (ms per step since profiling was enabled) of the 7 phases {prep (tile worklist + mask plan/init), flow
+ * pass A (innovation norms + fused mask propagation), median select, flow pass B (normal equations), 6x6
+ * epilogue, new-mask scatter (own stream), pose UKF (own stream)} into
  * ms_per_step[7] / steps (either may be NULL), then enables (1) or disables (0) profiling; enabling
  * resets the averages. */
 int roftb_profile(roftb_ctx* ctx, int32_t enable, double* ms_per_step, int64_t* steps);

@@ -249,7 +249,7 @@ class Tracker:
         """Make the main stream wait for the internal streams (call before recording an end-of-region event)."""
         self._check(self._lib.roftb_join(self._h), "roftb_join")
 
-    PHASES = ("rank", "flow_pass_a", "median_select", "flow_pass_b", "epilogue", "mask_sync", "ukf")
+    PHASES = ("prep", "flow_pass_a", "median_select", "flow_pass_b", "epilogue", "mask_scatter", "ukf")
 
     def profile(self, enable: bool):
         """Read the per-phase device times (ms per step) gathered so far, then enable/disable profiling."""

@@ -143,7 +143,10 @@ __global__ void __launch_bounds__(kThreads) k_tile_compact(int32_t* __restrict__
         if (threadIdx.x == kThreads - 1) { carry_r = cr + wr + ir; carry_l = cl + wl + il; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) wt_n[t] = carry_l;
+    if (threadIdx.x == 0) {
+        wt_n[t] = carry_l;              // number of non-empty warp tiles
+        wt_n[gridDim.x + t] = carry_r;  // number of candidates (bytes > thr) of the whole plane
+    }
 }
 
 // ---- the streaming pass ---------------------------------------------------------------------
@@ -164,15 +167,33 @@ struct PassArgs {
     double* partials; int max_blocks;
     double fx, fy;
     double cxd, cyd, inv_fxd, inv_fyd;   // FP64 intrinsics: pixel -> normalised coordinates without systematic rounding
+    // fused single-flow mask propagation (ImageSegmentationOFAidedSource.hpp:221-226) for tracks whose plan says so
+    const WarpPlan* plan; uint8_t* state_dst; int32_t* winner;
 };
 
 // AT = accumulation type of pass B: float (per-pixel terms and partial sums in FP32) or double (per-pixel terms
 // and sums in FP64: forward error ~ cond(Lambda) * 1e-16 instead of cond * 1e-7 / sqrt(N)).
-template <int PASS, bool FAST, typename AT>
+//
+// Each warp walks its track's worklist of non-empty warp tiles (512 px: 4 sub-tiles of one quad per lane).  The
+// sub-tile loop is kept ROLLED with the loads of the next quad in flight while the current one is processed: the
+// kernel stays a few hundred SASS instructions (a fully unrolled body was 8k instructions and stalled on
+// instruction fetch), registers stay below 128 and three 128-bit loads per lane are always outstanding.
+// Innovation norms are written to rank-addressed slots (base = number of selected candidates before the tile,
+// from the worklist prefix), so pass A needs no atomics; gated-out candidates are marked with -1.
+// SCATTER: the same walk also forward-scatters every non-zero mask pixel through the current flow (the "no new mask"
+// propagation of the mask synchronisation) - it needs exactly the mask words and flow values this pass loads anyway.
+template <int PASS, bool FAST, typename AT, bool SCATTER>
 __global__ void __launch_bounds__(kThreads, 2) k_flow_pass(PassArgs a) {
     const int t = blockIdx.y;
     const VelCtl c = a.ctl[t];
-    if (!c.enable) return;
+    bool do_sc = false;
+    uint8_t sc_val = 0;
+    if (SCATTER) {
+        const WarpPlan& p = a.plan[t];
+        do_sc = p.fused != 0;  // only single-valued masks are fused (WarpPlan::fused)
+        sc_val = (uint8_t)p.uniform_val;
+    }
+    if (!c.enable && !do_sc) return;
     const Geom& g = a.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t thr4 = (uint32_t)a.thr * 0x01010101u;
@@ -182,6 +203,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_flow_pass(PassArgs a) {
                         (long long)t * a.ft.flow_stride * (g.flow_s16 ? 2 : 4);
     const float4* fq = reinterpret_cast<const float4*>(fbase);
     const int nq = g.HW >> 2;
+    const uint32_t lt = (1u << lane) - 1u;
 
     // predicted velocity (F = I: the predicted mean is the previous corrected mean) and FP32 row scales
     float x[6];
@@ -197,195 +219,210 @@ __global__ void __launch_bounds__(kThreads, 2) k_flow_pass(PassArgs a) {
 #pragma unroll
         for (int i = 0; i < kNAcc; ++i) acc[i] = (AT)0;
     }
+    float* norms_out = a.norms + (long long)t * g.HW;
 
     const int n_list = a.wt_n[t];
     const int32_t* list = a.wt_list + (long long)t * a.n_warp_tiles;
+    const int32_t* prefix = a.wt_prefix + (long long)t * a.n_warp_tiles;
+#pragma unroll 1
     for (int li = blockIdx.x * (kThreads / 32) + warp; li < n_list; li += gridDim.x * (kThreads / 32)) {
         const int wt = list[li];  // warp-uniform
-        uint32_t sel[4];
+        const int q0 = wt * 128 + lane;
+        // candidate bits of this lane's four quads: bit (4j + i); scs: non-zero pixels to propagate (origin excluded)
+        uint32_t sel = 0, scs = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int q = wt * 128 + j * 32 + lane;
+            const int q = q0 + j * 32;
             const uint32_t m = q < nq ? ld_nc_u32(mq + q) : 0u;
-            sel[j] = __vcmpgtu4(m, thr4);
+            const uint32_t s8 = __vcmpgtu4(m, thr4);
+            sel |= ((s8 & 1u) | ((s8 >> 7) & 2u) | ((s8 >> 14) & 4u) | ((s8 >> 21) & 8u)) << (4 * j);
+            if (SCATTER) {
+                uint32_t z8 = __vcmpne4(m, 0u);
+                if (q == 0) z8 &= 0xffffff00u;  // mask_(0,0) = 0 (hpp:224)
+                scs |= ((z8 & 1u) | ((z8 >> 7) & 2u) | ((z8 >> 14) & 4u) | ((z8 >> 21) & 8u)) << (4 * j);
+            }
         }
+        if (!c.enable) sel = 0;
+        if (!do_sc) scs = 0;
+        const int rank0 = prefix[wt];  // candidates (row-major) before this tile
+        int nbase;                     // norm slot of the tile's first selected candidate
         if (g.stride > 1) {
-            // row-major rank of every candidate; keep rank % stride == 0 (hpp:237), BEFORE the gates
-            int r = a.wt_prefix[(long long)t * a.n_warp_tiles + wt];
+            // keep rank % stride == 0 (hpp:237), BEFORE the gates
+            int r = rank0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int cnt = __popc(sel[j]) >> 3;
+                const uint32_t nib = (sel >> (4 * j)) & 0xfu;
+                const int cnt = __popc(nib);
                 const int incl = warp_scan_incl(cnt, lane);
                 const int tot = __shfl_sync(0xffffffffu, incl, 31);
                 unsigned rank = (unsigned)(r + incl - cnt);
                 uint32_t ns = 0;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    if ((sel[j] >> (8 * i)) & 1u) {
-                        if (rank % (unsigned)g.stride == 0u) ns |= 0xffu << (8 * i);
+                    if ((nib >> i) & 1u) {
+                        if (rank % (unsigned)g.stride == 0u) ns |= 1u << i;
                         ++rank;
                     }
                 }
-                sel[j] = ns;
+                sel = (sel & ~(0xfu << (4 * j))) | (ns << (4 * j));
                 r += tot;
             }
+            nbase = (rank0 + g.stride - 1) / g.stride;
+        } else {
+            nbase = rank0;
         }
-        const uint32_t any = sel[0] | sel[1] | sel[2] | sel[3];
-        if (!__any_sync(0xffffffffu, any != 0u)) continue;
+        const uint32_t need = sel | scs;
+        if (!__any_sync(0xffffffffu, need != 0u)) continue;
 
-        float nrm[16];
-        uint32_t vmask = 0;  // bit (4j+i): pixel passed the gates
-        // loads are issued a batch of quads at a time, all before the data is touched (FP32: 12 x 128-bit in
-        // flight per lane; the FP64 accumulation variant halves the batch to stay within 128 registers)
-        constexpr int QB = (PASS == 1 && sizeof(AT) == 8) ? 2 : 4;
-#pragma unroll
-        for (int jb = 0; jb < 4; jb += QB) {
-            float4 D[QB], F0[QB], F1[QB];
-#pragma unroll
-            for (int jj = 0; jj < QB; ++jj) {
-                const int q = wt * 128 + (jb + jj) * 32 + lane;
-                const bool on = sel[jb + jj] != 0u;
-                D[jj] = get4(dq + q, on);
+        // software pipeline over the four quads: loads of quad j+1 are issued before quad j is processed
+        float4 Dc, F0c, F1c, Dn, F0n, F1n;
+        {
+            Dc = get4(dq + q0, (sel & 0xfu) != 0u);
+            if (FAST) {
+                const bool on = (need & 0xfu) != 0u;
+                F0c = get4(fq + 2 * q0, on);
+                F1c = get4(fq + 2 * q0 + 1, on);
+            }
+        }
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            if (j < 3) {
+                const int qn = q0 + (j + 1) * 32;
+                Dn = get4(dq + qn, ((sel >> (4 * (j + 1))) & 0xfu) != 0u);
                 if (FAST) {
-                    F0[jj] = get4(fq + 2 * q, on);
-                    F1[jj] = get4(fq + 2 * q + 1, on);
+                    const bool on = ((need >> (4 * (j + 1))) & 0xfu) != 0u;
+                    F0n = get4(fq + 2 * qn, on);
+                    F1n = get4(fq + 2 * qn + 1, on);
                 }
             }
+            const uint32_t nib = (sel >> (4 * j)) & 0xfu;
+            const uint32_t snib = (scs >> (4 * j)) & 0xfu;
+            const int px = (q0 + j * 32) << 2;
+            const int v = px / g.W;
+            const int u0 = px - v * g.W;
+            // normalised coordinates from FP64 intrinsics (a rounded 1/fx would bias every pixel the same way)
+            const double yhd = ((double)v - a.cyd) * a.inv_fyd;
+            const double xh0d = ((double)u0 - a.cxd) * a.inv_fxd;
+            const float yh = (float)yhd;
+            const float xh0 = (float)xh0d;
 #pragma unroll
-            for (int jj = 0; jj < QB; ++jj) {
-                const int j = jb + jj;
-                if (sel[j] == 0u) continue;
-                const int px = (wt * 128 + j * 32 + lane) << 2;
-                const int v = px / g.W;
-                const int u0 = px - v * g.W;
-                // normalised coordinates from FP64 intrinsics (a rounded 1/fx would bias every pixel the same way)
-                const double yhd = ((double)v - a.cyd) * a.inv_fyd;
-                const double xh0d = ((double)u0 - a.cxd) * a.inv_fxd;
-                const float yh = (float)yhd;
-                const float xh0 = (float)xh0d;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (!((sel[j] >> (8 * i)) & 1u)) continue;
-                    const float d = comp(D[jj], i);
-                    float dx, dy;
+            for (int i = 0; i < 4; ++i) {
+                const bool cand = (nib >> i) & 1u;
+                const bool scand = SCATTER && ((snib >> i) & 1u);
+                bool valid = false;
+                float nr = -1.0f;
+                float dx = 0.f, dy = 0.f, d = 1.f, xh = 0.f, ia = 0.f;
+                float l1[5], l2[5];
+                if (cand || scand) {
                     if (FAST) {
-                        const float4 f = i < 2 ? F0[jj] : F1[jj];
-                        dx = div_scale((i & 1) ? f.z : f.x, g);
-                        dy = div_scale((i & 1) ? f.w : f.y, g);
+                        const float4 f = i < 2 ? F0c : F1c;
+                        dx = (i & 1) ? f.z : f.x;  // FAST: float2 flow, grid 1, scale 1
+                        dy = (i & 1) ? f.w : f.y;
                     } else {
                         const int u = u0 + i;
                         const float2 f = load_flow(fbase, (long long)(v / g.grid) * g.Wf + (u / g.grid), g);
                         dx = f.x;
                         dy = f.y;
                     }
-                    // hpp:252 gates
-                    if (!(flow_valid(dx, dy) && d > 0.f && d < g.max_depth_f)) continue;
-                    const float xh = fmaf((float)i, g.inv_fx, xh0);
-                    const float ia = rcp_approx(d);
-                    const float l1[5] = {ia, -xh * ia, -xh * yh, 1.0f + xh * xh, -yh};
-                    const float l2[5] = {ia, -yh * ia, -(1.0f + yh * yh), xh * yh, xh};
-                    const float p1 = l1[0] * x[0] + l1[1] * x[2] + l1[2] * x[3] + l1[3] * x[4] + l1[4] * x[5];
-                    const float p2 = l2[0] * x[1] + l2[1] * x[2] + l2[2] * x[3] + l2[3] * x[4] + l2[4] * x[5];
-                    const float n1 = dx - c1 * p1, n2 = dy - c2 * p2;
-                    const float nr = sqrt_approx(n1 * n1 + n2 * n2);
-                    if (PASS == 0) {
-                        nrm[4 * j + i] = nr;
-                        vmask |= 1u << (4 * j + i);
-                    } else {
-                        float l = 1.0f;
-                        if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
-                        AT e1[5], e2[5];
-                        if (sizeof(AT) == 8) {
-                            // FP64 per-pixel terms: 1/d refined from the FP32 reciprocal by one Newton step
-                            const double xhd = fma((double)i, a.inv_fxd, xh0d);
-                            double r = (double)ia;
-                            r = r * (2.0 - (double)d * r);
-                            e1[0] = (AT)r; e1[1] = (AT)(-xhd * r); e1[2] = (AT)(-xhd * yhd); e1[3] = (AT)(1.0 + xhd * xhd); e1[4] = (AT)(-yhd);
-                            e2[0] = (AT)r; e2[1] = (AT)(-yhd * r); e2[2] = (AT)(-(1.0 + yhd * yhd)); e2[3] = (AT)(xhd * yhd); e2[4] = (AT)xhd;
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 5; ++k) {
-                                e1[k] = (AT)l1[k];
-                                e2[k] = (AT)l2[k];
-                            }
-                        }
-                        AT w1[5], w2[5];
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) {
-                            w1[k] = (AT)l * e1[k];
-                            w2[k] = (AT)l * e2[k];
-                        }
-                        int o = 0;
-#pragma unroll
-                        for (int r = 0; r < 5; ++r)
-#pragma unroll
-                            for (int s = r; s < 5; ++s) {
-                                acc[o] = fma(w1[r], e1[s], acc[o]);
-                                acc[15 + o] = fma(w2[r], e2[s], acc[15 + o]);
-                                ++o;
-                            }
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) {
-                            acc[30 + k] = fma(w1[k], (AT)dx, acc[30 + k]);
-                            acc[35 + k] = fma(w2[k], (AT)dy, acc[35 + k]);
-                        }
-                        acc[40] += (AT)1;
+                }
+                if (scand) {
+                    // hpp:249-278 for a single flow: the source pixel is inside the frame and its flow element is the one
+                    // just fetched; IEEE adds, x86 truncation, last check on the destination
+                    const float tx = __fadd_rn((float)(u0 + i), dx), ty = __fadd_rn((float)v, dy);
+                    const int ix = cvt_int(tx), iy = cvt_int(ty);
+                    if (ix >= 0 && ix < g.W && iy >= 0 && iy < g.H) {
+                        a.state_dst[(long long)t * g.HW + iy * g.W + ix] = sc_val;
                     }
                 }
-            }
-        }
-
-        if (PASS == 0) {
-            // warp-aggregated append of the valid norms (order is irrelevant for the order statistics)
-            int total = 0;
-            uint32_t ball[16];
+                if (cand) {
+                    d = comp(Dc, i);
+                    // hpp:252 gates
+                    valid = flow_valid(dx, dy) && d > 0.f && d < g.max_depth_f;
+                    if (valid) {
+                        xh = fmaf((float)i, g.inv_fx, xh0);
+                        ia = rcp_approx(d);
+                        l1[0] = ia; l1[1] = -xh * ia; l1[2] = -xh * yh; l1[3] = 1.0f + xh * xh; l1[4] = -yh;
+                        l2[0] = ia; l2[1] = -yh * ia; l2[2] = -(1.0f + yh * yh); l2[3] = xh * yh; l2[4] = xh;
+                        const float p1 = l1[0] * x[0] + l1[1] * x[2] + l1[2] * x[3] + l1[3] * x[4] + l1[4] * x[5];
+                        const float p2 = l2[0] * x[1] + l2[1] * x[2] + l2[2] * x[3] + l2[3] * x[4] + l2[4] * x[5];
+                        const float n1 = dx - c1 * p1, n2 = dy - c2 * p2;
+                        nr = sqrt_approx(n1 * n1 + n2 * n2);
+                    }
+                }
+                if (PASS == 0) {
+                    const uint32_t ball = __ballot_sync(0xffffffffu, cand);
+                    if (cand) norms_out[nbase + __popc(ball & lt)] = nr;
+                    nbase += __popc(ball);
+                } else if (valid) {
+                    float l = 1.0f;
+                    if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
+                    AT e1[5], e2[5];
+                    if (sizeof(AT) == 8) {
+                        // FP64 per-pixel terms: 1/d refined from the FP32 reciprocal by two Newton steps
+                        const double xhd = fma((double)i, a.inv_fxd, xh0d);
+                        double r = (double)ia;
+                        r = r * (2.0 - (double)d * r);
+                        r = r * (2.0 - (double)d * r);
+                        e1[0] = (AT)r; e1[1] = (AT)(-xhd * r); e1[2] = (AT)(-xhd * yhd); e1[3] = (AT)(1.0 + xhd * xhd); e1[4] = (AT)(-yhd);
+                        e2[0] = (AT)r; e2[1] = (AT)(-yhd * r); e2[2] = (AT)(-(1.0 + yhd * yhd)); e2[3] = (AT)(xhd * yhd); e2[4] = (AT)xhd;
+                    } else {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                ball[k] = __ballot_sync(0xffffffffu, (vmask >> k) & 1u);
-                total += __popc(ball[k]);
-            }
-            if (total) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(a.norm_count + t, (unsigned)total);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                float* out = a.norms + (long long)t * g.HW;
-                const uint32_t lt = (1u << lane) - 1u;
+                        for (int k = 0; k < 5; ++k) {
+                            e1[k] = (AT)l1[k];
+                            e2[k] = (AT)l2[k];
+                        }
+                    }
+                    AT w1[5], w2[5];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if ((vmask >> k) & 1u) out[base + __popc(ball[k] & lt)] = nrm[k];
-                    base += __popc(ball[k]);
+                    for (int k = 0; k < 5; ++k) {
+                        w1[k] = (AT)l * e1[k];
+                        w2[k] = (AT)l * e2[k];
+                    }
+                    int o = 0;
+#pragma unroll
+                    for (int r = 0; r < 5; ++r)
+#pragma unroll
+                        for (int s = r; s < 5; ++s) {
+                            acc[o] = fma(w1[r], e1[s], acc[o]);
+                            acc[15 + o] = fma(w2[r], e2[s], acc[15 + o]);
+                            ++o;
+                        }
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        acc[30 + k] = fma(w1[k], (AT)dx, acc[30 + k]);
+                        acc[35 + k] = fma(w2[k], (AT)dy, acc[35 + k]);
+                    }
+                    acc[40] += (AT)1;
                 }
             }
+            Dc = Dn;
+            F0c = F0n;
+            F1c = F1n;
         }
     }
 
     if (PASS == 1) {
-        __shared__ AT red[kThreads / 32][kNAcc];
+        // one partial per WARP (no block barrier: warps finish at different times)
+        double* out = a.partials + ((long long)t * a.max_blocks + blockIdx.x * (kThreads / 32) + warp) * kNAcc;
 #pragma unroll
         for (int i = 0; i < kNAcc; ++i) {
             const AT s = warp_sum(acc[i]);
-            if (lane == 0) red[warp][i] = s;
-        }
-        __syncthreads();
-        if (threadIdx.x < kNAcc) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) s += (double)red[w][threadIdx.x];
-            a.partials[((long long)t * a.max_blocks + blockIdx.x) * kNAcc + threadIdx.x] = s;
+            if (lane == 0) out[i] = (double)s;
         }
     }
 }
 
 // ---- exact radix select of the upper median + Laplacian parameters ---------------------------
-__global__ void k_sel_init(int n_tracks, const uint32_t* __restrict__ norm_count, SelState* __restrict__ sel,
+__global__ void k_sel_init(int n_tracks, const int32_t* __restrict__ wt_n, int stride, SelState* __restrict__ sel,
                            const VelCtl* __restrict__ ctl) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tracks) return;
     SelState s;
     s.prefix = 0;
-    s.n = ctl[t].enable ? norm_count[t] : 0u;
-    s.k = s.n >> 1;
-    s.pad = 0;
+    // norm slots written by pass A: one per selected candidate (gated-out ones hold -1)
+    s.n_entries = ctl[t].enable ? (uint32_t)((wt_n[n_tracks + t] + stride - 1) / stride) : 0u;
+    s.n = s.n_entries;  // valid count, fixed by the level-0 scan
+    s.k = 0;
     s.less_cnt = 0;
     s.less_sum = 0.0;
     s.total_sum = 0.0;
@@ -398,7 +435,8 @@ template <int LEVEL>
 __global__ void __launch_bounds__(kThreads) k_sel_hist(const float* __restrict__ norms, int HW, const SelState* __restrict__ sel,
                                                       uint32_t* __restrict__ hist) {
     const int t = blockIdx.y;
-    const uint32_t n = sel[t].n;
+    if (sel[t].n == 0) return;
+    const uint32_t n = sel[t].n_entries;
     const uint32_t prefix = sel[t].prefix;
     const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
     const uint32_t lo = blockIdx.x * per;
@@ -411,6 +449,7 @@ __global__ void __launch_bounds__(kThreads) k_sel_hist(const float* __restrict__
     const uint32_t* keys = reinterpret_cast<const uint32_t*>(norms + (long long)t * HW);
     for (uint32_t i = lo + threadIdx.x; i < hi; i += kThreads) {
         const uint32_t key = keys[i];
+        if (key >> 31) continue;  // gated-out candidate
         if (LEVEL == 0) {
             atomicAdd(&h[key >> 20], 1u);
         } else if (LEVEL == 1) {
@@ -446,11 +485,19 @@ __global__ void __launch_bounds__(kThreads) k_sel_scan(SelState* __restrict__ se
     const uint32_t incl = (uint32_t)warp_scan_incl((int)sum, lane);
     if (lane == 31) sh[warp] = incl;
     __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < warp; ++w) woff += sh[w];
+    uint32_t woff = 0, total = 0;
+    for (int w = 0; w < kThreads / 32; ++w) {
+        if (w < warp) woff += sh[w];
+        total += sh[w];
+    }
     uint32_t before = woff + incl - sum;
-    const uint32_t k = s.k;
+    // level 0 fixes the number of valid measurements and the rank of the upper median s[n/2]
+    const uint32_t k = LEVEL == 0 ? (total >> 1) : s.k;
     __syncthreads();
+    if (LEVEL == 0) {
+        if (threadIdx.x == 0) s.n = total;
+        if (total == 0) return;
+    }
     if (k >= before && k < before + sum) {  // exactly one thread
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
@@ -467,7 +514,8 @@ __global__ void __launch_bounds__(kThreads) k_sel_scan(SelState* __restrict__ se
 
 __global__ void __launch_bounds__(kThreads) k_sel_stats(const float* __restrict__ norms, int HW, SelState* __restrict__ sel) {
     const int t = blockIdx.y;
-    const uint32_t n = sel[t].n;
+    if (sel[t].n == 0) return;
+    const uint32_t n = sel[t].n_entries;
     const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
     const uint32_t lo = blockIdx.x * per;
     if (lo >= n) return;
@@ -479,6 +527,7 @@ __global__ void __launch_bounds__(kThreads) k_sel_stats(const float* __restrict_
     float lm = 0.f;
     for (uint32_t i = lo + threadIdx.x; i < hi; i += kThreads) {
         const float v = p[i];
+        if (v < 0.f) continue;  // gated-out candidate
         tot += (double)v;
         if (v < v1) {
             ls += (double)v;
@@ -589,7 +638,6 @@ struct EpiArgs {
     double r0, r1, fx, fy;
     double* vel_hist; int hist_ring;
     int32_t* out_count; double* out_lambda; double* out_eta;
-    uint32_t* norm_count;
     int update_state;
 };
 
@@ -608,7 +656,6 @@ __global__ void __launch_bounds__(32) k_vel_epilogue(EpiArgs a) {
     }
     __syncwarp();
     if (lane != 0) return;
-    if (a.norm_count) a.norm_count[t] = 0;
     double* x = a.v_mean + (long long)t * 6;
     double* P = a.v_cov + (long long)t * 36;
     int count = 0;
@@ -713,7 +760,7 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     // blocks per track: several waves over the machine in total; each warp walks the track's tile list with
     // a stride of (blocks x warps)
     int bpt = max(1, (148 * 16 + T - 1) / T);
-    bpt = min(bpt, min(n_block_tiles, a.max_blocks));
+    bpt = min(bpt, min(n_block_tiles, a.max_blocks / (kThreads / 32)));
 
     if (a.prof) cudaEventRecord(a.prof[0], s);
     if (a.prof) cudaEventRecord(a.prof[1], s);
@@ -742,14 +789,25 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     pa.cyd = a.cy;
     pa.inv_fxd = 1.0 / a.fx;
     pa.inv_fyd = 1.0 / a.fy;
-    const bool fast = (!g.flow_s16 && g.grid == 1);
+    pa.plan = a.plan;
+    pa.state_dst = a.state_dst;
+    pa.winner = a.winner;
+    const bool fast = (!g.flow_s16 && g.grid == 1 && g.scale_mode == 0);
+    const bool fuse = a.fuse_scatter != 0;  // the first streaming pass also propagates the mask
+#define ROFTB_PASS(PASS, AT, SC)                                                                          \
+    do {                                                                                                  \
+        if (fast)                                                                                         \
+            ROFTB_LAUNCH((k_flow_pass<PASS, true, AT, SC>), dim3(bpt, T), kThreads, 0, s, pa);            \
+        else                                                                                              \
+            ROFTB_LAUNCH((k_flow_pass<PASS, false, AT, SC>), dim3(bpt, T), kThreads, 0, s, pa);           \
+    } while (0)
     if (a.weight_flow) {
-        if (fast)
-            ROFTB_LAUNCH((k_flow_pass<0, true, float>), dim3(bpt, T), kThreads, 0, s, pa);
+        if (fuse)
+            ROFTB_PASS(0, float, true);
         else
-            ROFTB_LAUNCH((k_flow_pass<0, false, float>), dim3(bpt, T), kThreads, 0, s, pa);
+            ROFTB_PASS(0, float, false);
         if (a.prof) cudaEventRecord(a.prof[2], s);
-        ROFTB_LAUNCH(k_sel_init, (T + 127) / 128, 128, 0, s, T, a.norm_count, a.sel, a.ctl);
+        ROFTB_LAUNCH(k_sel_init, (T + 127) / 128, 128, 0, s, T, a.wt_n, g.stride, a.sel, a.ctl);
         // enough blocks per track to spread the list, few enough that the per-block histogram flush stays cheap
         int sb = max(1, min(32, (148 * 4 + T - 1) / T));
         ROFTB_LAUNCH(k_sel_hist<0>, dim3(sb, T), kThreads, 0, s, a.norms, g.HW, a.sel, a.hist);
@@ -764,24 +822,26 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
         cudaEventRecord(a.prof[2], s);
     }
     if (a.prof) cudaEventRecord(a.prof[3], s);
+    const bool fuse_b = fuse && !a.weight_flow;
     if (a.accum_fp64) {
-        if (fast)
-            ROFTB_LAUNCH((k_flow_pass<1, true, double>), dim3(bpt, T), kThreads, 0, s, pa);
+        if (fuse_b)
+            ROFTB_PASS(1, double, true);
         else
-            ROFTB_LAUNCH((k_flow_pass<1, false, double>), dim3(bpt, T), kThreads, 0, s, pa);
+            ROFTB_PASS(1, double, false);
     } else {
-        if (fast)
-            ROFTB_LAUNCH((k_flow_pass<1, true, float>), dim3(bpt, T), kThreads, 0, s, pa);
+        if (fuse_b)
+            ROFTB_PASS(1, float, true);
         else
-            ROFTB_LAUNCH((k_flow_pass<1, false, float>), dim3(bpt, T), kThreads, 0, s, pa);
+            ROFTB_PASS(1, float, false);
     }
+#undef ROFTB_PASS
     if (a.prof) cudaEventRecord(a.prof[4], s);
     EpiArgs e;
     e.n_tracks = T;
     e.ctl = a.ctl;
     e.partials = a.partials;
     e.max_blocks = a.max_blocks;
-    e.n_blocks = bpt;
+    e.n_blocks = bpt * (kThreads / 32);  // one partial per warp
     e.v_mean = a.v_mean;
     e.v_cov = a.v_cov;
     e.q_diag = a.q_diag;
@@ -794,7 +854,6 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     e.out_count = a.out_count;
     e.out_lambda = a.out_lambda;
     e.out_eta = a.out_eta;
-    e.norm_count = a.weight_flow ? a.norm_count : nullptr;
     e.update_state = a.update_state;
     ROFTB_LAUNCH(k_vel_epilogue, T, 32, 0, s, e);
     if (a.prof) cudaEventRecord(a.prof[5], s);

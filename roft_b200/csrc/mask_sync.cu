@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kThreads) k_mask_stats(const uint8_t* __restri
 // ---------------------------------------------------------------------------------------------
 __global__ void k_warp_plan(int n_tracks, const WarpCtl* __restrict__ ctl, MaskStat* __restrict__ stat,
                             WarpPlan* __restrict__ plan, FlowBuf* __restrict__ fbuf, const uint8_t* __restrict__ new_mask,
-                            long long new_stride, const uint8_t* __restrict__ state_src, int HW, int segm_delay) {
+                            long long new_stride, const uint8_t* __restrict__ state_src, int HW, int segm_delay, int fuse) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tracks) return;
     const WarpCtl c = ctl[t];
@@ -81,7 +81,8 @@ __global__ void k_warp_plan(int n_tracks, const WarpCtl* __restrict__ ctl, MaskS
     for (int i = 0; i < kMaxFlows; ++i) p.flow_slot[i] = 0;
     p.uniform_val = fb.uniform_val;
     p.dflt = 0;
-    p.pad[0] = p.pad[1] = 0;
+    p.fused = 0;
+    p.pad = 0;
     if (c.reset) fb.n = 0;
     const int new_uniform = (st.nnz > 0 && st.vmin == st.vmax) ? st.vmin : 0;
 
@@ -130,6 +131,8 @@ __global__ void k_warp_plan(int n_tracks, const WarpCtl* __restrict__ ctl, MaskS
             p.flow_slot[0] = c.cur_slot;
             p.uniform_val = fb.uniform_val;
             p.dflt = 0;
+            // state source + the current flow only + single-valued mask (plain byte stores, no winner plane)
+            p.fused = (fuse && !init_now && fb.uniform_val != 0) ? 1 : 0;
         } else if (init_now) {
             p.mode = kWarpCopyNew;
         }
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft
     __shared__ WarpPlan sp;
     if (threadIdx.x == 0) sp = plan[t];
     __syncthreads();
-    if (sp.mode != kWarpScatter) return;
+    if (sp.mode != kWarpScatter || sp.fused) return;
     const uint8_t* src = sp.src_new ? track_plane(new_mask, new_stride, t) : state_src + (long long)t * g.HW;
     uint8_t* dst = state_dst + (long long)t * g.HW;
     int32_t* win = winner + (long long)t * g.HW;
@@ -222,17 +225,53 @@ __global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft
             m[j] = q < nq ? ld_nc_u32(reinterpret_cast<const uint32_t*>(src) + q) : 0u;
             if (sp.zero_origin && q == 0) m[j] &= 0xffffff00u;
         }
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < 4; ++j) {
-            if (m[j] == 0u) continue;
+            const uint32_t mj = m[j];
+            if (mj == 0u) continue;
             const int px = (wt * 128 + j * 32 + lane) << 2;
             const int v = px / g.W;
             const int u0 = px - v * g.W;
+            // the four pixels of the quad are chased together: four independent flow gathers in flight per hop
+            // (a chain of D dependent DRAM accesses per pixel is pure latency otherwise)
+            float tx[4], ty[4];
+            bool alive[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (((m[j] >> (8 * i)) & 0xffu) == 0u) continue;
-                const int d = chase(g, ft, sp, t, u0 + i, v);
-                if (d < 0) continue;
+                tx[i] = (float)(u0 + i);
+                ty[i] = (float)v;
+                alive[i] = ((mj >> (8 * i)) & 0xffu) != 0u;
+            }
+            for (int h = 0; h < sp.n_flows; ++h) {
+                const char* base = reinterpret_cast<const char*>(ft.flow[sp.flow_slot[h]]) +
+                                   (long long)t * ft.flow_stride * (g.flow_s16 ? 2 : 4);
+                float2 f[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    f[i] = make_float2(0.f, 0.f);
+                    if (!alive[i]) continue;
+                    const int ix = cvt_int(tx[i]), iy = cvt_int(ty[i]);
+                    if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) {  // hpp:262-266
+                        alive[i] = false;
+                        continue;
+                    }
+                    const int fr = cvt_int(div_grid(ty[i], g));
+                    const int fc = cvt_int(div_grid(tx[i], g));
+                    f[i] = load_flow(base, (long long)fr * g.Wf + fc, g);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!alive[i]) continue;
+                    tx[i] = __fadd_rn(tx[i], f[i].x);
+                    ty[i] = __fadd_rn(ty[i], f[i].y);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!alive[i]) continue;
+                const int ix = cvt_int(tx[i]), iy = cvt_int(ty[i]);
+                if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) continue;
+                const int d = iy * g.W + ix;
                 if (general)
                     atomicMax(win + d, px + i);
                 else
@@ -282,11 +321,10 @@ __global__ void __launch_bounds__(kThreads) k_threshold(const uint4* __restrict_
 
 }  // namespace
 
-int launch_mask_sync(const MaskSyncArgs& a, cudaStream_t s, bool planned) {
+int launch_mask_plan_init(const MaskSyncArgs& a, cudaStream_t s, bool planned) {
     const int T = a.n_tracks;
     const int HW = a.g.HW;
     const int n16 = HW >> 4;
-    const int nq = HW >> 2;
     // enough blocks per track to fill the machine at small T, few enough to keep launch tails short at large T
     int bx = (n16 + kThreads - 1) / kThreads;
     int target = max(1, (148 * 8 + T - 1) / T);
@@ -294,10 +332,17 @@ int launch_mask_sync(const MaskSyncArgs& a, cudaStream_t s, bool planned) {
     if (!planned) {
         if (a.new_mask) ROFTB_LAUNCH(k_mask_stats, dim3(bx, T), kThreads, 0, s, a.new_mask, a.new_stride, a.ctl, n16, a.stat);
         ROFTB_LAUNCH(k_warp_plan, (T + 127) / 128, 128, 0, s, T, a.ctl, a.stat, a.plan, a.fbuf, a.new_mask, a.new_stride,
-                     a.state_src, HW, a.segm_delay);
+                     a.state_src, HW, a.segm_delay, a.fuse);
     }
     ROFTB_LAUNCH(k_warp_init, dim3(bx, T), kThreads, 0, s, a.plan, a.new_mask, a.new_stride, a.state_src, a.state_dst,
                  a.winner, HW);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_mask_scatter_gather(const MaskSyncArgs& a, cudaStream_t s) {
+    const int T = a.n_tracks;
+    const int HW = a.g.HW;
+    const int nq = HW >> 2;
     int bq = (nq + kThreads - 1) / kThreads;
     int targetq = max(1, (148 * 16 + T - 1) / T);
     bq = max(1, min(bq, targetq));
@@ -307,6 +352,11 @@ int launch_mask_sync(const MaskSyncArgs& a, cudaStream_t s, bool planned) {
     ROFTB_LAUNCH(k_warp_gather, dim3(bq, T), kThreads, 0, s, a.plan, a.new_mask, a.new_stride, a.state_src, a.state_dst,
                  a.winner, HW);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_mask_sync(const MaskSyncArgs& a, cudaStream_t s, bool planned) {
+    if (launch_mask_plan_init(a, s, planned)) return -1;
+    return launch_mask_scatter_gather(a, s);
 }
 
 int launch_threshold(const uint8_t* src, uint8_t* dst, size_t n, cudaStream_t s) {

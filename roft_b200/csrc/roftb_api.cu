@@ -51,9 +51,10 @@ struct roftb_ctx {
     size_t HW = 0;
     size_t flow_elems = 0;  // scalar elements per track
     int dev = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr;
-    cudaEvent_t vel_event[8], ukf_event[8], join_event = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr;
+    cudaEvent_t vel_event[8], ukf_event[8], join_event = nullptr, plan_event = nullptr, mask_event = nullptr;
     bool ukf_event_used[8];
+    bool mask_event_used = false;
     std::string err;
     long long launches0 = 0;
 
@@ -103,7 +104,7 @@ struct roftb_ctx {
 
     // optional per-phase device timing (bench.py roofline): 8 events per in-flight step
     bool prof_on = false;
-    cudaEvent_t prof_ev[kCtlRing][9];
+    cudaEvent_t prof_ev[kCtlRing][11];
     bool prof_used[kCtlRing];
     double prof_ms[7];
     long long prof_steps = 0;
@@ -238,7 +239,7 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
         ctx->ukf_event_used[i] = false;
         ctx->vel_event[i] = nullptr;
         ctx->ukf_event[i] = nullptr;
-        for (int j = 0; j < 9; ++j) ctx->prof_ev[i][j] = nullptr;
+        for (int j = 0; j < 11; ++j) ctx->prof_ev[i][j] = nullptr;
     }
     for (int j = 0; j < 7; ++j) ctx->prof_ms[j] = 0.0;
     memset(&ctx->ft, 0, sizeof(ctx->ft));
@@ -247,7 +248,8 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     const size_t HW = ctx->HW;
     ctx->n_warp_tiles = (int)((HW + kWarpTilePx - 1) / kWarpTilePx);
     const int n_block_tiles = (int)((HW + kBlockTilePx - 1) / kBlockTilePx);
-    ctx->max_blocks = n_block_tiles;
+    ctx->max_blocks = 256;  // warp partials per track (32 blocks x 8 warps)
+    (void)n_block_tiles;
 #define CKC(call)                                                              \
     do {                                                                       \
         cudaError_t e__ = (call);                                              \
@@ -262,6 +264,9 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->ukf_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->join_event, cudaEventDisableTiming));
+    CKC(cudaStreamCreateWithFlags(&ctx->mask_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->plan_event, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->mask_event, cudaEventDisableTiming));
     for (int i = 0; i < kCtlRing; ++i) {
         CKC(cudaEventCreateWithFlags(&ctx->vel_event[i], cudaEventDisableTiming));
         CKC(cudaEventCreateWithFlags(&ctx->ukf_event[i], cudaEventDisableTiming));
@@ -269,7 +274,7 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
     for (int i = 0; i < kCtlRing; ++i) CKC(cudaEventCreateWithFlags(&ctx->ctl_event[i], cudaEventDisableTiming));
     for (int i = 0; i < kCtlRing; ++i)
-        for (int j = 0; j < 9; ++j) CKC(cudaEventCreate(&ctx->prof_ev[i][j]));
+        for (int j = 0; j < 11; ++j) CKC(cudaEventCreate(&ctx->prof_ev[i][j]));
     CKC(dalloc(&ctx->mask_state[0], T * HW));
     CKC(dalloc(&ctx->mask_state[1], T * HW));
     CKC(dalloc(&ctx->winner, T * HW));
@@ -282,10 +287,10 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(dalloc(&ctx->wt_count, (size_t)T * ctx->n_warp_tiles));
     CKC(dalloc(&ctx->wt_count2, (size_t)T * ctx->n_warp_tiles));
     CKC(dalloc(&ctx->wt_list, (size_t)T * ctx->n_warp_tiles));
-    CKC(dalloc(&ctx->wt_n, (size_t)T));
+    CKC(dalloc(&ctx->wt_n, (size_t)2 * T));
     CKC(dalloc(&ctx->nl_count, (size_t)T * ctx->n_warp_tiles));
     CKC(dalloc(&ctx->nl_list, (size_t)T * ctx->n_warp_tiles));
-    CKC(dalloc(&ctx->nl_n, (size_t)T));
+    CKC(dalloc(&ctx->nl_n, (size_t)2 * T));
     CKC(dalloc(&ctx->stat, (size_t)T));
     CKC(dalloc(&ctx->plan, (size_t)T));
     CKC(dalloc(&ctx->fbuf, (size_t)T));
@@ -348,13 +353,16 @@ void roftb_destroy(roftb_ctx* ctx) {
     for (int i = 0; i < kCtlRing; ++i)
         if (ctx->ctl_event[i]) cudaEventDestroy(ctx->ctl_event[i]);
     for (int i = 0; i < kCtlRing; ++i)
-        for (int j = 0; j < 9; ++j)
+        for (int j = 0; j < 11; ++j)
             if (ctx->prof_ev[i][j]) cudaEventDestroy(ctx->prof_ev[i][j]);
     for (int i = 0; i < kCtlRing; ++i) {
         if (ctx->vel_event[i]) cudaEventDestroy(ctx->vel_event[i]);
         if (ctx->ukf_event[i]) cudaEventDestroy(ctx->ukf_event[i]);
     }
     if (ctx->join_event) cudaEventDestroy(ctx->join_event);
+    if (ctx->plan_event) cudaEventDestroy(ctx->plan_event);
+    if (ctx->mask_event) cudaEventDestroy(ctx->mask_event);
+    if (ctx->mask_stream) { cudaStreamSynchronize(ctx->mask_stream); cudaStreamDestroy(ctx->mask_stream); }
     if (ctx->ukf_stream) { cudaStreamSynchronize(ctx->ukf_stream); cudaStreamDestroy(ctx->ukf_stream); }
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -367,6 +375,7 @@ int roftb_sync(roftb_ctx* ctx) {
     CK(cudaSetDevice(ctx->dev));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->mask_stream));
     CK(cudaStreamSynchronize(ctx->ukf_stream));
     return 0;
 }
@@ -376,16 +385,20 @@ int roftb_join(roftb_ctx* ctx) {
     CK(cudaSetDevice(ctx->dev));
     CK(cudaEventRecord(ctx->join_event, ctx->ukf_stream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->join_event, 0));
+    if (ctx->mask_event_used) CK(cudaStreamWaitEvent(ctx->stream, ctx->mask_event, 0));
     return 0;
 }
 
 static void prof_collect(roftb_ctx* ctx, int slot) {
     if (!ctx->prof_used[slot]) return;
-    cudaEventSynchronize(ctx->prof_ev[slot][6]);
-    cudaEventSynchronize(ctx->prof_ev[slot][8]);
+    cudaEventSynchronize(ctx->prof_ev[slot][5]);
+    cudaEventSynchronize(ctx->prof_ev[slot][7]);
+    cudaEventSynchronize(ctx->prof_ev[slot][9]);
+    // phases: prep (worklist + mask plan/init), pass A, select, pass B, epilogue, mask scatter (own stream), UKF (own stream)
+    static const int kE0[7] = {10, 1, 2, 3, 4, 6, 8}, kE1[7] = {0, 2, 3, 4, 5, 7, 9};
     for (int j = 0; j < 7; ++j) {
         float ms = 0.f;
-        const int e0 = j < 6 ? j : 7, e1 = j < 6 ? j + 1 : 8;
+        const int e0 = kE0[j], e1 = kE1[j];
         if (cudaEventElapsedTime(&ms, ctx->prof_ev[slot][e0], ctx->prof_ev[slot][e1]) == cudaSuccess) ctx->prof_ms[j] += ms;
     }
     ctx->prof_steps++;
@@ -413,7 +426,9 @@ int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mea
     const int T = ctx->T;
     CK(cudaSetDevice(ctx->dev));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->mask_stream));
     CK(cudaStreamSynchronize(ctx->ukf_stream));
+    ctx->mask_event_used = false;
     // ROFTFilter::initialization_step (ROFTFilter.cpp:216-237)
     std::vector<double> pm((size_t)T * 13, 0.0), pc((size_t)T * 144, 0.0), vm((size_t)T * 6, 0.0), vc((size_t)T * 36, 0.0);
     for (int t = 0; t < T; ++t) {
@@ -659,16 +674,45 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
     }
     ctx->ctl_event_used[cslot] = true;
 
-    // ---- device work: velocity (previous mask/depth, current flow), mask sync, pose UKF ---------
+    // ---- device work ------------------------------------------------------------------------------
+    // main stream : worklist -> mask plan/init -> velocity passes (the first pass also propagates the mask of
+    //               the tracks that received no new mask) -> 6x6 epilogue
+    // mask stream : scatter/gather of the tracks with a NEW mask (chained through the buffered flows)
+    // ukf stream  : pose UKF (needs only the twist published by the epilogue and the host-built op list)
     const uint8_t* seg_prev = ctx->mask_state[ctx->mask_cur];
     uint8_t* seg_next = ctx->mask_state[ctx->mask_cur ^ 1];
-    // worklists of non-empty warp tiles: the state mask (velocity pass + propagation scatter) and the new mask
+    cudaEvent_t* pe = ctx->prof_on ? ctx->prof_ev[cslot] : nullptr;
+    if (pe) prof_collect(ctx, cslot);
+    // the previous step's mask stream work produced (part of) seg_prev
+    if (ctx->mask_event_used) CK(cudaStreamWaitEvent(s, ctx->mask_event, 0));
+    if (pe) CK(cudaEventRecord(pe[10], s));
     if (launch_tile_list(seg_prev, (long long)ctx->HW, 1, ctx->g.HW, T, ctx->wt_count, ctx->wt_list, ctx->wt_n, nullptr, 0, s))
         return fail(ctx, "launch_tile_list failed");
+    MaskSyncArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.g = ctx->g; ma.ft = ctx->ft; ma.n_tracks = T;
+    ma.new_mask = any_new_mask ? d_mask : nullptr; ma.new_stride = mask_stride;
+    ma.state_src = seg_prev; ma.state_dst = seg_next; ma.winner = ctx->winner;
+    ma.ctl = ctx->d_wctl; ma.stat = ctx->stat; ma.plan = ctx->plan; ma.fbuf = ctx->fbuf;
+    ma.segm_delay = cfg.segm_delay;
+    ma.s_list = ctx->wt_list; ma.s_n = ctx->wt_n; ma.n_list = ctx->nl_list; ma.n_n = ctx->nl_n; ma.n_warp_tiles = ctx->n_warp_tiles;
+    ma.fuse = 1;
+    if (launch_mask_plan_init(ma, s)) return fail(ctx, "launch_mask_plan_init failed");
     if (any_new_mask &&
         launch_tile_list(d_mask, mask_stride, 0, ctx->g.HW, T, ctx->nl_count, ctx->nl_list, ctx->nl_n,
                          reinterpret_cast<const int32_t*>(ctx->d_wctl), (int)(sizeof(WarpCtl) / 4), s))
         return fail(ctx, "launch_tile_list failed");
+    CK(cudaEventRecord(ctx->plan_event, s));
+    {
+        cudaStream_t ms = ctx->mask_stream;
+        CK(cudaStreamWaitEvent(ms, ctx->plan_event, 0));
+        if (pe) CK(cudaEventRecord(pe[6], ms));
+        if (launch_mask_scatter_gather(ma, ms)) return fail(ctx, "launch_mask_scatter_gather failed");
+        if (pe) CK(cudaEventRecord(pe[7], ms));
+        CK(cudaEventRecord(ctx->mask_event, ms));
+        ctx->mask_event_used = true;
+        ctx->mask_cur ^= 1;
+    }
     {
         VelocityArgs a;
         memset(&a, 0, sizeof(a));
@@ -684,15 +728,12 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
         a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
         a.out_count = ctx->d_count; a.out_lambda = ctx->d_lambda; a.out_eta = ctx->d_eta;
         a.update_state = 1;
-        if (ctx->prof_on) {
-            prof_collect(ctx, cslot);
-            a.prof = ctx->prof_ev[cslot];
-        }
+        a.fuse_scatter = 1; a.plan = ctx->plan; a.state_dst = seg_next; a.winner = ctx->winner;
+        a.prof = pe;
         if (launch_velocity(a, s)) return fail(ctx, "launch_velocity failed");
         CK(cudaEventRecord(ctx->vel_event[cslot], s));
     }
     {
-        // pose UKF on its own stream: it only needs this step's twist (vel_hist) and the host-built op list
         cudaStream_t us = ctx->ukf_stream;
         CK(cudaStreamWaitEvent(us, ctx->vel_event[cslot], 0));
         UkfArgs a;
@@ -701,29 +742,20 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
         a.ops = d_ops; a.n_ops = d_nops; a.max_ops = kMaxUkfOps;
         a.mean = ctx->p_mean; a.cov = ctx->p_cov; a.buf_mean = ctx->pb_mean; a.buf_cov = ctx->pb_cov;
         a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
-        if (ctx->prof_on) CK(cudaEventRecord(ctx->prof_ev[cslot][7], us));
+        if (pe) CK(cudaEventRecord(pe[8], us));
         if (launch_ukf(a, us)) return fail(ctx, "launch_ukf failed");
-        if (ctx->prof_on) {
-            CK(cudaEventRecord(ctx->prof_ev[cslot][8], us));
+        if (pe) {
+            CK(cudaEventRecord(pe[9], us));
             ctx->prof_used[cslot] = true;
         }
         CK(cudaEventRecord(ctx->ukf_event[cslot], us));
         ctx->ukf_event_used[cslot] = true;
     }
-    {
-        MaskSyncArgs a;
-        memset(&a, 0, sizeof(a));
-        a.g = ctx->g; a.ft = ctx->ft; a.n_tracks = T;
-        a.new_mask = any_new_mask ? d_mask : nullptr; a.new_stride = mask_stride;
-        a.state_src = seg_prev; a.state_dst = seg_next; a.winner = ctx->winner;
-        a.ctl = ctx->d_wctl; a.stat = ctx->stat; a.plan = ctx->plan; a.fbuf = ctx->fbuf;
-        a.segm_delay = cfg.segm_delay;
-        a.s_list = ctx->wt_list; a.s_n = ctx->wt_n; a.n_list = ctx->nl_list; a.n_n = ctx->nl_n; a.n_warp_tiles = ctx->n_warp_tiles;
-        if (launch_mask_sync(a, s)) return fail(ctx, "launch_mask_sync failed");
-        ctx->mask_cur ^= 1;
-        if (ctx->prof_on) CK(cudaEventRecord(ctx->prof_ev[cslot][6], s));
+    // staged host frames may be overwritten once BOTH the main and the mask stream are done with them
+    if (f->memory == ROFTB_MEM_HOST) {
+        CK(cudaStreamWaitEvent(s, ctx->mask_event, 0));
+        CK(cudaEventRecord(ctx->copy_done, s));
     }
-    if (f->memory == ROFTB_MEM_HOST) CK(cudaEventRecord(ctx->copy_done, s));
     (void)any_vel;
     ctx->frame_idx++;
     cudaError_t e = cudaGetLastError();
@@ -752,6 +784,7 @@ int roftb_get_mask(roftb_ctx* ctx, uint8_t* raw, uint8_t* thresholded) {
     CK(cudaSetDevice(ctx->dev));
     cudaStream_t s = ctx->stream;
     const uint8_t* cur = ctx->mask_state[ctx->mask_cur];
+    if (ctx->mask_event_used) CK(cudaStreamWaitEvent(s, ctx->mask_event, 0));
     if (raw) CK(cudaMemcpyAsync(raw, cur, n, cudaMemcpyDeviceToHost, s));
     if (thresholded) {
         if (!ctx->thr_tmp) CK(cudaMalloc(&ctx->thr_tmp, n));
@@ -850,7 +883,7 @@ int roftb_mask_sync(roftb_ctx* ctx, int32_t n_masks, const uint8_t* mask, const 
         const int nwt = ctx->n_warp_tiles;
         int32_t* cnt = tb.alloc<int32_t>(N * nwt);
         int32_t* lst = tb.alloc<int32_t>(N * nwt);
-        int32_t* ln = tb.alloc<int32_t>(N);
+        int32_t* ln = tb.alloc<int32_t>(2 * N);
         if (!cnt || !lst || !ln) return fail(ctx, "roftb_mask_sync: out of device memory");
         if (launch_tile_list(d_mask, (long long)HW, 0, ctx->g.HW, (int)N, cnt, lst, ln, nullptr, 0, s)) return fail(ctx, "launch_tile_list failed");
         a.s_list = lst; a.s_n = ln; a.n_list = lst; a.n_n = ln; a.n_warp_tiles = nwt;
@@ -897,7 +930,7 @@ static int velocity_operator(roftb_ctx* ctx, int32_t n, const uint8_t* mask, con
     a.ctl = d_ctl; a.weight_flow = ctx->cfg.weight_flow;
     a.wt_count = tb.alloc<int32_t>(N * nwt);
     a.wt_list = tb.alloc<int32_t>(N * nwt);
-    a.wt_n = tb.alloc<int32_t>(N);
+    a.wt_n = tb.alloc<int32_t>(2 * N);
     a.norms = tb.alloc<float>(N * HW);
     a.norm_count = tb.alloc<uint32_t>(N, true);
     a.hist = tb.alloc<uint32_t>(N * kSelBins, true);

@@ -70,7 +70,8 @@ struct WarpPlan {          // device-resolved by k_warp_plan
     int32_t flow_slot[kMaxFlows];
     int32_t uniform_val;   // >0: every non-zero source pixel has this value (byte-store fast path)
     int32_t dflt;          // value sampled by unmapped destinations = src(0,0) (Q2)
-    int32_t pad[2];
+    int32_t fused;         // 1: the scatter of this track is done by the velocity pass (single current flow, state source)
+    int32_t pad;
 };
 
 struct FlowBuf {           // per-track device mirror of flow_buffer_ (hpp:82,208,218)
@@ -99,8 +100,8 @@ struct WeightParams {      // Laplacian re-weighting parameters (SKFCorrection.c
 struct SelState {          // radix-select state (upper median = s[n/2])
     uint32_t prefix;       // key bits fixed so far
     uint32_t k;            // remaining rank inside the prefix
-    uint32_t n;
-    uint32_t pad;
+    uint32_t n;            // valid measurements
+    uint32_t n_entries;    // norm slots (valid + gated-out)
     // statistics gathered by the last pass
     unsigned long long less_cnt;
     double less_sum;
@@ -142,7 +143,12 @@ struct MaskSyncArgs {
     const int32_t* s_list; const int32_t* s_n;
     const int32_t* n_list; const int32_t* n_n;
     int n_warp_tiles;
+    int fuse;              // allow k_warp_plan to hand single-flow propagation to the velocity pass
 };
+// the mask synchronisation in two halves: (stats, plan, init) must precede a fused velocity pass; (scatter of the
+// non-fused tracks, gather) may run concurrently with the velocity passes
+int launch_mask_plan_init(const MaskSyncArgs& a, cudaStream_t s, bool planned = false);
+int launch_mask_scatter_gather(const MaskSyncArgs& a, cudaStream_t s);
 // planned = true: a.plan was filled by the caller (operator mode), skip the stats / plan kernels
 int launch_mask_sync(const MaskSyncArgs& a, cudaStream_t s, bool planned = false);
 int launch_threshold(const uint8_t* src, uint8_t* dst, size_t n, cudaStream_t s);
@@ -157,7 +163,7 @@ struct VelocityArgs {
     // scratch
     int32_t* wt_count;      // [T][n_warp_tiles] row-major rank base of each warp tile   } built by
     int32_t* wt_list;       // [T][n_warp_tiles] non-empty warp tiles of the mask        } launch_tile_list
-    int32_t* wt_n;          // [T] their number                                          }
+    int32_t* wt_n;          // [2T] their number, then the candidate totals              }
     float* norms;           // [T][HW]
     uint32_t* norm_count;   // [T]
     uint32_t* hist;         // [T][kSelBins]
@@ -174,6 +180,8 @@ struct VelocityArgs {
     double* vel_hist; int hist_ring;   // [T][ring][6]
     // diagnostics
     int32_t* out_count; double* out_lambda; double* out_eta;  // device [T], [T][36], [T][6]
+    // fused mask propagation (see WarpPlan::fused)
+    int fuse_scatter; const WarpPlan* plan; uint8_t* state_dst; int32_t* winner;
     cudaEvent_t* prof;                 // optional: 6 events recorded at the phase boundaries (start, rank, pass A,
                                        // select, pass B, epilogue)
     int update_state;                  // 0: only compute lambda/eta/count (operator mode)
