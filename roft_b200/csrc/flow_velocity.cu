@@ -182,8 +182,18 @@ struct PassArgs {
 // from the worklist prefix), so pass A needs no atomics; gated-out candidates are marked with -1.
 // SCATTER: the same walk also forward-scatters every non-zero mask pixel through the current flow (the "no new mask"
 // propagation of the mask synchronisation) - it needs exactly the mask words and flow values this pass loads anyway.
+//
+// The per-pixel body is written for instruction count (the kernel is issue-bound, not DRAM-bound): predicates instead
+// of branches, one multiply to pack the per-byte compare result into a nibble, unsigned range checks, lane-private
+// norm slots (one warp scan per tile instead of a ballot per pixel), row/column tracked incrementally instead of a
+// division per quad.
+__device__ __forceinline__ uint32_t nibble_of(uint32_t bytemask) {
+    // bytemask has 0xff / 0x00 per byte (vcmp result): gather bit 0 of each byte into bits 0..3
+    return ((bytemask & 0x01010101u) * 0x10204080u) >> 28;
+}
+
 template <int PASS, bool FAST, typename AT, bool SCATTER>
-__global__ void __launch_bounds__(kThreads, 2) k_flow_pass(PassArgs a) {
+__global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassArgs a) {
     const int t = blockIdx.y;
     const VelCtl c = a.ctl[t];
     bool do_sc = false;
@@ -203,7 +213,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_flow_pass(PassArgs a) {
                         (long long)t * a.ft.flow_stride * (g.flow_s16 ? 2 : 4);
     const float4* fq = reinterpret_cast<const float4*>(fbase);
     const int nq = g.HW >> 2;
-    const uint32_t lt = (1u << lane) - 1u;
+    const int W = g.W;
+    const unsigned uW = (unsigned)g.W, uH = (unsigned)g.H;
+    uint8_t* dst_t = SCATTER ? a.state_dst + (long long)t * g.HW : nullptr;
+    float* norms_t = a.norms + (long long)t * g.HW;
+    const float inv_fx = g.inv_fx, max_d = g.max_depth_f;
 
     // predicted velocity (F = I: the predicted mean is the previous corrected mean) and FP32 row scales
     float x[6];
@@ -219,7 +233,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_flow_pass(PassArgs a) {
 #pragma unroll
         for (int i = 0; i < kNAcc; ++i) acc[i] = (AT)0;
     }
-    float* norms_out = a.norms + (long long)t * g.HW;
 
     const int n_list = a.wt_n[t];
     const int32_t* list = a.wt_list + (long long)t * a.n_warp_tiles;
@@ -234,14 +247,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_flow_pass(PassArgs a) {
         for (int j = 0; j < 4; ++j) {
             const int q = q0 + j * 32;
             const uint32_t m = q < nq ? ld_nc_u32(mq + q) : 0u;
-            const uint32_t s8 = __vcmpgtu4(m, thr4);
-            sel |= ((s8 & 1u) | ((s8 >> 7) & 2u) | ((s8 >> 14) & 4u) | ((s8 >> 21) & 8u)) << (4 * j);
-            if (SCATTER) {
-                uint32_t z8 = __vcmpne4(m, 0u);
-                if (q == 0) z8 &= 0xffffff00u;  // mask_(0,0) = 0 (hpp:224)
-                scs |= ((z8 & 1u) | ((z8 >> 7) & 2u) | ((z8 >> 14) & 4u) | ((z8 >> 21) & 8u)) << (4 * j);
-            }
+            sel |= nibble_of(__vcmpgtu4(m, thr4)) << (4 * j);
+            if (SCATTER) scs |= nibble_of(__vcmpne4(m, 0u)) << (4 * j);
         }
+        if (SCATTER && q0 == 0) scs &= ~1u;  // mask_(0,0) = 0 (hpp:224)
         if (!c.enable) sel = 0;
         if (!do_sc) scs = 0;
         const int rank0 = prefix[wt];  // candidates (row-major) before this tile
@@ -274,6 +283,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_flow_pass(PassArgs a) {
         const uint32_t need = sel | scs;
         if (!__any_sync(0xffffffffu, need != 0u)) continue;
 
+        // lane-private norm slots: [nbase + (candidates of the lower lanes), + own candidates)
+        float* np = norms_t;
+        if (PASS == 0) {
+            const int mine = __popc(sel);
+            np += nbase + warp_scan_incl(mine, lane) - mine;
+        }
+
+        // row / first column of this lane's first quad; the next quads are 128 px further along the row-major order
+        int px = q0 << 2;
+        int v = px / W;
+        int u0 = px - v * W;
+
         // software pipeline over the four quads: loads of quad j+1 are issued before quad j is processed
         float4 Dc, F0c, F1c, Dn, F0n, F1n;
         {
@@ -297,107 +318,115 @@ __global__ void __launch_bounds__(kThreads, 2) k_flow_pass(PassArgs a) {
             }
             const uint32_t nib = (sel >> (4 * j)) & 0xfu;
             const uint32_t snib = (scs >> (4 * j)) & 0xfu;
-            const int px = (q0 + j * 32) << 2;
-            const int v = px / g.W;
-            const int u0 = px - v * g.W;
-            // normalised coordinates from FP64 intrinsics (a rounded 1/fx would bias every pixel the same way)
-            const double yhd = ((double)v - a.cyd) * a.inv_fyd;
-            const double xh0d = ((double)u0 - a.cxd) * a.inv_fxd;
-            const float yh = (float)yhd;
-            const float xh0 = (float)xh0d;
+            if ((nib | snib) != 0u) {
+                const float vf = (float)v;
+                float yh, xh0;
+                double yhd = 0.0, xh0d = 0.0;
+                if (PASS == 1) {
+                    // normalised coordinates from FP64 intrinsics (a rounded 1/fx would bias every pixel the same way)
+                    yhd = ((double)v - a.cyd) * a.inv_fyd;
+                    xh0d = ((double)u0 - a.cxd) * a.inv_fxd;
+                    yh = (float)yhd;
+                    xh0 = (float)xh0d;
+                } else {
+                    // pass A only feeds the Laplacian weights: FP32 coordinates are plenty
+                    yh = (vf - g.cy) * g.inv_fy;
+                    xh0 = ((float)u0 - g.cx) * inv_fx;
+                }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool cand = (nib >> i) & 1u;
-                const bool scand = SCATTER && ((snib >> i) & 1u);
-                bool valid = false;
-                float nr = -1.0f;
-                float dx = 0.f, dy = 0.f, d = 1.f, xh = 0.f, ia = 0.f;
-                float l1[5], l2[5];
-                if (cand || scand) {
+                for (int i = 0; i < 4; ++i) {
+                    const bool cand = (nib >> i) & 1u;
+                    float dx, dy;
                     if (FAST) {
                         const float4 f = i < 2 ? F0c : F1c;
                         dx = (i & 1) ? f.z : f.x;  // FAST: float2 flow, grid 1, scale 1
                         dy = (i & 1) ? f.w : f.y;
                     } else {
-                        const int u = u0 + i;
-                        const float2 f = load_flow(fbase, (long long)(v / g.grid) * g.Wf + (u / g.grid), g);
-                        dx = f.x;
-                        dy = f.y;
+                        dx = 0.f;
+                        dy = 0.f;
+                        if (cand || (SCATTER && ((snib >> i) & 1u))) {
+                            const float2 f = load_flow(fbase, (long long)(v / g.grid) * g.Wf + ((u0 + i) / g.grid), g);
+                            dx = f.x;
+                            dy = f.y;
+                        }
                     }
-                }
-                if (scand) {
-                    // hpp:249-278 for a single flow: the source pixel is inside the frame and its flow element is the one
-                    // just fetched; IEEE adds, x86 truncation, last check on the destination
-                    const float tx = __fadd_rn((float)(u0 + i), dx), ty = __fadd_rn((float)v, dy);
-                    const int ix = cvt_int(tx), iy = cvt_int(ty);
-                    if (ix >= 0 && ix < g.W && iy >= 0 && iy < g.H) {
-                        a.state_dst[(long long)t * g.HW + iy * g.W + ix] = sc_val;
+                    if (SCATTER) {
+                        // hpp:249-278 for a single flow: the source pixel is inside the frame and its flow element is the
+                        // one just fetched; IEEE adds; C truncation (a NaN would convert to 0 on the GPU, so it is tested;
+                        // +-inf / huge values saturate outside the frame exactly like x86's INT_MIN)
+                        const float tx = __fadd_rn((float)(u0 + i), dx), ty = __fadd_rn(vf, dy);
+                        const unsigned ix = (unsigned)(int)tx, iy = (unsigned)(int)ty;
+                        const bool ok = ((snib >> i) & 1u) && tx == tx && ty == ty && ix < uW && iy < uH;
+                        if (ok) dst_t[iy * uW + ix] = sc_val;
                     }
-                }
-                if (cand) {
-                    d = comp(Dc, i);
+                    const float d = comp(Dc, i);
                     // hpp:252 gates
-                    valid = flow_valid(dx, dy) && d > 0.f && d < g.max_depth_f;
-                    if (valid) {
-                        xh = fmaf((float)i, g.inv_fx, xh0);
-                        ia = rcp_approx(d);
-                        l1[0] = ia; l1[1] = -xh * ia; l1[2] = -xh * yh; l1[3] = 1.0f + xh * xh; l1[4] = -yh;
-                        l2[0] = ia; l2[1] = -yh * ia; l2[2] = -(1.0f + yh * yh); l2[3] = xh * yh; l2[4] = xh;
-                        const float p1 = l1[0] * x[0] + l1[1] * x[2] + l1[2] * x[3] + l1[3] * x[4] + l1[4] * x[5];
-                        const float p2 = l2[0] * x[1] + l2[1] * x[2] + l2[2] * x[3] + l2[3] * x[4] + l2[4] * x[5];
-                        const float n1 = dx - c1 * p1, n2 = dy - c2 * p2;
-                        nr = sqrt_approx(n1 * n1 + n2 * n2);
-                    }
-                }
-                if (PASS == 0) {
-                    const uint32_t ball = __ballot_sync(0xffffffffu, cand);
-                    if (cand) norms_out[nbase + __popc(ball & lt)] = nr;
-                    nbase += __popc(ball);
-                } else if (valid) {
-                    float l = 1.0f;
-                    if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
-                    AT e1[5], e2[5];
-                    if (sizeof(AT) == 8) {
-                        // FP64 per-pixel terms: 1/d refined from the FP32 reciprocal by two Newton steps
-                        const double xhd = fma((double)i, a.inv_fxd, xh0d);
-                        double r = (double)ia;
-                        r = r * (2.0 - (double)d * r);
-                        r = r * (2.0 - (double)d * r);
-                        e1[0] = (AT)r; e1[1] = (AT)(-xhd * r); e1[2] = (AT)(-xhd * yhd); e1[3] = (AT)(1.0 + xhd * xhd); e1[4] = (AT)(-yhd);
-                        e2[0] = (AT)r; e2[1] = (AT)(-yhd * r); e2[2] = (AT)(-(1.0 + yhd * yhd)); e2[3] = (AT)(xhd * yhd); e2[4] = (AT)xhd;
-                    } else {
+                    const bool valid = cand && fabsf(dx) < 1e9f && fabsf(dy) < 1e9f && d > 0.f && d < max_d;
+                    const float xh = fmaf((float)i, inv_fx, xh0);
+                    const float ia = rcp_approx(d);
+                    float l1[5], l2[5];
+                    l1[0] = ia; l1[1] = -xh * ia; l1[2] = -xh * yh; l1[3] = fmaf(xh, xh, 1.0f); l1[4] = -yh;
+                    l2[0] = ia; l2[1] = -yh * ia; l2[2] = -fmaf(yh, yh, 1.0f); l2[3] = xh * yh; l2[4] = xh;
+                    const float p1 = l1[0] * x[0] + l1[1] * x[2] + l1[2] * x[3] + l1[3] * x[4] + l1[4] * x[5];
+                    const float p2 = l2[0] * x[1] + l2[1] * x[2] + l2[2] * x[3] + l2[3] * x[4] + l2[4] * x[5];
+                    const float n1 = dx - c1 * p1, n2 = dy - c2 * p2;
+                    const float nr = sqrt_approx(n1 * n1 + n2 * n2);
+                    if (PASS == 0) {
+                        if (cand) *np++ = valid ? nr : -1.0f;  // gated-out candidates are marked
+                    } else if (valid) {
+                        float l = 1.0f;
+                        if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
+                        AT e1[5], e2[5];
+                        if (sizeof(AT) == 8) {
+                            // FP64 per-pixel terms: 1/d from the FP32 approximation (rel. error < 2^-22) by two Newton steps
+                            // (error^2 per step: 6e-14, then below 1 ulp)
+                            const double xhd = fma((double)i, a.inv_fxd, xh0d);
+                            const double dd = (double)d;
+                            double r = (double)ia;
+                            r = fma(r, fma(-dd, r, 1.0), r);
+                            r = fma(r, fma(-dd, r, 1.0), r);
+                            e1[0] = (AT)r; e1[1] = (AT)(-xhd * r); e1[2] = (AT)(-xhd * yhd); e1[3] = (AT)(1.0 + xhd * xhd); e1[4] = (AT)(-yhd);
+                            e2[0] = (AT)r; e2[1] = (AT)(-yhd * r); e2[2] = (AT)(-(1.0 + yhd * yhd)); e2[3] = (AT)(xhd * yhd); e2[4] = (AT)xhd;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) {
+                                e1[k] = (AT)l1[k];
+                                e2[k] = (AT)l2[k];
+                            }
+                        }
+                        AT w1[5], w2[5];
 #pragma unroll
                         for (int k = 0; k < 5; ++k) {
-                            e1[k] = (AT)l1[k];
-                            e2[k] = (AT)l2[k];
+                            w1[k] = (AT)l * e1[k];
+                            w2[k] = (AT)l * e2[k];
                         }
-                    }
-                    AT w1[5], w2[5];
+                        int o = 0;
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        w1[k] = (AT)l * e1[k];
-                        w2[k] = (AT)l * e2[k];
-                    }
-                    int o = 0;
+                        for (int r = 0; r < 5; ++r)
 #pragma unroll
-                    for (int r = 0; r < 5; ++r)
+                            for (int s = r; s < 5; ++s) {
+                                acc[o] = fma(w1[r], e1[s], acc[o]);
+                                acc[15 + o] = fma(w2[r], e2[s], acc[15 + o]);
+                                ++o;
+                            }
 #pragma unroll
-                        for (int s = r; s < 5; ++s) {
-                            acc[o] = fma(w1[r], e1[s], acc[o]);
-                            acc[15 + o] = fma(w2[r], e2[s], acc[15 + o]);
-                            ++o;
+                        for (int k = 0; k < 5; ++k) {
+                            acc[30 + k] = fma(w1[k], (AT)dx, acc[30 + k]);
+                            acc[35 + k] = fma(w2[k], (AT)dy, acc[35 + k]);
                         }
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        acc[30 + k] = fma(w1[k], (AT)dx, acc[30 + k]);
-                        acc[35 + k] = fma(w2[k], (AT)dy, acc[35 + k]);
+                        acc[40] += (AT)1;
                     }
-                    acc[40] += (AT)1;
                 }
             }
             Dc = Dn;
             F0c = F0n;
             F1c = F1n;
+            // next quad: 128 px ahead
+            u0 += 128;
+            while (u0 >= W) {
+                u0 -= W;
+                ++v;
+            }
         }
     }
 
