@@ -1,0 +1,96 @@
+"""Host-side C++ mirror of the reference interface (roft_b200/host): dataset formats, delay schedule and - on a GPU -
+the batched ROFTFilter driven from Fast-YCB-format directories by the roft_b200_tracker executable."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import roft_oracle as o
+from helpers import frame_inputs, quat_close, rel, sequence, small_cfg
+from roft_b200 import dataset_io
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "roft_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def hostlib(lib_built):
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    return ctypes.CDLL(os.path.join(HOST, "libroft_b200_host.so"))
+
+
+def test_flow_file_format_roundtrip(hostlib, tmp_path):
+    rng = np.random.default_rng(0)
+    for flow in (rng.normal(0, 3, (18, 32, 2)).astype(np.float32), rng.integers(-900, 900, (9, 16, 2)).astype(np.int16)):
+        a, b = str(tmp_path / "a.float"), str(tmp_path / "b.float")
+        dataset_io.write_flow(a, flow)
+        t = ctypes.c_int(0); c = ctypes.c_ulonglong(0); r = ctypes.c_ulonglong(0)
+        assert hostlib.rofth_flow_roundtrip(a.encode(), b.encode(), ctypes.byref(t), ctypes.byref(c), ctypes.byref(r)) == 0
+        assert (t.value, c.value, r.value) == (11 if flow.dtype == np.int16 else 13, flow.shape[1], flow.shape[0])
+        assert open(a, "rb").read() == open(b, "rb").read()  # 20-byte header, no padding (OpticalFlowUtilities.cpp:38-62)
+        assert os.path.getsize(a) == 20 + flow.nbytes
+        assert np.array_equal(dataset_io.read_flow(b), flow)
+    assert hostlib.rofth_flow_roundtrip(b"/nonexistent.float", b"/tmp/x", ctypes.byref(t), ctypes.byref(c), ctypes.byref(r)) < 0
+
+
+def test_delay_schedule_and_flow_validity(hostlib):
+    for delay in (1, 4, 6):
+        s = o.DelayedMaskSchedule(delay)
+        for head in range(0, 30):
+            e = s.index_for(head)
+            assert hostlib.rofth_delivered_index(head, delay, 0, 1) == (-1 if e is None else e)
+    hostlib.rofth_is_flow_valid.argtypes = [ctypes.c_float, ctypes.c_float]
+    for fx, fy, ok in ((0.5, -3.0, 1), (float("nan"), 0.0, 0), (0.0, float("inf"), 0), (1e10, 0.0, 0), (-9.9e8, 9.9e8, 1)):
+        assert hostlib.rofth_is_flow_valid(fx, fy) == ok
+
+
+def test_depth_file_roundtrip(tmp_path):
+    d = np.random.default_rng(1).uniform(0, 2, (12, 20)).astype(np.float32)
+    p = str(tmp_path / "0.float")
+    dataset_io.write_depth(p, d)
+    assert os.path.getsize(p) == 16 + d.nbytes and np.array_equal(dataset_io.read_depth(p), d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["f32", "s16"])
+def test_tracker_executable_matches_oracle(hostlib, tmp_path, fmt):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = small_cfg(flow_grid=1 if fmt == "f32" else 4, flow_scale=1.0 if fmt == "f32" else 32.0, subsampling_radius=4.0,
+                    segm_delay=3, pose_delay=3, sample_time=1.0 / 30.0)
+    T, F = 2, 10
+    seq = sequence(cfg, T, F, flow_format=fmt, target_coverage=0.3)
+    args = [os.path.join(HOST, "roft_b200_tracker"), "--log", str(tmp_path), "--stride", "4", "--desired-fps", "10"]
+    for t in range(T):
+        root = str(tmp_path / f"seq{t}")
+        dataset_io.write_sequence(root, seq, t, fx=cfg.fx, fy=cfg.fy, cx=cfg.cx, cy=cfg.cy)
+        args += ["--sequence", root]
+    out = subprocess.run(args, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert f"tracked {F} frames x {T} tracks" in out.stdout
+    for t in range(T):
+        pose_log = np.loadtxt(tmp_path / f"track{t}_pose_estimate.txt")
+        vel_log = np.loadtxt(tmp_path / f"track{t}_velocity_estimate.txt")
+        assert pose_log.shape == (F, 13) and vel_log.shape == (F, 6)
+        x0 = np.zeros(13)
+        # the executable initialises from the first pose row, which went through axis-angle text
+        aa = dataset_io.quat_to_axis_angle(seq.pose[0, t].numpy()[3:])
+        x0[6:9] = seq.pose[0, t, :3].numpy()
+        x0[9] = np.cos(aa[3] / 2); x0[10:] = np.sin(aa[3] / 2) * aa[:3]
+        orc = o.RoftFilterOracle(cfg, x0)
+        for k in range(F):
+            fr = frame_inputs(seq, cfg, k, t)
+            if fr.pose is not None:  # poses.txt stores axis-angle
+                a2 = dataset_io.quat_to_axis_angle(fr.pose[3:])
+                fr.pose = np.concatenate([fr.pose[:3], [np.cos(a2[3] / 2)], np.sin(a2[3] / 2) * a2[:3]])
+            fr.dt = None if k == 0 else (k * seq.dt - (k - 1) * seq.dt)
+            ep, ev = orc.step(fr)
+            assert rel(vel_log[k], ev) < 1e-4 or np.linalg.norm(vel_log[k] - ev) < 1e-9, (k, t)
+            assert rel(pose_log[k, :9], ep[:9]) < 1e-4, (k, t)
+            eaa = dataset_io.quat_to_axis_angle(ep[9:])
+            q_log = np.concatenate([[np.cos(pose_log[k, 12] / 2)], np.sin(pose_log[k, 12] / 2) * pose_log[k, 9:12]])
+            q_exp = np.concatenate([[np.cos(eaa[3] / 2)], np.sin(eaa[3] / 2) * eaa[:3]])
+            assert quat_close(q_log, q_exp) < 1e-4, (k, t)
