@@ -37,8 +37,8 @@ BYTES_PER_TRACK_FRAME = W * H * (4 + 8 + 1)  # depth f32 + dense flow 2xf32 + ma
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=24)
-    ap.add_argument("--warmup", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=120)
+    ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", default="roft_b200", choices=["roft_b200", "reference"])
     ap.add_argument("--tracks", type=int, default=256, help="tracks per GPU")
     ap.add_argument("--frames", type=int, default=12, help="distinct resident frames per track")
@@ -73,11 +73,11 @@ class ClockSampler(threading.Thread):
             for line in self.proc.stdout:
                 if self.stop_flag.is_set():
                     break
-                self.samples.append([x.strip() for x in line.split(",")])
+                self.samples.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
         except Exception:
             pass
 
-    def finish(self):
+    def finish(self, t0=None, t1=None):
         self.stop_flag.set()
         if self.proc:
             try:
@@ -86,7 +86,10 @@ class ClockSampler(threading.Thread):
                 pass
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        inside = [s for (ts, s) in self.samples if t0 is None or (t0 <= ts <= t1 + 0.15)]
+        if not inside and self.samples:  # region shorter than the sampling period: take the closest samples
+            inside = [s for (_, s) in self.samples[-2:]]
+        for s in inside:
             try:
                 sm.append(float(s[0])); mx = max(mx, float(s[1]))
                 for n, v in zip(names, s[3:7]):
@@ -106,6 +109,19 @@ def measured_peak_gbs():
             return float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def ncu_traffic(kernel: str, tracks: int, fp32: bool):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            d = json.load(f)
+        e = d.get(kernel + ("_fp32" if fp32 and kernel == "flow_pass_b" else ""))
+        if e and e.get("tracks") == tracks:
+            return e["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 def workload_name(args):
@@ -179,13 +195,13 @@ def run_own(args):
 
     # ---- device-resident throughput ------------------------------------------------------
     step = 0
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(args.warmup):
         do_step(step); step += 1
     barrier()
     trk.profile(True)
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     l0 = trk.kernel_launches
     barrier()
     t0 = time.perf_counter()
@@ -201,7 +217,7 @@ def run_own(args):
     dev_ms = ev0.elapsed_time(ev1)
     launches = trk.kernel_launches - l0
     phases, psteps = trk.profile(False)
-    clocks = sampler.finish() if sampler else None
+    clocks = sampler.finish(t0, t0 + wall) if sampler else None
     tms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -265,7 +281,8 @@ def run_own(args):
                    "l2_policy": f"inputs larger than L2: {T * BYTES_PER_TRACK_FRAME / 1e9:.2f} GB touched per step, no flush needed",
                    "accumulation": "fp32" if args.fp32_accum else "fp64", "parallelism": f"tracks partitioned over {world} GPU(s), no collective"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_kind": peak_kind,
+                     "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(dom, T, args.fp32_accum),
+                     "peak_kind": peak_kind, "kernel_ms": dom_ms,
                      "whole_step_achieved": step_bytes_gbs, "whole_step_frac": step_bytes_gbs / peak,
                      "algorithmic_bytes_per_track_frame": BYTES_PER_TRACK_FRAME},
         "phases_ms_per_step": phases,
