@@ -1,3 +1,4 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --no-cpu 2>&1 | tail -1 > gpurun_out/bench_r1_2gpu.json; python -c "
-import json; d=json.load(open('gpurun_out/bench_r1_2gpu.json')); print(round(d['value']), d['n_gpus'], round(d['ms_per_step'],3), d['e2e'], d['clocks'])"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --impl reference --cpu-seconds 5 2>&1 | tail -1 | cut -c1-200
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -m gpu -x 2>&1 | tail -3
+for extra in "" ; do
+timeout 800 python bench.py --no-cpu --no-e2e $extra --steps 24 --warmup 6 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['phases_ms_per_step'].items()})"
+done

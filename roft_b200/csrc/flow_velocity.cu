@@ -81,13 +81,14 @@ __global__ void __launch_bounds__(kThreads) k_wt_scan(int32_t* __restrict__ wt_c
     if (total && threadIdx.x == 0) total[t] = carry;
 }
 
-// ---- worklist of non-empty warp tiles ------------------------------------------------------------
-// Masks cover a compact fraction of the frame, so every streaming kernel iterates over the list of
-// non-empty warp tiles of its track instead of the whole plane: no time is spent on empty tiles and
-// the work is evenly spread over the blocks of a track regardless of where the object is.
-// k_tile_count packs, per warp tile, (#bytes > 0) | (#bytes > thr) << 16.
+// ---- worklist of non-empty units ------------------------------------------------------------------
+// Masks cover a compact fraction of the frame, so every streaming kernel iterates over the list of non-empty
+// UNITS of its track (a unit = 128 consecutive pixels = one quad per lane of a warp) instead of the whole plane:
+// no time is spent on empty pixels, lanes are (almost) all busy inside a unit, and the work is evenly spread over
+// the blocks of a track regardless of where the object is.
+// k_tile_count packs, per unit, (#bytes > 0) | (#bytes > thr) << 16.
 __global__ void __launch_bounds__(kThreads) k_tile_count(const uint8_t* __restrict__ plane, long long stride, int thr, int HW,
-                                                        int n_warp_tiles, int32_t* __restrict__ wt_count,
+                                                        int n_units, int32_t* __restrict__ wt_count,
                                                         const int32_t* __restrict__ active, int active_stride) {
     const int t = blockIdx.y;
     if (active && !active[(long long)t * active_stride]) return;
@@ -95,38 +96,39 @@ __global__ void __launch_bounds__(kThreads) k_tile_count(const uint8_t* __restri
     const uint32_t thr4 = (uint32_t)thr * 0x01010101u;
     const uint32_t* mq = reinterpret_cast<const uint32_t*>(plane + (long long)t * stride);
     const int nq = HW >> 2;
-    for (int wt = blockIdx.x * (kThreads / 32) + warp; wt < n_warp_tiles; wt += gridDim.x * (kThreads / 32)) {
-        int c0 = 0, c1 = 0;
+    const int n_super = (n_units + 3) >> 2;  // four units per warp iteration: four independent loads in flight
+    for (int wt = blockIdx.x * (kThreads / 32) + warp; wt < n_super; wt += gridDim.x * (kThreads / 32)) {
+        int c[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int q = wt * 128 + j * 32 + lane;
             const uint32_t m = q < nq ? ld_nc_u32(mq + q) : 0u;
-            c0 += __popc(__vcmpne4(m, 0u)) >> 3;
-            c1 += __popc(__vcmpgtu4(m, thr4)) >> 3;
+            c[j] = (__popc(__vcmpne4(m, 0u)) >> 3) | ((__popc(__vcmpgtu4(m, thr4)) >> 3) << 16);
         }
-        c0 = warp_sum(c0);
-        c1 = warp_sum(c1);
-        if (lane == 0) wt_count[(long long)t * n_warp_tiles + wt] = c0 | (c1 << 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[j] = warp_sum(c[j]);  // both 16-bit fields stay below 2^16 (<= 128)
+        if (lane < 4 && wt * 4 + lane < n_units)
+            wt_count[(long long)t * n_units + wt * 4 + lane] = lane == 0 ? c[0] : lane == 1 ? c[1] : lane == 2 ? c[2] : c[3];
     }
 }
 
 // one block per track: wt_count <- exclusive prefix of the (> thr) counts (row-major rank base), wt_list <- ids of
-// the warp tiles holding any non-zero byte (ascending), wt_n <- their number
+// the units holding any non-zero byte (ascending), wt_n <- their number
 __global__ void __launch_bounds__(kThreads) k_tile_compact(int32_t* __restrict__ wt_count, int32_t* __restrict__ wt_list,
-                                                          int32_t* __restrict__ wt_n, int n_warp_tiles,
+                                                          int32_t* __restrict__ wt_n, int n_units,
                                                           const int32_t* __restrict__ active, int active_stride) {
     const int t = blockIdx.x;
     if (active && !active[(long long)t * active_stride]) return;
     __shared__ int sh_r[kThreads / 32], sh_l[kThreads / 32];
     __shared__ int carry_r, carry_l;
-    int32_t* cnt = wt_count + (long long)t * n_warp_tiles;
-    int32_t* list = wt_list + (long long)t * n_warp_tiles;
+    int32_t* cnt = wt_count + (long long)t * n_units;
+    int32_t* list = wt_list + (long long)t * n_units;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { carry_r = 0; carry_l = 0; }
     __syncthreads();
-    for (int base = 0; base < n_warp_tiles; base += kThreads) {
+    for (int base = 0; base < n_units; base += kThreads) {
         const int i = base + threadIdx.x;
-        const int packed = i < n_warp_tiles ? cnt[i] : 0;
+        const int packed = i < n_units ? cnt[i] : 0;
         const int vr = packed >> 16;
         const int vl = (packed & 0xffff) ? 1 : 0;
         const int ir = warp_scan_incl(vr, lane), il = warp_scan_incl(vl, lane);
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kThreads) k_tile_compact(int32_t* __restrict__
         int wr = 0, wl = 0;
         for (int w = 0; w < warp; ++w) { wr += sh_r[w]; wl += sh_l[w]; }
         const int cr = carry_r, cl = carry_l;
-        if (i < n_warp_tiles) {
+        if (i < n_units) {
             cnt[i] = cr + wr + ir - vr;
             if (vl) list[cl + wl + il - 1] = i;
         }
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(kThreads) k_tile_compact(int32_t* __restrict__
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        wt_n[t] = carry_l;              // number of non-empty warp tiles
+        wt_n[t] = carry_l;              // number of non-empty units
         wt_n[gridDim.x + t] = carry_r;  // number of candidates (bytes > thr) of the whole plane
     }
 }
@@ -157,10 +159,11 @@ struct PassArgs {
     FrameTable ft;
     const uint8_t* seg; long long seg_stride; int thr;
     const VelCtl* ctl;
-    int n_warp_tiles;
-    const int32_t* wt_prefix;   // [T][n_warp_tiles] row-major rank base of each warp tile
-    const int32_t* wt_list;     // [T][n_warp_tiles] non-empty warp tiles
+    int n_units;
+    const int32_t* wt_prefix;   // [T][n_units] row-major rank base of each unit
+    const int32_t* wt_list;     // [T][n_units] non-empty units
     const int32_t* wt_n;        // [T]
+    long long norm_stride;      // norm slots per track
     float* norms; uint32_t* norm_count;
     const WeightParams* wp; int weight_flow;
     const double* x_pred; int x_stride;
@@ -215,8 +218,9 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
     const int nq = g.HW >> 2;
     const int W = g.W;
     const unsigned uW = (unsigned)g.W, uH = (unsigned)g.H;
+    const unsigned ustride = (unsigned)g.stride;
     uint8_t* dst_t = SCATTER ? a.state_dst + (long long)t * g.HW : nullptr;
-    float* norms_t = a.norms + (long long)t * g.HW;
+    float* norms_t = a.norms + (long long)t * a.norm_stride;
     const float inv_fx = g.inv_fx, max_d = g.max_depth_f;
 
     // predicted velocity (F = I: the predicted mean is the previous corrected mean) and FP32 row scales
@@ -235,80 +239,50 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
     }
 
     const int n_list = a.wt_n[t];
-    const int32_t* list = a.wt_list + (long long)t * a.n_warp_tiles;
-    const int32_t* prefix = a.wt_prefix + (long long)t * a.n_warp_tiles;
+    const int32_t* list = a.wt_list + (long long)t * a.n_units;
+    const int32_t* prefix = a.wt_prefix + (long long)t * a.n_units;
+    // each warp iteration takes four consecutive list entries (units of 128 px, one quad per lane each)
 #pragma unroll 1
-    for (int li = blockIdx.x * (kThreads / 32) + warp; li < n_list; li += gridDim.x * (kThreads / 32)) {
-        const int wt = list[li];  // warp-uniform
-        const int q0 = wt * 128 + lane;
-        // candidate bits of this lane's four quads: bit (4j + i); scs: non-zero pixels to propagate (origin excluded)
+    for (int g0 = (blockIdx.x * (kThreads / 32) + warp) * 4; g0 < n_list; g0 += gridDim.x * (kThreads / 32) * 4) {
+        // lanes 0..3 fetch the unit ids and their rank bases; broadcast by shuffle inside the rolled loop
+        int my_unit = -1, my_rank = 0;
+        if (lane < 4 && g0 + lane < n_list) {
+            my_unit = list[g0 + lane];
+            my_rank = prefix[my_unit];
+        }
+        // candidate bits of this lane's quad in each unit: bit (4j + i); scs: non-zero pixels to propagate
         uint32_t sel = 0, scs = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int q = q0 + j * 32;
-            const uint32_t m = q < nq ? ld_nc_u32(mq + q) : 0u;
+            const int unit = __shfl_sync(0xffffffffu, my_unit, j);
+            const int q = unit * 32 + lane;
+            const uint32_t m = (unit >= 0 && q < nq) ? ld_nc_u32(mq + q) : 0u;
             sel |= nibble_of(__vcmpgtu4(m, thr4)) << (4 * j);
-            if (SCATTER) scs |= nibble_of(__vcmpne4(m, 0u)) << (4 * j);
+            if (SCATTER) {
+                uint32_t z = nibble_of(__vcmpne4(m, 0u));
+                if (q == 0) z &= ~1u;  // mask_(0,0) = 0 (hpp:224)
+                scs |= z << (4 * j);
+            }
         }
-        if (SCATTER && q0 == 0) scs &= ~1u;  // mask_(0,0) = 0 (hpp:224)
         if (!c.enable) sel = 0;
         if (!do_sc) scs = 0;
-        const int rank0 = prefix[wt];  // candidates (row-major) before this tile
-        int nbase;                     // norm slot of the tile's first selected candidate
-        if (g.stride > 1) {
-            // keep rank % stride == 0 (hpp:237), BEFORE the gates
-            int r = rank0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t nib = (sel >> (4 * j)) & 0xfu;
-                const int cnt = __popc(nib);
-                const int incl = warp_scan_incl(cnt, lane);
-                const int tot = __shfl_sync(0xffffffffu, incl, 31);
-                unsigned rank = (unsigned)(r + incl - cnt);
-                uint32_t ns = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if ((nib >> i) & 1u) {
-                        if (rank % (unsigned)g.stride == 0u) ns |= 1u << i;
-                        ++rank;
-                    }
-                }
-                sel = (sel & ~(0xfu << (4 * j))) | (ns << (4 * j));
-                r += tot;
-            }
-            nbase = (rank0 + g.stride - 1) / g.stride;
-        } else {
-            nbase = rank0;
-        }
         const uint32_t need = sel | scs;
-        if (!__any_sync(0xffffffffu, need != 0u)) continue;
 
-        // lane-private norm slots: [nbase + (candidates of the lower lanes), + own candidates)
-        float* np = norms_t;
-        if (PASS == 0) {
-            const int mine = __popc(sel);
-            np += nbase + warp_scan_incl(mine, lane) - mine;
-        }
-
-        // row / first column of this lane's first quad; the next quads are 128 px further along the row-major order
-        int px = q0 << 2;
-        int v = px / W;
-        int u0 = px - v * W;
-
-        // software pipeline over the four quads: loads of quad j+1 are issued before quad j is processed
+        // software pipeline over the four units: loads of unit j+1 are issued before unit j is processed
         float4 Dc, F0c, F1c, Dn, F0n, F1n;
         {
-            Dc = get4(dq + q0, (sel & 0xfu) != 0u);
+            const int q = __shfl_sync(0xffffffffu, my_unit, 0) * 32 + lane;
+            Dc = get4(dq + q, (sel & 0xfu) != 0u);
             if (FAST) {
                 const bool on = (need & 0xfu) != 0u;
-                F0c = get4(fq + 2 * q0, on);
-                F1c = get4(fq + 2 * q0 + 1, on);
+                F0c = get4(fq + 2 * q, on);
+                F1c = get4(fq + 2 * q + 1, on);
             }
         }
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             if (j < 3) {
-                const int qn = q0 + (j + 1) * 32;
+                const int qn = __shfl_sync(0xffffffffu, my_unit, j + 1) * 32 + lane;
                 Dn = get4(dq + qn, ((sel >> (4 * (j + 1))) & 0xfu) != 0u);
                 if (FAST) {
                     const bool on = ((need >> (4 * (j + 1))) & 0xfu) != 0u;
@@ -316,9 +290,32 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
                     F1n = get4(fq + 2 * qn + 1, on);
                 }
             }
-            const uint32_t nib = (sel >> (4 * j)) & 0xfu;
+            const int unit = __shfl_sync(0xffffffffu, my_unit, j);
+            if (unit < 0) break;  // warp-uniform: past the end of the list
+            uint32_t nib = (sel >> (4 * j)) & 0xfu;
             const uint32_t snib = (scs >> (4 * j)) & 0xfu;
+            int nslot = 0;  // stride > 1: compact norm slot of this lane's first selected candidate
+            if (g.stride > 1) {
+                // keep rank % stride == 0 over the row-major rank of the candidates (hpp:237), BEFORE the gates
+                const int cnt = __popc(nib);
+                const int incl = warp_scan_incl(cnt, lane);
+                unsigned rank = (unsigned)(__shfl_sync(0xffffffffu, my_rank, j) + incl - cnt);
+                nslot = (int)((rank + ustride - 1u) / ustride);
+                uint32_t ns = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if ((nib >> i) & 1u) {
+                        if (rank % ustride == 0u) ns |= 1u << i;
+                        ++rank;
+                    }
+                }
+                nib = ns;
+            }
+            float4 nv = make_float4(-1.f, -1.f, -1.f, -1.f);  // pass A: norms of this quad (-1: not a valid measurement)
             if ((nib | snib) != 0u) {
+                const int px = (unit * 32 + lane) << 2;
+                const int v = px / W;
+                const int u0 = px - v * W;
                 const float vf = (float)v;
                 float yh, xh0;
                 double yhd = 0.0, xh0d = 0.0;
@@ -372,7 +369,11 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
                     const float n1 = dx - c1 * p1, n2 = dy - c2 * p2;
                     const float nr = sqrt_approx(n1 * n1 + n2 * n2);
                     if (PASS == 0) {
-                        if (cand) *np++ = valid ? nr : -1.0f;  // gated-out candidates are marked
+                        if (g.stride > 1) {
+                            if (cand) norms_t[nslot++] = valid ? nr : -1.0f;  // compact: slot = rank / stride
+                        } else if (valid) {
+                            if (i == 0) nv.x = nr; else if (i == 1) nv.y = nr; else if (i == 2) nv.z = nr; else nv.w = nr;
+                        }
                     } else if (valid) {
                         float l = 1.0f;
                         if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
@@ -418,15 +419,11 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
                     }
                 }
             }
+            // pass A, stride 1: position-addressed norm slots, one coalesced 128-bit store per lane
+            if (PASS == 0 && g.stride == 1) reinterpret_cast<float4*>(norms_t)[(g0 + j) * 32 + lane] = nv;
             Dc = Dn;
             F0c = F0n;
             F1c = F1n;
-            // next quad: 128 px ahead
-            u0 += 128;
-            while (u0 >= W) {
-                u0 -= W;
-                ++v;
-            }
         }
     }
 
@@ -449,7 +446,8 @@ __global__ void k_sel_init(int n_tracks, const int32_t* __restrict__ wt_n, int s
     SelState s;
     s.prefix = 0;
     // norm slots written by pass A: one per selected candidate (gated-out ones hold -1)
-    s.n_entries = ctl[t].enable ? (uint32_t)((wt_n[n_tracks + t] + stride - 1) / stride) : 0u;
+    s.n_entries = !ctl[t].enable ? 0u : stride > 1 ? (uint32_t)((wt_n[n_tracks + t] + stride - 1) / stride)
+                                                   : (uint32_t)wt_n[t] * 128u;  // stride 1: 128 slots per listed unit
     s.n = s.n_entries;  // valid count, fixed by the level-0 scan
     s.k = 0;
     s.less_cnt = 0;
@@ -772,12 +770,12 @@ int launch_wt_scan(int32_t* wt_count, int n_warp_tiles, int n_items, int32_t* to
 
 int launch_tile_list(const uint8_t* plane, long long stride, int thr, int HW, int n_items, int32_t* wt_count, int32_t* wt_list,
                      int32_t* wt_n, const int32_t* active, int active_stride, cudaStream_t s) {
-    const int n_warp_tiles = (HW + kWarpTilePx - 1) / kWarpTilePx;
+    const int n_units = (HW + kUnitPx - 1) / kUnitPx;
     const int n_block_tiles = (HW + kBlockTilePx - 1) / kBlockTilePx;
     const int bx = max(1, min(n_block_tiles, (148 * 8 + n_items - 1) / n_items));
-    ROFTB_LAUNCH(k_tile_count, dim3(bx, n_items), kThreads, 0, s, plane, stride, thr, HW, n_warp_tiles, wt_count, active,
+    ROFTB_LAUNCH(k_tile_count, dim3(bx, n_items), kThreads, 0, s, plane, stride, thr, HW, n_units, wt_count, active,
                  active_stride);
-    ROFTB_LAUNCH(k_tile_compact, n_items, kThreads, 0, s, wt_count, wt_list, wt_n, n_warp_tiles, active, active_stride);
+    ROFTB_LAUNCH(k_tile_compact, n_items, kThreads, 0, s, wt_count, wt_list, wt_n, n_units, active, active_stride);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -800,7 +798,8 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     pa.seg_stride = a.seg_stride;
     pa.thr = a.thr;
     pa.ctl = a.ctl;
-    pa.n_warp_tiles = n_warp_tiles;
+    pa.n_units = (g.HW + kUnitPx - 1) / kUnitPx;
+    pa.norm_stride = (long long)pa.n_units * kUnitPx;
     pa.wt_prefix = a.wt_count;
     pa.wt_list = a.wt_list;
     pa.wt_n = a.wt_n;
@@ -839,13 +838,13 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
         ROFTB_LAUNCH(k_sel_init, (T + 127) / 128, 128, 0, s, T, a.wt_n, g.stride, a.sel, a.ctl);
         // enough blocks per track to spread the list, few enough that the per-block histogram flush stays cheap
         int sb = max(1, min(32, (148 * 4 + T - 1) / T));
-        ROFTB_LAUNCH(k_sel_hist<0>, dim3(sb, T), kThreads, 0, s, a.norms, g.HW, a.sel, a.hist);
+        ROFTB_LAUNCH(k_sel_hist<0>, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel, a.hist);
         ROFTB_LAUNCH(k_sel_scan<0>, T, kThreads, 0, s, a.sel, a.hist);
-        ROFTB_LAUNCH(k_sel_hist<1>, dim3(sb, T), kThreads, 0, s, a.norms, g.HW, a.sel, a.hist);
+        ROFTB_LAUNCH(k_sel_hist<1>, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel, a.hist);
         ROFTB_LAUNCH(k_sel_scan<1>, T, kThreads, 0, s, a.sel, a.hist);
-        ROFTB_LAUNCH(k_sel_hist<2>, dim3(sb, T), kThreads, 0, s, a.norms, g.HW, a.sel, a.hist);
+        ROFTB_LAUNCH(k_sel_hist<2>, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel, a.hist);
         ROFTB_LAUNCH(k_sel_scan<2>, T, kThreads, 0, s, a.sel, a.hist);
-        ROFTB_LAUNCH(k_sel_stats, dim3(sb, T), kThreads, 0, s, a.norms, g.HW, a.sel);
+        ROFTB_LAUNCH(k_sel_stats, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel);
         ROFTB_LAUNCH(k_sel_final, (T + 127) / 128, 128, 0, s, T, a.sel, a.wp);
     } else if (a.prof) {
         cudaEventRecord(a.prof[2], s);

@@ -213,23 +213,16 @@ __global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft
     const uint8_t uval = (uint8_t)sp.uniform_val;
     const bool general = (sp.uniform_val == 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // walk the worklist of non-empty warp tiles of the source plane; one quad (4 px) per lane per sub-tile
+    // walk the worklist of non-empty units (128 px) of the source plane; one quad (4 px) per lane
     const int32_t* list = (sp.src_new ? n_list : s_list) + (long long)t * n_warp_tiles;
     const int n_list_items = (sp.src_new ? n_n : s_n)[t];
     for (int li = blockIdx.x * (kThreads / 32) + warp; li < n_list_items; li += gridDim.x * (kThreads / 32)) {
-        const int wt = list[li];
-        uint32_t m[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int q = wt * 128 + j * 32 + lane;
-            m[j] = q < nq ? ld_nc_u32(reinterpret_cast<const uint32_t*>(src) + q) : 0u;
-            if (sp.zero_origin && q == 0) m[j] &= 0xffffff00u;
-        }
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t mj = m[j];
+        const int q = list[li] * 32 + lane;
+        uint32_t mj = q < nq ? ld_nc_u32(reinterpret_cast<const uint32_t*>(src) + q) : 0u;
+        if (sp.zero_origin && q == 0) mj &= 0xffffff00u;
+        {
             if (mj == 0u) continue;
-            const int px = (wt * 128 + j * 32 + lane) << 2;
+            const int px = q << 2;
             const int v = px / g.W;
             const int u0 = px - v * g.W;
             // the four pixels of the quad are chased together: four independent flow gathers in flight per hop

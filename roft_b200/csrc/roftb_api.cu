@@ -76,7 +76,8 @@ struct roftb_ctx {
     int32_t* nl_list = nullptr;
     int32_t* nl_n = nullptr;
     int32_t* wt_count2 = nullptr;
-    int n_warp_tiles = 0;
+    int n_warp_tiles = 0;   // 512-px tiles (extract kernels)
+    int n_units = 0;        // 128-px worklist units
     MaskStat* stat = nullptr;
     WarpPlan* plan = nullptr;
     FlowBuf* fbuf = nullptr;
@@ -247,6 +248,7 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     const int T = ctx->T;
     const size_t HW = ctx->HW;
     ctx->n_warp_tiles = (int)((HW + kWarpTilePx - 1) / kWarpTilePx);
+    ctx->n_units = (int)((HW + kUnitPx - 1) / kUnitPx);
     const int n_block_tiles = (int)((HW + kBlockTilePx - 1) / kBlockTilePx);
     ctx->max_blocks = 256;  // warp partials per track (32 blocks x 8 warps)
     (void)n_block_tiles;
@@ -278,18 +280,18 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(dalloc(&ctx->mask_state[0], T * HW));
     CKC(dalloc(&ctx->mask_state[1], T * HW));
     CKC(dalloc(&ctx->winner, T * HW));
-    CKC(dalloc(&ctx->norms, T * HW));
+    CKC(dalloc(&ctx->norms, (size_t)T * ctx->n_units * kUnitPx));
     CKC(dalloc(&ctx->norm_count, (size_t)T));
     CKC(dalloc(&ctx->hist, (size_t)T * kSelBins));
     CKC(dalloc(&ctx->sel, (size_t)T));
     CKC(dalloc(&ctx->wp, (size_t)T));
     CKC(dalloc(&ctx->partials, (size_t)T * ctx->max_blocks * kNAcc));
-    CKC(dalloc(&ctx->wt_count, (size_t)T * ctx->n_warp_tiles));
+    CKC(dalloc(&ctx->wt_count, (size_t)T * ctx->n_units));
     CKC(dalloc(&ctx->wt_count2, (size_t)T * ctx->n_warp_tiles));
-    CKC(dalloc(&ctx->wt_list, (size_t)T * ctx->n_warp_tiles));
+    CKC(dalloc(&ctx->wt_list, (size_t)T * ctx->n_units));
     CKC(dalloc(&ctx->wt_n, (size_t)2 * T));
-    CKC(dalloc(&ctx->nl_count, (size_t)T * ctx->n_warp_tiles));
-    CKC(dalloc(&ctx->nl_list, (size_t)T * ctx->n_warp_tiles));
+    CKC(dalloc(&ctx->nl_count, (size_t)T * ctx->n_units));
+    CKC(dalloc(&ctx->nl_list, (size_t)T * ctx->n_units));
     CKC(dalloc(&ctx->nl_n, (size_t)2 * T));
     CKC(dalloc(&ctx->stat, (size_t)T));
     CKC(dalloc(&ctx->plan, (size_t)T));
@@ -695,7 +697,7 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
     ma.state_src = seg_prev; ma.state_dst = seg_next; ma.winner = ctx->winner;
     ma.ctl = ctx->d_wctl; ma.stat = ctx->stat; ma.plan = ctx->plan; ma.fbuf = ctx->fbuf;
     ma.segm_delay = cfg.segm_delay;
-    ma.s_list = ctx->wt_list; ma.s_n = ctx->wt_n; ma.n_list = ctx->nl_list; ma.n_n = ctx->nl_n; ma.n_warp_tiles = ctx->n_warp_tiles;
+    ma.s_list = ctx->wt_list; ma.s_n = ctx->wt_n; ma.n_list = ctx->nl_list; ma.n_n = ctx->nl_n; ma.n_warp_tiles = ctx->n_units;
     ma.fuse = 1;
     if (launch_mask_plan_init(ma, s)) return fail(ctx, "launch_mask_plan_init failed");
     if (any_new_mask &&
@@ -880,7 +882,7 @@ int roftb_mask_sync(roftb_ctx* ctx, int32_t n_masks, const uint8_t* mask, const 
     a.new_mask = d_mask; a.new_stride = (long long)HW;
     a.state_src = d_mask; a.state_dst = d_out; a.winner = d_win; a.plan = d_plan;
     {
-        const int nwt = ctx->n_warp_tiles;
+        const int nwt = ctx->n_units;
         int32_t* cnt = tb.alloc<int32_t>(N * nwt);
         int32_t* lst = tb.alloc<int32_t>(N * nwt);
         int32_t* ln = tb.alloc<int32_t>(2 * N);
@@ -920,7 +922,7 @@ static int velocity_operator(roftb_ctx* ctx, int32_t n, const uint8_t* mask, con
     double* d_x = tb.upload(x ? x : zeros.data(), N * 6, s);
     double* d_P = tb.upload(P ? P : zeros.data(), N * 36, s);
     double* d_xp = x_pred ? tb.upload(x_pred, N * 6, s) : nullptr;
-    const int nwt = ctx->n_warp_tiles;
+    const int nwt = ctx->n_units;
     VelocityArgs a;
     memset(&a, 0, sizeof(a));
     a.g = ctx->g; a.n_tracks = (int)N;
@@ -931,7 +933,7 @@ static int velocity_operator(roftb_ctx* ctx, int32_t n, const uint8_t* mask, con
     a.wt_count = tb.alloc<int32_t>(N * nwt);
     a.wt_list = tb.alloc<int32_t>(N * nwt);
     a.wt_n = tb.alloc<int32_t>(2 * N);
-    a.norms = tb.alloc<float>(N * HW);
+    a.norms = tb.alloc<float>(N * (size_t)nwt * kUnitPx);
     a.norm_count = tb.alloc<uint32_t>(N, true);
     a.hist = tb.alloc<uint32_t>(N * kSelBins, true);
     a.sel = tb.alloc<SelState>(N, true);

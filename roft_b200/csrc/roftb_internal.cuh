@@ -12,7 +12,8 @@ namespace roftb {
 constexpr int kMaxFlows = ROFTB_MAX_DELAY;   // longest flow chain a mask is warped through
 constexpr int kFrameRing = 16;               // device-side table of recent frames (> kMaxFlows)
 constexpr int kThreads = 256;                // streaming kernels: 8 warps
-constexpr int kWarpTilePx = 512;             // one warp covers 4 sub-tiles of 128 px (one quad per lane each)
+constexpr int kWarpTilePx = 512;             // extract kernels: one warp covers 4 sub-tiles of 128 px
+constexpr int kUnitPx = 128;                 // worklist granularity: 128 consecutive px = one quad per lane of a warp
 constexpr int kBlockTilePx = kThreads / 32 * kWarpTilePx;  // 4096 px
 // accumulators of the flow->velocity normal equations:
 //   S1 = sum l L1^T L1 over index set {0,2,3,4,5} (15 upper-triangular entries)
