@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--fp32-accum", action="store_true", help="FP32 per-pixel terms in pass B")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--single-mask", action="store_true", help="diagnostic: deliver the mask / pose only at step 0")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     return ap.parse_args()
@@ -170,7 +171,7 @@ def run_own(args):
 
     def stale(step):  # DatasetImageSegmentationDelayed.cpp:42-63: frame delivered (late) at this step, or None
         idx = step - D
-        if idx % D != 0:
+        if idx % D != 0 or (args.single_mask and step > 0):
             return None
         return frame_of(max(idx, 0))
 

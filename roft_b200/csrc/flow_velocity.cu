@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kThreads) k_tile_count(const uint8_t* __restri
             c[j] = (__popc(__vcmpne4(m, 0u)) >> 3) | ((__popc(__vcmpgtu4(m, thr4)) >> 3) << 16);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) c[j] = warp_sum(c[j]);  // both 16-bit fields stay below 2^16 (<= 128)
+        for (int j = 0; j < 4; ++j) c[j] = (int)__reduce_add_sync(0xffffffffu, (unsigned)c[j]);  // fields stay <= 128
         if (lane < 4 && wt * 4 + lane < n_units)
             wt_count[(long long)t * n_units + wt * 4 + lane] = lane == 0 ? c[0] : lane == 1 ? c[1] : lane == 2 ? c[2] : c[3];
     }
@@ -114,19 +114,20 @@ __global__ void __launch_bounds__(kThreads) k_tile_count(const uint8_t* __restri
 
 // one block per track: wt_count <- exclusive prefix of the (> thr) counts (row-major rank base), wt_list <- ids of
 // the units holding any non-zero byte (ascending), wt_n <- their number
-__global__ void __launch_bounds__(kThreads) k_tile_compact(int32_t* __restrict__ wt_count, int32_t* __restrict__ wt_list,
+constexpr int kCompactThreads = 1024;
+__global__ void __launch_bounds__(kCompactThreads) k_tile_compact(int32_t* __restrict__ wt_count, int32_t* __restrict__ wt_list,
                                                           int32_t* __restrict__ wt_n, int n_units,
                                                           const int32_t* __restrict__ active, int active_stride) {
     const int t = blockIdx.x;
     if (active && !active[(long long)t * active_stride]) return;
-    __shared__ int sh_r[kThreads / 32], sh_l[kThreads / 32];
+    __shared__ int sh_r[kCompactThreads / 32], sh_l[kCompactThreads / 32];
     __shared__ int carry_r, carry_l;
     int32_t* cnt = wt_count + (long long)t * n_units;
     int32_t* list = wt_list + (long long)t * n_units;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) { carry_r = 0; carry_l = 0; }
     __syncthreads();
-    for (int base = 0; base < n_units; base += kThreads) {
+    for (int base = 0; base < n_units; base += kCompactThreads) {
         const int i = base + threadIdx.x;
         const int packed = i < n_units ? cnt[i] : 0;
         const int vr = packed >> 16;
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) k_tile_compact(int32_t* __restrict__
             if (vl) list[cl + wl + il - 1] = i;
         }
         __syncthreads();
-        if (threadIdx.x == kThreads - 1) { carry_r = cr + wr + ir; carry_l = cl + wl + il; }
+        if (threadIdx.x == kCompactThreads - 1) { carry_r = cr + wr + ir; carry_l = cl + wl + il; }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -474,9 +475,10 @@ __global__ void __launch_bounds__(kThreads) k_sel_hist(const float* __restrict__
     for (int i = threadIdx.x; i < NB; i += kThreads) h[i] = 0;
     __syncthreads();
     const uint32_t* keys = reinterpret_cast<const uint32_t*>(norms + (long long)t * HW);
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += kThreads) {
-        const uint32_t key = keys[i];
-        if (key >> 31) continue;  // gated-out candidate
+    // 128-bit loads, two in flight per thread: a scalar loop keeps one 4-byte load in flight per thread, which is
+    // ~10 % of the bytes in flight HBM3e needs (measured: 0.3 ms per pass instead of 0.06)
+    auto count = [&](uint32_t key) {
+        if (key >> 31) return;  // gated-out candidate
         if (LEVEL == 0) {
             atomicAdd(&h[key >> 20], 1u);
         } else if (LEVEL == 1) {
@@ -484,7 +486,22 @@ __global__ void __launch_bounds__(kThreads) k_sel_hist(const float* __restrict__
         } else {
             if ((key >> 8) == (prefix >> 8)) atomicAdd(&h[key & 0xffu], 1u);
         }
+    };
+    const uint4* keys4 = reinterpret_cast<const uint4*>(keys);
+    const uint32_t lo4 = (lo + 3) >> 2, hi4 = hi >> 2;  // whole uint4s inside [lo, hi)
+    for (uint32_t i = lo + threadIdx.x; i < min(hi, lo4 << 2); i += kThreads) count(keys[i]);  // head
+    uint32_t i4 = lo4 + threadIdx.x;
+    for (; i4 + kThreads < hi4; i4 += 2 * kThreads) {
+        const uint4 k0 = keys4[i4], k1 = keys4[i4 + kThreads];
+        count(k0.x); count(k0.y); count(k0.z); count(k0.w);
+        count(k1.x); count(k1.y); count(k1.z); count(k1.w);
     }
+    if (i4 < hi4) {
+        const uint4 k0 = keys4[i4];
+        count(k0.x); count(k0.y); count(k0.z); count(k0.w);
+    }
+    if (hi4 >= lo4)
+        for (uint32_t i = (hi4 << 2) + threadIdx.x; i < hi; i += kThreads) count(keys[i]);  // tail
     __syncthreads();
     uint32_t* gh = hist + (long long)t * kSelBins;
     for (int i = threadIdx.x; i < NB; i += kThreads)
@@ -539,7 +556,11 @@ __global__ void __launch_bounds__(kThreads) k_sel_scan(SelState* __restrict__ se
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_sel_stats(const float* __restrict__ norms, int HW, SelState* __restrict__ sel) {
+// Last pass over the norms, after two radix levels fixed the top 24 key bits of the upper median s[n/2]: histogram of
+// the low 8 bits of the keys inside that 24-bit bin (all keys with the same low bits are the SAME float, so counts are
+// enough to reconstruct sums there), and count / sum / max of everything below the bin, plus the grand total.
+__global__ void __launch_bounds__(kThreads) k_sel_l2stats(const float* __restrict__ norms, int HW, SelState* __restrict__ sel,
+                                                         uint32_t* __restrict__ hist) {
     const int t = blockIdx.y;
     if (sel[t].n == 0) return;
     const uint32_t n = sel[t].n_entries;
@@ -547,23 +568,42 @@ __global__ void __launch_bounds__(kThreads) k_sel_stats(const float* __restrict_
     const uint32_t lo = blockIdx.x * per;
     if (lo >= n) return;
     const uint32_t hi = min(n, lo + per);
-    const float v1 = __uint_as_float(sel[t].prefix);
-    const float* p = norms + (long long)t * HW;
-    double tot = 0.0, ls = 0.0;
+    const uint32_t pbin = sel[t].prefix >> 8;
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t* keys = reinterpret_cast<const uint32_t*>(norms + (long long)t * (long long)HW);
+    float tot = 0.f, ls = 0.f, lm = 0.f;  // per-thread FP32 partials (<= a few hundred terms), FP64 across threads
     unsigned lc = 0;
-    float lm = 0.f;
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += kThreads) {
-        const float v = p[i];
-        if (v < 0.f) continue;  // gated-out candidate
-        tot += (double)v;
-        if (v < v1) {
-            ls += (double)v;
+    auto visit = [&](uint32_t key) {
+        if (key >> 31) return;  // gated-out candidate
+        const float v = __uint_as_float(key);
+        tot += v;
+        const uint32_t kb = key >> 8;
+        if (kb < pbin) {
+            ls += v;
             ++lc;
             lm = fmaxf(lm, v);
+        } else if (kb == pbin) {
+            atomicAdd(&h[key & 0xffu], 1u);
         }
+    };
+    const uint4* keys4 = reinterpret_cast<const uint4*>(keys);
+    const uint32_t lo4 = (lo + 3) >> 2, hi4 = hi >> 2;
+    for (uint32_t i = lo + threadIdx.x; i < min(hi, lo4 << 2); i += kThreads) visit(keys[i]);
+    uint32_t i4 = lo4 + threadIdx.x;
+    for (; i4 + kThreads < hi4; i4 += 2 * kThreads) {
+        const uint4 k0 = keys4[i4], k1 = keys4[i4 + kThreads];
+        visit(k0.x); visit(k0.y); visit(k0.z); visit(k0.w);
+        visit(k1.x); visit(k1.y); visit(k1.z); visit(k1.w);
     }
-    tot = warp_sum(tot);
-    ls = warp_sum(ls);
+    if (i4 < hi4) {
+        const uint4 k0 = keys4[i4];
+        visit(k0.x); visit(k0.y); visit(k0.z); visit(k0.w);
+    }
+    if (hi4 >= lo4)
+        for (uint32_t i = (hi4 << 2) + threadIdx.x; i < hi; i += kThreads) visit(keys[i]);
+    double dtot = warp_sum((double)tot), dls = warp_sum((double)ls);
     lc = (unsigned)warp_sum((int)lc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lm = fmaxf(lm, __shfl_xor_sync(0xffffffffu, lm, o));
@@ -572,26 +612,114 @@ __global__ void __launch_bounds__(kThreads) k_sel_stats(const float* __restrict_
     __shared__ float s_lm[kThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
-        s_tot[warp] = tot;
-        s_ls[warp] = ls;
+        s_tot[warp] = dtot;
+        s_ls[warp] = dls;
         s_lc[warp] = lc;
         s_lm[warp] = lm;
     }
     __syncthreads();
+    uint32_t* gh = hist + (long long)t * kSelBins;
+    if (h[threadIdx.x]) atomicAdd(gh + threadIdx.x, h[threadIdx.x]);
     if (threadIdx.x == 0) {
         for (int w = 1; w < kThreads / 32; ++w) {
-            tot += s_tot[w];
-            ls += s_ls[w];
+            dtot += s_tot[w];
+            dls += s_ls[w];
             lc += s_lc[w];
             lm = fmaxf(lm, s_lm[w]);
         }
-        atomicAdd(&sel[t].total_sum, tot);
-        atomicAdd(&sel[t].less_sum, ls);
+        atomicAdd(&sel[t].total_sum, dtot);
+        atomicAdd(&sel[t].less_sum, dls);
         atomicAdd(&sel[t].less_cnt, (unsigned long long)lc);
         atomicMax(&sel[t].less_max_bits, __float_as_uint(lm));
     }
 }
 
+// one warp per track: finish the select from the 256-bin histogram and emit the Laplacian parameters
+__global__ void __launch_bounds__(32) k_sel_final(int n_tracks, SelState* __restrict__ sel, uint32_t* __restrict__ hist,
+                                                  WeightParams* __restrict__ wp) {
+    const int t = blockIdx.x;
+    const int lane = threadIdx.x;
+    SelState s = sel[t];
+    WeightParams w;
+    w.m = 0.f;
+    w.inv_b = 0.f;
+    w.coef = 0.f;
+    w.inv_lmax = 1.f;
+    w.use = 0;
+    w.n = (int32_t)s.n;
+    w.pad[0] = w.pad[1] = 0;
+    if (s.n > 0) {
+        // bins of this lane: 8 consecutive low-byte values
+        uint32_t* gh = hist + (long long)t * kSelBins;
+        uint32_t loc[8];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            loc[i] = gh[lane * 8 + i];
+            gh[lane * 8 + i] = 0;
+            sum += loc[i];
+        }
+        const uint32_t incl = (uint32_t)warp_scan_incl((int)sum, lane);
+        uint32_t before = incl - sum;
+        // the lane whose bins contain rank s.k decides the low byte of the upper median
+        int bsel = -1;
+        if (s.k >= before && s.k < before + sum) {
+            uint32_t acc = before;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (bsel < 0 && s.k < acc + loc[i]) bsel = lane * 8 + i;
+                acc += loc[i];
+            }
+        }
+        const uint32_t vote = __ballot_sync(0xffffffffu, bsel >= 0);
+        const int src = __ffs(vote) - 1;
+        bsel = __shfl_sync(0xffffffffu, bsel, src < 0 ? 0 : src);
+        // statistics of the in-bin keys below the selected one
+        unsigned long long c_in = 0;
+        double s_in = 0.0;
+        float m_in = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int b = lane * 8 + i;
+            if (b < bsel && loc[i]) {
+                const float v = __uint_as_float((s.prefix & 0xffffff00u) | (uint32_t)b);
+                c_in += loc[i];
+                s_in += (double)loc[i] * (double)v;
+                m_in = fmaxf(m_in, v);
+            }
+        }
+        c_in = (unsigned long long)warp_sum((int)c_in);
+        s_in = warp_sum(s_in);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m_in = fmaxf(m_in, __shfl_xor_sync(0xffffffffu, m_in, o));
+        s.prefix = (s.prefix & 0xffffff00u) | (uint32_t)bsel;
+        s.less_cnt += c_in;
+        s.less_sum += s_in;
+        const float less_max = fmaxf(__uint_as_float(s.less_max_bits), m_in);
+        // SKFCorrection.cpp:95-102: median (even: mean of the two middle values), b = mean |n - m|
+        const double n = (double)s.n;
+        const double k1 = (double)(s.n >> 1);
+        const double v1 = (double)__uint_as_float(s.prefix);
+        const double lower = (s.less_cnt == (unsigned long long)(s.n >> 1)) ? (double)less_max : v1;
+        const bool even = (s.n & 1u) == 0u;
+        const double m = even ? 0.5 * (lower + v1) : v1;
+        const double s_below = s.less_sum + (k1 - (double)s.less_cnt) * v1;  // sum of the k1 smallest
+        const double s_above = s.total_sum - s_below;
+        const double b = ((s_above - (n - k1) * m) + (k1 * m - s_below)) / n;
+        if (b > 1e-4) {  // SKFCorrection.cpp:106
+            const double dmin = even ? 0.5 * (v1 - lower) : 0.0;
+            const double lmax = fmax(exp(-dmin / b) / (2.0 * b), 1e-6);
+            w.m = (float)m;
+            w.inv_b = (float)(1.0 / b);
+            w.coef = (float)(1.0 / (2.0 * b));
+            w.inv_lmax = (float)(1.0 / lmax);
+            w.use = 1;
+        }
+    }
+    if (lane == 0) wp[t] = w;
+}
+
+#if 0
 __global__ void k_sel_final(int n_tracks, const SelState* __restrict__ sel, WeightParams* __restrict__ wp) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tracks) return;
@@ -627,6 +755,8 @@ __global__ void k_sel_final(int n_tracks, const SelState* __restrict__ sel, Weig
     }
     wp[t] = w;
 }
+
+#endif
 
 // ---- per-track epilogue: FP64 reduction of the block partials, 6x6 solve, gate, publish ------------
 // In-place Gauss-Jordan inverse of a symmetric positive definite 6x6 matrix held in shared memory
@@ -775,7 +905,7 @@ int launch_tile_list(const uint8_t* plane, long long stride, int thr, int HW, in
     const int bx = max(1, min(n_block_tiles, (148 * 8 + n_items - 1) / n_items));
     ROFTB_LAUNCH(k_tile_count, dim3(bx, n_items), kThreads, 0, s, plane, stride, thr, HW, n_units, wt_count, active,
                  active_stride);
-    ROFTB_LAUNCH(k_tile_compact, n_items, kThreads, 0, s, wt_count, wt_list, wt_n, n_units, active, active_stride);
+    ROFTB_LAUNCH(k_tile_compact, n_items, kCompactThreads, 0, s, wt_count, wt_list, wt_n, n_units, active, active_stride);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -837,15 +967,13 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
         if (a.prof) cudaEventRecord(a.prof[2], s);
         ROFTB_LAUNCH(k_sel_init, (T + 127) / 128, 128, 0, s, T, a.wt_n, g.stride, a.sel, a.ctl);
         // enough blocks per track to spread the list, few enough that the per-block histogram flush stays cheap
-        int sb = max(1, min(32, (148 * 4 + T - 1) / T));
+        int sb = max(1, min(32, (148 * 8 + T - 1) / T));
         ROFTB_LAUNCH(k_sel_hist<0>, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel, a.hist);
         ROFTB_LAUNCH(k_sel_scan<0>, T, kThreads, 0, s, a.sel, a.hist);
         ROFTB_LAUNCH(k_sel_hist<1>, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel, a.hist);
         ROFTB_LAUNCH(k_sel_scan<1>, T, kThreads, 0, s, a.sel, a.hist);
-        ROFTB_LAUNCH(k_sel_hist<2>, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel, a.hist);
-        ROFTB_LAUNCH(k_sel_scan<2>, T, kThreads, 0, s, a.sel, a.hist);
-        ROFTB_LAUNCH(k_sel_stats, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel);
-        ROFTB_LAUNCH(k_sel_final, (T + 127) / 128, 128, 0, s, T, a.sel, a.wp);
+        ROFTB_LAUNCH(k_sel_l2stats, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel, a.hist);
+        ROFTB_LAUNCH(k_sel_final, T, 32, 0, s, T, a.sel, a.hist, a.wp);
     } else if (a.prof) {
         cudaEventRecord(a.prof[2], s);
     }
