@@ -45,7 +45,8 @@ def parse_args():
     ap.add_argument("--stride", type=int, default=1, help="subsampling radius (reference default 35; 1 = every masked pixel)")
     ap.add_argument("--coverage", type=float, default=0.25, help="target mask coverage of the frame")
     ap.add_argument("--delay", type=int, default=6, help="mask / pose delay in frames")
-    ap.add_argument("--fp32-accum", action="store_true", help="FP32 per-pixel terms in pass B")
+    ap.add_argument("--accum", default="auto", choices=["auto", "fp64", "fp32"],
+                    help="precision of the per-pixel terms of the normal equations (roftb_config.accum_fp64)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--single-mask", action="store_true", help="diagnostic: deliver the mask / pose only at step 0")
@@ -159,7 +160,7 @@ def run_own(args):
     T, F, D = args.tracks, args.frames, args.delay
 
     cfg = api.default_config(n_tracks=T, subsampling_radius=args.stride, segm_delay=D, pose_delay=D, device=local,
-                             accum_fp64=0 if args.fp32_accum else 1)
+                             accum_fp64={"fp32": 0, "fp64": 1, "auto": 2}[args.accum])
     trk = api.Tracker(cfg)
     seq = build_frames(args, dev, rank * T)
     x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
@@ -277,12 +278,13 @@ def run_own(args):
         "metric": "tracked frames/sec at 1280x720 (batched tracks)", "value": value, "unit": "tracked frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64" if not args.fp32_accum else "f32", "data": "synthetic",
+        "dtype": {"auto": "f32 per-pixel terms + f64 reduction/solve (f64 terms for tracks < 32768 px)", "fp64": "f64", "fp32": "f32"}[args.accum],
+        "data": "synthetic",
         "config": {"workload": workload_name(args), "tracks_per_gpu": T, "resident_frames": F,
                    "l2_policy": f"inputs larger than L2: {T * BYTES_PER_TRACK_FRAME / 1e9:.2f} GB touched per step, no flush needed",
-                   "accumulation": "fp32" if args.fp32_accum else "fp64", "parallelism": f"tracks partitioned over {world} GPU(s), no collective"},
+                   "accumulation": args.accum, "parallelism": f"tracks partitioned over {world} GPU(s), no collective"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(dom, T, args.fp32_accum),
+                     "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(dom, T, args.accum != "fp64"),
                      "peak_kind": peak_kind, "kernel_ms": dom_ms,
                      "whole_step_achieved": step_bytes_gbs, "whole_step_frac": step_bytes_gbs / peak,
                      "algorithmic_bytes_per_track_frame": BYTES_PER_TRACK_FRAME},

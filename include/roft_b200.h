@@ -74,8 +74,10 @@ typedef struct roftb_config {
     int32_t pose_delay;              /* same for pose_dataset                                      */
     int32_t device;                  /* CUDA device ordinal                                        */
     int32_t use_cuda_graph;          /* reserved                                                   */
-    int32_t accum_fp64;              /* 1 (default): per-pixel Jacobian terms and normal-equation sums in
-                                        FP64; 0: FP32 terms (agreement then scales with cond(Lambda)*1e-7/sqrt(N)) */
+    int32_t accum_fp64;              /* precision of the per-pixel Jacobian terms / normal-equation sums:
+                                        1: FP64; 0: FP32 terms, FP64 reduction (agreement with the FP64 reference then
+                                        scales as cond(Lambda)*6e-8/sqrt(N)); 2 (default): FP64 for tracks with fewer
+                                        than 32768 candidate pixels, FP32 terms above */
 } roftb_config;
 
 /* One camera frame for all tracks = what the reference's sources deliver at one

@@ -173,6 +173,9 @@ struct PassArgs {
     double cxd, cyd, inv_fxd, inv_fyd;   // FP64 intrinsics: pixel -> normalised coordinates without systematic rounding
     // fused single-flow mask propagation (ImageSegmentationOFAidedSource.hpp:221-226) for tracks whose plan says so
     const WarpPlan* plan; uint8_t* state_dst; int32_t* winner;
+    // accumulation-precision routing of pass B: -1 = every track; otherwise this launch handles the tracks whose
+    // candidate count is (auto_small_is64 ? below : at or above) auto_threshold
+    int auto_threshold; int auto_take_small;
 };
 
 // AT = accumulation type of pass B: float (per-pixel terms and partial sums in FP32) or double (per-pixel terms
@@ -208,6 +211,10 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
         sc_val = (uint8_t)p.uniform_val;
     }
     if (!c.enable && !do_sc) return;
+    if (PASS == 1 && a.auto_threshold >= 0) {
+        const bool small = a.wt_n[gridDim.y + t] < a.auto_threshold;
+        if (small != (a.auto_take_small != 0)) return;  // the other precision variant handles this track
+    }
     const Geom& g = a.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t thr4 = (uint32_t)a.thr * 0x01010101u;
@@ -979,12 +986,23 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     }
     if (a.prof) cudaEventRecord(a.prof[3], s);
     const bool fuse_b = fuse && !a.weight_flow;
-    if (a.accum_fp64) {
+    // accum_fp64: 0 = FP32 terms, 1 = FP64 terms, 2 = auto: FP64 for tracks with fewer than kAutoFp64Candidates
+    // candidate pixels (small, typically ill-conditioned problems where FP32 rounding is amplified most and FP64 costs
+    // least), FP32 terms with FP64 reduction above (rounding averages out as 1/sqrt(N)); see DESIGN.md 4.1
+    pa.auto_threshold = -1;
+    pa.auto_take_small = 0;
+    if (a.accum_fp64 == 2) {
+        pa.auto_threshold = kAutoFp64Candidates;
+        pa.auto_take_small = 1;
+    }
+    if (a.accum_fp64 >= 1) {
         if (fuse_b)
             ROFTB_PASS(1, double, true);
         else
             ROFTB_PASS(1, double, false);
-    } else {
+    }
+    if (a.accum_fp64 == 2) pa.auto_take_small = 0;
+    if (a.accum_fp64 != 1) {
         if (fuse_b)
             ROFTB_PASS(1, float, true);
         else

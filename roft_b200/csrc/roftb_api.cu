@@ -204,7 +204,7 @@ void roftb_config_default(roftb_config* c) {
     c->use_pose = 1; c->use_pose_resync = 1; c->use_velocity = 1; c->flow_aided = 1;
     c->segm_delay = 6; c->pose_delay = 6;
     c->device = 0;
-    c->accum_fp64 = 1;
+    c->accum_fp64 = 2;
 }
 
 const char* roftb_last_error(const roftb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }

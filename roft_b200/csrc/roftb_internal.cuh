@@ -20,6 +20,7 @@ constexpr int kBlockTilePx = kThreads / 32 * kWarpTilePx;  // 4096 px
 //   S2 = sum l L2^T L2 over index set {1,2,3,4,5} (15)
 //   g1 = sum l L1^T dx (5), g2 = sum l L2^T dy (5), count (1)
 constexpr int kNAcc = 41;
+constexpr int kAutoFp64Candidates = 32768;   // accum_fp64 == 2: tracks with fewer candidate pixels accumulate in FP64
 constexpr int kSelBins = 4096;               // radix-select histogram bins per level
 constexpr int kMaxUkfOps = 2 * (ROFTB_MAX_DELAY + 2) + 2;
 

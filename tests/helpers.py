@@ -34,7 +34,7 @@ def to_roftb_config(cfg: o.RoftConfig, n_tracks: int, flow_format="f32"):
         ut_alpha=cfg.ut_alpha, ut_beta=cfg.ut_beta, ut_kappa=cfg.ut_kappa,
         use_pose=int(cfg.use_pose), use_pose_resync=int(cfg.use_pose_resync), use_velocity=int(cfg.use_velocity),
         flow_aided=int(cfg.flow_aided), segm_delay=cfg.segm_delay, pose_delay=cfg.pose_delay,
-        accum_fp64=int(os.environ.get("ROFTB_TEST_ACCUM_FP64", "1")))
+        accum_fp64=int(os.environ.get("ROFTB_TEST_ACCUM_FP64", "2")))
 
 
 def sequence(cfg: o.RoftConfig, n_tracks, n_frames, seed=3, flow_format="f32", **kw):

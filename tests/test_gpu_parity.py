@@ -283,3 +283,37 @@ def test_full_resolution_properties(api):
     m0 = m.copy(); m0[:, 0, 0] = 0
     assert np.array_equal(raw0, m0)
     assert np.array_equal(o.threshold_mask(thr0.reshape(-1, cfg.width)).reshape(thr0.shape), thr0)
+
+
+@pytest.mark.parametrize("accum", [2, 1])
+def test_full_resolution_filter_loop_vs_sequential_cpp(api, accum):
+    """BASELINE size (1280x720, every masked pixel, ~3e5 measurements per frame): the whole filter loop against the
+    C++ restatement with the SEQUENTIAL per-pixel Kalman update, for the default (auto) and the FP64 accumulation."""
+    import cpu_ref
+    cfg = o.RoftConfig(subsampling_radius=1.0, segm_delay=2, pose_delay=2)
+    T, F = 2, 6
+    seq = sequence(cfg, T, F, target_coverage=0.3)
+    x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
+    rc = to_roftb_config(cfg, T)
+    rc.accum_fp64 = accum
+    trk = api.Tracker(rc)
+    trk.init(x0)
+    refs = [cpu_ref.CFilter(cfg, x0[t]) for t in range(T)]
+    for k in range(F):
+        frs = [frame_inputs(seq, cfg, k, t) for t in range(T)]
+        mask = np.stack([f.mask for f in frs]) if frs[0].mask is not None else None
+        pose = np.stack([f.pose if f.pose is not None else np.zeros(7) for f in frs])
+        pv = np.array([f.pose is not None for f in frs], np.uint8)
+        flow = np.stack([f.flow for f in frs]) if k > 0 else None
+        trk.step(np.stack([f.depth for f in frs]), flow, mask, pose=pose, pose_valid=pv)
+        pm, vm = trk.state()
+        raw, thr = trk.mask()
+        cnt, _, _ = trk.velocity_info()
+        for t in range(T):
+            refs[t].step(frs[t].depth, frs[t].flow, frs[t].mask, frs[t].pose, frs[t].dt)
+            epm, _, evm, _, en = refs[t].state()
+            eraw, ethr = refs[t].mask()
+            assert np.array_equal(raw[t], eraw) and np.array_equal(thr[t], ethr), (k, t)
+            assert cnt[t] == en, (k, t, cnt[t], en)
+            assert rel(vm[t], evm) < TOL or np.linalg.norm(vm[t] - evm) < 1e-9, (accum, k, t, rel(vm[t], evm))
+            assert rel(pm[t, :9], epm[:9]) < TOL and quat_close(pm[t, 9:], epm[9:]) < TOL, (accum, k, t)
