@@ -241,9 +241,15 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
     if (PASS == 1 && a.weight_flow) wp = a.wp[t];
 
     AT acc[kNAcc];
+    // FP32 variant: S1/S2 (and g1/g2) are accumulated as packed pairs with FFMA2 (two FP32 FMAs per issue slot on sm_100)
+    constexpr bool kPacked = (PASS == 1 && sizeof(AT) == 4);
+    float2 acc2[kPacked ? 20 : 1];
+    float cnt_acc = 0.f;
     if (PASS == 1) {
 #pragma unroll
         for (int i = 0; i < kNAcc; ++i) acc[i] = (AT)0;
+#pragma unroll
+        for (int i = 0; i < (kPacked ? 20 : 1); ++i) acc2[i] = make_float2(0.f, 0.f);
     }
 
     const int n_list = a.wt_n[t];
@@ -372,10 +378,14 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
                     float l1[5], l2[5];
                     l1[0] = ia; l1[1] = -xh * ia; l1[2] = -xh * yh; l1[3] = fmaf(xh, xh, 1.0f); l1[4] = -yh;
                     l2[0] = ia; l2[1] = -yh * ia; l2[2] = -fmaf(yh, yh, 1.0f); l2[3] = xh * yh; l2[4] = xh;
-                    const float p1 = l1[0] * x[0] + l1[1] * x[2] + l1[2] * x[3] + l1[3] * x[4] + l1[4] * x[5];
-                    const float p2 = l2[0] * x[1] + l2[1] * x[2] + l2[2] * x[3] + l2[3] * x[4] + l2[4] * x[5];
-                    const float n1 = dx - c1 * p1, n2 = dy - c2 * p2;
-                    const float nr = sqrt_approx(n1 * n1 + n2 * n2);
+                    // predicted flow of both rows at once (packed FP32x2): p = sum_k (l1[k], l2[k]) * (xa[k], xb[k])
+                    float2 pp = __fmul2_rn(make_float2(l1[0], l2[0]), make_float2(x[0], x[1]));
+                    pp = __ffma2_rn(make_float2(l1[1], l2[1]), make_float2(x[2], x[2]), pp);
+                    pp = __ffma2_rn(make_float2(l1[2], l2[2]), make_float2(x[3], x[3]), pp);
+                    pp = __ffma2_rn(make_float2(l1[3], l2[3]), make_float2(x[4], x[4]), pp);
+                    pp = __ffma2_rn(make_float2(l1[4], l2[4]), make_float2(x[5], x[5]), pp);
+                    const float2 nn = __ffma2_rn(make_float2(-c1, -c2), pp, make_float2(dx, dy));
+                    const float nr = sqrt_approx(fmaf(nn.x, nn.x, nn.y * nn.y));
                     if (PASS == 0) {
                         if (g.stride > 1) {
                             if (cand) norms_t[nslot++] = valid ? nr : -1.0f;  // compact: slot = rank / stride
@@ -385,6 +395,27 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
                     } else if (valid) {
                         float l = 1.0f;
                         if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
+                        if (kPacked) {
+                            const float2 e[5] = {make_float2(l1[0], l2[0]), make_float2(l1[1], l2[1]), make_float2(l1[2], l2[2]),
+                                                 make_float2(l1[3], l2[3]), make_float2(l1[4], l2[4])};
+                            const float2 ll = make_float2(l, l);
+                            float2 w[5];
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) w[k] = __fmul2_rn(ll, e[k]);
+                            int o = 0;
+#pragma unroll
+                            for (int r = 0; r < 5; ++r)
+#pragma unroll
+                                for (int q = r; q < 5; ++q) {
+                                    acc2[o] = __ffma2_rn(w[r], e[q], acc2[o]);
+                                    ++o;
+                                }
+                            const float2 zz = make_float2(dx, dy);
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) acc2[15 + k] = __ffma2_rn(w[k], zz, acc2[15 + k]);
+                            cnt_acc += 1.0f;
+                            continue;
+                        }
                         AT e1[5], e2[5];
                         if (sizeof(AT) == 8) {
                             // FP64 per-pixel terms: 1/d from the FP32 approximation (rel. error < 2^-22) by two Newton steps
@@ -435,6 +466,19 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
         }
     }
 
+    if (kPacked) {
+#pragma unroll
+        for (int o = 0; o < 15; ++o) {
+            acc[o] = (AT)acc2[o].x;
+            acc[15 + o] = (AT)acc2[o].y;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            acc[30 + k] = (AT)acc2[15 + k].x;
+            acc[35 + k] = (AT)acc2[15 + k].y;
+        }
+        acc[40] = (AT)cnt_acc;
+    }
     if (PASS == 1) {
         // one partial per WARP (no block barrier: warps finish at different times)
         double* out = a.partials + ((long long)t * a.max_blocks + blockIdx.x * (kThreads / 32) + warp) * kNAcc;
