@@ -176,6 +176,7 @@ struct PassArgs {
     // accumulation-precision routing of pass B: -1 = every track; otherwise this launch handles the tracks whose
     // candidate count is (auto_small_is64 ? below : at or above) auto_threshold
     int auto_threshold; int auto_take_small;
+    int reuse_norms;  // pass B, stride 1, weighting on: read the innovation norm / validity written by pass A
 };
 
 // AT = accumulation type of pass B: float (per-pixel terms and partial sums in FP32) or double (per-pixel terms
@@ -284,8 +285,12 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
 
         // software pipeline over the four units: loads of unit j+1 are issued before unit j is processed
         float4 Dc, F0c, F1c, Dn, F0n, F1n;
+        float4 Nc = make_float4(-1.f, -1.f, -1.f, -1.f), Nn = Nc;  // pass B: norms of pass A (negative: not a valid measurement)
+        const bool reuse = PASS == 1 && a.reuse_norms;
+        const float4* nq4 = reinterpret_cast<const float4*>(norms_t);
         {
             const int q = __shfl_sync(0xffffffffu, my_unit, 0) * 32 + lane;
+            if (reuse) Nc = get4(nq4 + g0 * 32 + lane, (sel & 0xfu) != 0u);
             Dc = get4(dq + q, (sel & 0xfu) != 0u);
             if (FAST) {
                 const bool on = (need & 0xfu) != 0u;
@@ -297,6 +302,7 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
         for (int j = 0; j < 4; ++j) {
             if (j < 3) {
                 const int qn = __shfl_sync(0xffffffffu, my_unit, j + 1) * 32 + lane;
+                if (reuse) Nn = get4(nq4 + (g0 + j + 1) * 32 + lane, ((sel >> (4 * (j + 1))) & 0xfu) != 0u);
                 Dn = get4(dq + qn, ((sel >> (4 * (j + 1))) & 0xfu) != 0u);
                 if (FAST) {
                     const bool on = ((need >> (4 * (j + 1))) & 0xfu) != 0u;
@@ -371,32 +377,45 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
                         if (ok) dst_t[iy * uW + ix] = sc_val;
                     }
                     const float d = comp(Dc, i);
-                    // hpp:252 gates
-                    const bool valid = cand && fabsf(dx) < 1e9f && fabsf(dy) < 1e9f && d > 0.f && d < max_d;
                     const float xh = fmaf((float)i, inv_fx, xh0);
                     const float ia = rcp_approx(d);
                     float l1[5], l2[5];
                     l1[0] = ia; l1[1] = -xh * ia; l1[2] = -xh * yh; l1[3] = fmaf(xh, xh, 1.0f); l1[4] = -yh;
                     l2[0] = ia; l2[1] = -yh * ia; l2[2] = -fmaf(yh, yh, 1.0f); l2[3] = xh * yh; l2[4] = xh;
-                    // predicted flow of both rows at once (packed FP32x2): p = sum_k (l1[k], l2[k]) * (xa[k], xb[k])
-                    float2 pp = __fmul2_rn(make_float2(l1[0], l2[0]), make_float2(x[0], x[1]));
-                    pp = __ffma2_rn(make_float2(l1[1], l2[1]), make_float2(x[2], x[2]), pp);
-                    pp = __ffma2_rn(make_float2(l1[2], l2[2]), make_float2(x[3], x[3]), pp);
-                    pp = __ffma2_rn(make_float2(l1[3], l2[3]), make_float2(x[4], x[4]), pp);
-                    pp = __ffma2_rn(make_float2(l1[4], l2[4]), make_float2(x[5], x[5]), pp);
-                    const float2 nn = __ffma2_rn(make_float2(-c1, -c2), pp, make_float2(dx, dy));
-                    const float nr = sqrt_approx(fmaf(nn.x, nn.x, nn.y * nn.y));
+                    bool valid;
+                    float nr;
+                    if (reuse) {
+                        // pass A already applied the gates and computed the innovation norm of this pixel
+                        nr = comp(Nc, i);
+                        valid = cand && nr >= 0.f;
+                    } else {
+                        // hpp:252 gates
+                        valid = cand && fabsf(dx) < 1e9f && fabsf(dy) < 1e9f && d > 0.f && d < max_d;
+                        // predicted flow of both rows at once (packed FP32x2): p = sum_k (l1[k], l2[k]) * (xa[k], xb[k])
+                        float2 pp = __fmul2_rn(make_float2(l1[0], l2[0]), make_float2(x[0], x[1]));
+                        pp = __ffma2_rn(make_float2(l1[1], l2[1]), make_float2(x[2], x[2]), pp);
+                        pp = __ffma2_rn(make_float2(l1[2], l2[2]), make_float2(x[3], x[3]), pp);
+                        pp = __ffma2_rn(make_float2(l1[3], l2[3]), make_float2(x[4], x[4]), pp);
+                        pp = __ffma2_rn(make_float2(l1[4], l2[4]), make_float2(x[5], x[5]), pp);
+                        const float2 nn = __ffma2_rn(make_float2(-c1, -c2), pp, make_float2(dx, dy));
+                        nr = sqrt_approx(fmaf(nn.x, nn.x, nn.y * nn.y));
+                    }
                     if (PASS == 0) {
                         if (g.stride > 1) {
                             if (cand) norms_t[nslot++] = valid ? nr : -1.0f;  // compact: slot = rank / stride
                         } else if (valid) {
                             if (i == 0) nv.x = nr; else if (i == 1) nv.y = nr; else if (i == 2) nv.z = nr; else nv.w = nr;
                         }
-                    } else if (valid) {
+                    } else if (kPacked) {
+                        // branch-free: an invalid pixel contributes with weight 0 (its inputs are sanitised first)
                         float l = 1.0f;
                         if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
-                        if (kPacked) {
-                            const float2 e[5] = {make_float2(l1[0], l2[0]), make_float2(l1[1], l2[1]), make_float2(l1[2], l2[2]),
+                        l = valid ? l : 0.f;
+                        const float ias = valid ? ia : 0.f;
+                        dx = valid ? dx : 0.f;
+                        dy = valid ? dy : 0.f;
+                        {
+                            const float2 e[5] = {make_float2(ias, ias), make_float2(-xh * ias, -yh * ias), make_float2(l1[2], l2[2]),
                                                  make_float2(l1[3], l2[3]), make_float2(l1[4], l2[4])};
                             const float2 ll = make_float2(l, l);
                             float2 w[5];
@@ -413,9 +432,11 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
                             const float2 zz = make_float2(dx, dy);
 #pragma unroll
                             for (int k = 0; k < 5; ++k) acc2[15 + k] = __ffma2_rn(w[k], zz, acc2[15 + k]);
-                            cnt_acc += 1.0f;
-                            continue;
+                            cnt_acc += valid ? 1.0f : 0.f;
                         }
+                    } else if (valid) {
+                        float l = 1.0f;
+                        if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
                         AT e1[5], e2[5];
                         if (sizeof(AT) == 8) {
                             // FP64 per-pixel terms: 1/d from the FP32 approximation (rel. error < 2^-22) by two Newton steps
@@ -463,6 +484,7 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
             Dc = Dn;
             F0c = F0n;
             F1c = F1n;
+            Nc = Nn;
         }
     }
 
@@ -1035,6 +1057,7 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     // least), FP32 terms with FP64 reduction above (rounding averages out as 1/sqrt(N)); see DESIGN.md 4.1
     pa.auto_threshold = -1;
     pa.auto_take_small = 0;
+    pa.reuse_norms = (a.weight_flow && g.stride == 1) ? 1 : 0;
     if (a.accum_fp64 == 2) {
         pa.auto_threshold = kAutoFp64Candidates;
         pa.auto_take_small = 1;
