@@ -95,20 +95,31 @@ __global__ void __launch_bounds__(kThreads) k_tile_count(const uint8_t* __restri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t thr4 = (uint32_t)thr * 0x01010101u;
     const uint32_t* mq = reinterpret_cast<const uint32_t*>(plane + (long long)t * stride);
-    const int nq = HW >> 2;
-    const int n_super = (n_units + 3) >> 2;  // four units per warp iteration: four independent loads in flight
-    for (int wt = blockIdx.x * (kThreads / 32) + warp; wt < n_super; wt += gridDim.x * (kThreads / 32)) {
-        int c[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int q = wt * 128 + j * 32 + lane;
-            const uint32_t m = q < nq ? ld_nc_u32(mq + q) : 0u;
-            c[j] = (__popc(__vcmpne4(m, 0u)) >> 3) | ((__popc(__vcmpgtu4(m, thr4)) >> 3) << 16);
+    const uint4* m4 = reinterpret_cast<const uint4*>(plane + (long long)t * stride);
+    const int n16 = HW >> 4;
+    const int n_blk = (n_units + 3) >> 2;  // 512-px blocks: one 128-bit load per lane, 8 lanes per unit
+    const unsigned gmask = 0xffu << (8 * (lane >> 3));
+    auto count16 = [&](const uint4& w) {
+        const int c0 = __popc(__vcmpne4(w.x, 0u)) + __popc(__vcmpne4(w.y, 0u)) + __popc(__vcmpne4(w.z, 0u)) + __popc(__vcmpne4(w.w, 0u));
+        const int c1 = __popc(__vcmpgtu4(w.x, thr4)) + __popc(__vcmpgtu4(w.y, thr4)) + __popc(__vcmpgtu4(w.z, thr4)) +
+                       __popc(__vcmpgtu4(w.w, thr4));
+        return (unsigned)((c0 >> 3) | ((c1 >> 3) << 16));
+    };
+    const int wstride = gridDim.x * (kThreads / 32);
+    for (int b = blockIdx.x * (kThreads / 32) + warp; b < n_blk; b += 2 * wstride) {
+        // two independent 128-bit loads in flight per lane
+        const int b2 = b + wstride;
+        const int qa = b * 32 + lane, qb = b2 * 32 + lane;
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 wa = qa < n16 ? ld_nc_u4(m4 + qa) : zero;
+        const uint4 wb = (b2 < n_blk && qb < n16) ? ld_nc_u4(m4 + qb) : zero;
+        const unsigned ca = __reduce_add_sync(gmask, count16(wa));  // both 16-bit fields stay <= 128
+        const unsigned cb = __reduce_add_sync(gmask, count16(wb));
+        if ((lane & 7) == 0) {
+            const int ua = b * 4 + (lane >> 3), ub = b2 * 4 + (lane >> 3);
+            if (ua < n_units) wt_count[(long long)t * n_units + ua] = (int)ca;
+            if (b2 < n_blk && ub < n_units) wt_count[(long long)t * n_units + ub] = (int)cb;
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) c[j] = (int)__reduce_add_sync(0xffffffffu, (unsigned)c[j]);  // fields stay <= 128
-        if (lane < 4 && wt * 4 + lane < n_units)
-            wt_count[(long long)t * n_units + wt * 4 + lane] = lane == 0 ? c[0] : lane == 1 ? c[1] : lane == 2 ? c[2] : c[3];
     }
 }
 

@@ -216,60 +216,67 @@ __global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft
     // walk the worklist of non-empty units (128 px) of the source plane; one quad (4 px) per lane
     const int32_t* list = (sp.src_new ? n_list : s_list) + (long long)t * n_warp_tiles;
     const int n_list_items = (sp.src_new ? n_n : s_n)[t];
-    for (int li = blockIdx.x * (kThreads / 32) + warp; li < n_list_items; li += gridDim.x * (kThreads / 32)) {
-        const int q = list[li] * 32 + lane;
-        uint32_t mj = q < nq ? ld_nc_u32(reinterpret_cast<const uint32_t*>(src) + q) : 0u;
-        if (sp.zero_origin && q == 0) mj &= 0xffffff00u;
-        {
-            if (mj == 0u) continue;
+    // NQ units per warp iteration: every lane chases 4*NQ pixels together, so 4*NQ independent flow gathers are in
+    // flight per hop (a chain of D dependent DRAM accesses per pixel is pure latency otherwise)
+    constexpr int NQ = 2, NP = 4 * NQ;
+    for (int li = (blockIdx.x * (kThreads / 32) + warp) * NQ; li < n_list_items; li += gridDim.x * (kThreads / 32) * NQ) {
+        float tx[NP], ty[NP];
+        bool alive[NP];
+        int src_px[NQ];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            const bool in = li + k < n_list_items;
+            const int q = in ? list[li + k] * 32 + lane : 0;
+            uint32_t mj = (in && q < nq) ? ld_nc_u32(reinterpret_cast<const uint32_t*>(src) + q) : 0u;
+            if (sp.zero_origin && q == 0) mj &= 0xffffff00u;
             const int px = q << 2;
             const int v = px / g.W;
             const int u0 = px - v * g.W;
-            // the four pixels of the quad are chased together: four independent flow gathers in flight per hop
-            // (a chain of D dependent DRAM accesses per pixel is pure latency otherwise)
-            float tx[4], ty[4];
-            bool alive[4];
+            src_px[k] = px;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                tx[i] = (float)(u0 + i);
-                ty[i] = (float)v;
-                alive[i] = ((mj >> (8 * i)) & 0xffu) != 0u;
+                tx[4 * k + i] = (float)(u0 + i);
+                ty[4 * k + i] = (float)v;
+                alive[4 * k + i] = ((mj >> (8 * i)) & 0xffu) != 0u;
+                any |= alive[4 * k + i];
             }
-            for (int h = 0; h < sp.n_flows; ++h) {
-                const char* base = reinterpret_cast<const char*>(ft.flow[sp.flow_slot[h]]) +
-                                   (long long)t * ft.flow_stride * (g.flow_s16 ? 2 : 4);
-                float2 f[4];
+        }
+        if (!any) continue;
+        for (int h = 0; h < sp.n_flows; ++h) {
+            const char* base = reinterpret_cast<const char*>(ft.flow[sp.flow_slot[h]]) +
+                               (long long)t * ft.flow_stride * (g.flow_s16 ? 2 : 4);
+            float2 f[NP];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    f[i] = make_float2(0.f, 0.f);
-                    if (!alive[i]) continue;
-                    const int ix = cvt_int(tx[i]), iy = cvt_int(ty[i]);
-                    if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) {  // hpp:262-266
-                        alive[i] = false;
-                        continue;
-                    }
-                    const int fr = cvt_int(div_grid(ty[i], g));
-                    const int fc = cvt_int(div_grid(tx[i], g));
-                    f[i] = load_flow(base, (long long)fr * g.Wf + fc, g);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (!alive[i]) continue;
-                    tx[i] = __fadd_rn(tx[i], f[i].x);
-                    ty[i] = __fadd_rn(ty[i], f[i].y);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < NP; ++i) {
+                f[i] = make_float2(0.f, 0.f);
                 if (!alive[i]) continue;
                 const int ix = cvt_int(tx[i]), iy = cvt_int(ty[i]);
-                if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) continue;
-                const int d = iy * g.W + ix;
-                if (general)
-                    atomicMax(win + d, px + i);
-                else
-                    dst[d] = uval;
+                if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) {  // hpp:262-266
+                    alive[i] = false;
+                    continue;
+                }
+                const int fr = cvt_int(div_grid(ty[i], g));
+                const int fc = cvt_int(div_grid(tx[i], g));
+                f[i] = load_flow(base, (long long)fr * g.Wf + fc, g);
             }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                if (!alive[i]) continue;
+                tx[i] = __fadd_rn(tx[i], f[i].x);
+                ty[i] = __fadd_rn(ty[i], f[i].y);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            if (!alive[i]) continue;
+            const int ix = cvt_int(tx[i]), iy = cvt_int(ty[i]);
+            if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) continue;
+            const int d = iy * g.W + ix;
+            if (general)
+                atomicMax(win + d, src_px[i >> 2] + (i & 3));
+            else
+                dst[d] = uval;
         }
     }
 }
