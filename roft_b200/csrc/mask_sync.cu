@@ -194,6 +194,9 @@ __device__ __forceinline__ int chase(const Geom& g, const FrameTable& ft, const 
     return iy * g.W + ix;
 }
 
+// FASTF: float2 flow at full resolution with scale 1 - the hop is then 2 conversions, an unsigned range check, one
+// 64-bit gather and two IEEE adds (the generic hop spends ~80 instructions on format / grid / scale handling)
+template <bool FASTF>
 __global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft, const WarpPlan* __restrict__ plan,
                                                           const uint8_t* __restrict__ new_mask, long long new_stride,
                                                           const uint8_t* __restrict__ state_src,
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft
             }
         }
         if (!any) continue;
+        const unsigned uW = (unsigned)g.W, uH = (unsigned)g.H;
         for (int h = 0; h < sp.n_flows; ++h) {
             const char* base = reinterpret_cast<const char*>(ft.flow[sp.flow_slot[h]]) +
                                (long long)t * ft.flow_stride * (g.flow_s16 ? 2 : 4);
@@ -250,6 +254,14 @@ __global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 f[i] = make_float2(0.f, 0.f);
+                if (FASTF) {
+                    // C truncation; the GPU converts NaN to 0, so NaN is tested; +-inf / huge saturate out of range like
+                    // x86's INT_MIN; the flow element of (int(ty), int(tx)) is element iy*W+ix (grid 1)
+                    const unsigned ix = (unsigned)(int)tx[i], iy = (unsigned)(int)ty[i];
+                    alive[i] = alive[i] && tx[i] == tx[i] && ty[i] == ty[i] && ix < uW && iy < uH;  // hpp:262-266
+                    if (alive[i]) f[i] = __ldg(reinterpret_cast<const float2*>(base) + (iy * uW + ix));
+                    continue;
+                }
                 if (!alive[i]) continue;
                 const int ix = cvt_int(tx[i]), iy = cvt_int(ty[i]);
                 if (ix < 0 || ix >= g.W || iy < 0 || iy >= g.H) {  // hpp:262-266
@@ -347,8 +359,12 @@ int launch_mask_scatter_gather(const MaskSyncArgs& a, cudaStream_t s) {
     int targetq = max(1, (148 * 16 + T - 1) / T);
     bq = max(1, min(bq, targetq));
     int bs = max(1, min((a.n_warp_tiles + 7) / 8, (148 * 16 + T - 1) / T));
-    ROFTB_LAUNCH(k_warp_scatter, dim3(bs, T), kThreads, 0, s, a.g, a.ft, a.plan, a.new_mask, a.new_stride, a.state_src,
-                 a.state_dst, a.winner, a.s_list, a.s_n, a.n_list, a.n_n, a.n_warp_tiles);
+    if (!a.g.flow_s16 && a.g.grid == 1 && a.g.scale_mode == 0)
+        ROFTB_LAUNCH(k_warp_scatter<true>, dim3(bs, T), kThreads, 0, s, a.g, a.ft, a.plan, a.new_mask, a.new_stride, a.state_src,
+                     a.state_dst, a.winner, a.s_list, a.s_n, a.n_list, a.n_n, a.n_warp_tiles);
+    else
+        ROFTB_LAUNCH(k_warp_scatter<false>, dim3(bs, T), kThreads, 0, s, a.g, a.ft, a.plan, a.new_mask, a.new_stride, a.state_src,
+                     a.state_dst, a.winner, a.s_list, a.s_n, a.n_list, a.n_n, a.n_warp_tiles);
     ROFTB_LAUNCH(k_warp_gather, dim3(bq, T), kThreads, 0, s, a.plan, a.new_mask, a.new_stride, a.state_src, a.state_dst,
                  a.winner, HW);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
