@@ -1003,7 +1003,6 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     int bpt = max(1, (148 * 16 + T - 1) / T);
     bpt = min(bpt, min(n_block_tiles, a.max_blocks / (kThreads / 32)));
 
-    if (a.prof) cudaEventRecord(a.prof[0], s);
     if (a.prof) cudaEventRecord(a.prof[1], s);
     PassArgs pa;
     pa.g = g;
@@ -1048,6 +1047,7 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
             ROFTB_PASS(0, float, true);
         else
             ROFTB_PASS(0, float, false);
+        if (a.ev_first_pass) cudaEventRecord(a.ev_first_pass, s);
         if (a.prof) cudaEventRecord(a.prof[2], s);
         ROFTB_LAUNCH(k_sel_init, (T + 127) / 128, 128, 0, s, T, a.wt_n, g.stride, a.sel, a.ctl);
         // enough blocks per track to spread the list, few enough that the per-block histogram flush stays cheap
@@ -1087,6 +1087,7 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
             ROFTB_PASS(1, float, false);
     }
 #undef ROFTB_PASS
+    if (a.ev_first_pass && !a.weight_flow) cudaEventRecord(a.ev_first_pass, s);
     if (a.prof) cudaEventRecord(a.prof[4], s);
     EpiArgs e;
     e.n_tracks = T;

@@ -51,7 +51,9 @@ struct roftb_ctx {
     size_t HW = 0;
     size_t flow_elems = 0;  // scalar elements per track
     int dev = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr, prep_stream = nullptr;
+    cudaEvent_t prep_event[2] = {nullptr, nullptr}, pass_a_event = nullptr;
+    bool pass_a_event_used = false;
     cudaEvent_t vel_event[8], ukf_event[8], join_event = nullptr, plan_event = nullptr, mask_event = nullptr;
     bool ukf_event_used[8];
     bool mask_event_used = false;
@@ -59,7 +61,7 @@ struct roftb_ctx {
     long long launches0 = 0;
 
     // device state
-    uint8_t* mask_state[2] = {nullptr, nullptr};
+    uint8_t* mask_state[3] = {nullptr, nullptr, nullptr};  // ring of 3: step k reads [k%3], writes [(k+1)%3]
     int mask_cur = 0;
     int32_t* winner = nullptr;
     float* norms = nullptr;
@@ -267,6 +269,10 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(cudaStreamCreateWithFlags(&ctx->ukf_stream, cudaStreamNonBlocking));
     CKC(cudaEventCreateWithFlags(&ctx->join_event, cudaEventDisableTiming));
     CKC(cudaStreamCreateWithFlags(&ctx->mask_stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->prep_event[0], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->prep_event[1], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->pass_a_event, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->plan_event, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->mask_event, cudaEventDisableTiming));
     for (int i = 0; i < kCtlRing; ++i) {
@@ -279,6 +285,7 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
         for (int j = 0; j < 11; ++j) CKC(cudaEventCreate(&ctx->prof_ev[i][j]));
     CKC(dalloc(&ctx->mask_state[0], T * HW));
     CKC(dalloc(&ctx->mask_state[1], T * HW));
+    CKC(dalloc(&ctx->mask_state[2], T * HW));
     CKC(dalloc(&ctx->winner, T * HW));
     CKC(dalloc(&ctx->norms, (size_t)T * ctx->n_units * kUnitPx));
     CKC(dalloc(&ctx->norm_count, (size_t)T));
@@ -286,15 +293,15 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(dalloc(&ctx->sel, (size_t)T));
     CKC(dalloc(&ctx->wp, (size_t)T));
     CKC(dalloc(&ctx->partials, (size_t)T * ctx->max_blocks * kNAcc));
-    CKC(dalloc(&ctx->wt_count, (size_t)T * ctx->n_units));
+    CKC(dalloc(&ctx->wt_count, (size_t)2 * T * ctx->n_units));   // x2: worklists / plans are double-buffered by step parity
     CKC(dalloc(&ctx->wt_count2, (size_t)T * ctx->n_warp_tiles));
-    CKC(dalloc(&ctx->wt_list, (size_t)T * ctx->n_units));
-    CKC(dalloc(&ctx->wt_n, (size_t)2 * T));
-    CKC(dalloc(&ctx->nl_count, (size_t)T * ctx->n_units));
-    CKC(dalloc(&ctx->nl_list, (size_t)T * ctx->n_units));
-    CKC(dalloc(&ctx->nl_n, (size_t)2 * T));
+    CKC(dalloc(&ctx->wt_list, (size_t)2 * T * ctx->n_units));
+    CKC(dalloc(&ctx->wt_n, (size_t)4 * T));
+    CKC(dalloc(&ctx->nl_count, (size_t)2 * T * ctx->n_units));
+    CKC(dalloc(&ctx->nl_list, (size_t)2 * T * ctx->n_units));
+    CKC(dalloc(&ctx->nl_n, (size_t)4 * T));
     CKC(dalloc(&ctx->stat, (size_t)T));
-    CKC(dalloc(&ctx->plan, (size_t)T));
+    CKC(dalloc(&ctx->plan, (size_t)2 * T));
     CKC(dalloc(&ctx->fbuf, (size_t)T));
     CKC(dalloc(&ctx->v_mean, (size_t)T * 6));
     CKC(dalloc(&ctx->v_cov, (size_t)T * 36));
@@ -307,7 +314,7 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(dalloc(&ctx->d_count, (size_t)T));
     CKC(dalloc(&ctx->d_lambda, (size_t)T * 36));
     CKC(dalloc(&ctx->d_eta, (size_t)T * 6));
-    CKC(dalloc(&ctx->d_wctl, (size_t)T));
+    CKC(dalloc(&ctx->d_wctl, (size_t)2 * T));
     CKC(dalloc(&ctx->d_vctl, (size_t)T));
     CKC(dalloc(&ctx->d_ops, (size_t)T * kMaxUkfOps * kCtlRing));
     CKC(dalloc(&ctx->d_nops, (size_t)T * kCtlRing));
@@ -341,7 +348,7 @@ void roftb_destroy(roftb_ctx* ctx) {
     cudaSetDevice(ctx->dev);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->winner, ctx->norms, ctx->norm_count, ctx->hist, ctx->sel,
+    void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->mask_state[2], ctx->winner, ctx->norms, ctx->norm_count, ctx->hist, ctx->sel,
                      ctx->wp, ctx->partials, ctx->wt_count, ctx->wt_count2, ctx->wt_list, ctx->wt_n, ctx->nl_count, ctx->nl_list, ctx->nl_n, ctx->stat, ctx->plan, ctx->fbuf, ctx->v_mean,
                      ctx->v_cov, ctx->p_mean, ctx->p_cov, ctx->pb_mean, ctx->pb_cov, ctx->vel_hist, ctx->q_diag,
                      ctx->d_count, ctx->d_lambda, ctx->d_eta, ctx->d_wctl, ctx->d_vctl, ctx->d_ops, ctx->d_nops,
@@ -365,6 +372,10 @@ void roftb_destroy(roftb_ctx* ctx) {
     if (ctx->plan_event) cudaEventDestroy(ctx->plan_event);
     if (ctx->mask_event) cudaEventDestroy(ctx->mask_event);
     if (ctx->mask_stream) { cudaStreamSynchronize(ctx->mask_stream); cudaStreamDestroy(ctx->mask_stream); }
+    if (ctx->prep_stream) { cudaStreamSynchronize(ctx->prep_stream); cudaStreamDestroy(ctx->prep_stream); }
+    for (int i = 0; i < 2; ++i)
+        if (ctx->prep_event[i]) cudaEventDestroy(ctx->prep_event[i]);
+    if (ctx->pass_a_event) cudaEventDestroy(ctx->pass_a_event);
     if (ctx->ukf_stream) { cudaStreamSynchronize(ctx->ukf_stream); cudaStreamDestroy(ctx->ukf_stream); }
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -376,6 +387,7 @@ int roftb_sync(roftb_ctx* ctx) {
     if (!ctx) return -2;
     CK(cudaSetDevice(ctx->dev));
     CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->prep_stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->mask_stream));
     CK(cudaStreamSynchronize(ctx->ukf_stream));
@@ -427,10 +439,12 @@ int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mea
     if (!ctx) return -2;
     const int T = ctx->T;
     CK(cudaSetDevice(ctx->dev));
+    CK(cudaStreamSynchronize(ctx->prep_stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->mask_stream));
     CK(cudaStreamSynchronize(ctx->ukf_stream));
     ctx->mask_event_used = false;
+    ctx->pass_a_event_used = false;
     // ROFTFilter::initialization_step (ROFTFilter.cpp:216-237)
     std::vector<double> pm((size_t)T * 13, 0.0), pc((size_t)T * 144, 0.0), vm((size_t)T * 6, 0.0), vc((size_t)T * 36, 0.0);
     for (int t = 0; t < T; ++t) {
@@ -449,6 +463,7 @@ int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mea
     CK(cudaMemset(ctx->vel_hist, 0, sizeof(double) * T * kHistRing * 6));
     CK(cudaMemset(ctx->mask_state[0], 0, (size_t)T * ctx->HW));
     CK(cudaMemset(ctx->mask_state[1], 0, (size_t)T * ctx->HW));
+    CK(cudaMemset(ctx->mask_state[2], 0, (size_t)T * ctx->HW));
     CK(cudaMemset(ctx->fbuf, 0, sizeof(FlowBuf) * T));
     CK(cudaMemset(ctx->norm_count, 0, sizeof(uint32_t) * T));
     CK(cudaMemset(ctx->d_count, 0, sizeof(int32_t) * T));
@@ -662,7 +677,9 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
     }
 
     cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->d_wctl, wc, sizeof(WarpCtl) * T, cudaMemcpyHostToDevice, s));
+    const int par = (int)(ctx->frame_idx & 1);
+    WarpCtl* d_wctl = ctx->d_wctl + (size_t)par * T;
+    CK(cudaMemcpyAsync(d_wctl, wc, sizeof(WarpCtl) * T, cudaMemcpyHostToDevice, ctx->prep_stream));
     CK(cudaMemcpyAsync(ctx->d_vctl, vc, sizeof(VelCtl) * T, cudaMemcpyHostToDevice, s));
     UkfOp* d_ops = ctx->d_ops + (size_t)cslot * T * kMaxUkfOps;
     int32_t* d_nops = ctx->d_nops + (size_t)cslot * T;
@@ -682,46 +699,60 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
     // mask stream : scatter/gather of the tracks with a NEW mask (chained through the buffered flows)
     // ukf stream  : pose UKF (needs only the twist published by the epilogue and the host-built op list)
     const uint8_t* seg_prev = ctx->mask_state[ctx->mask_cur];
-    uint8_t* seg_next = ctx->mask_state[ctx->mask_cur ^ 1];
+    uint8_t* seg_next = ctx->mask_state[(ctx->mask_cur + 1) % 3];
+    int32_t* wt_count = ctx->wt_count + (size_t)par * T * ctx->n_units;
+    int32_t* wt_list = ctx->wt_list + (size_t)par * T * ctx->n_units;
+    int32_t* wt_n = ctx->wt_n + (size_t)par * 2 * T;
+    int32_t* nl_count = ctx->nl_count + (size_t)par * T * ctx->n_units;
+    int32_t* nl_list = ctx->nl_list + (size_t)par * T * ctx->n_units;
+    int32_t* nl_n = ctx->nl_n + (size_t)par * 2 * T;
+    WarpPlan* plan = ctx->plan + (size_t)par * T;
     cudaEvent_t* pe = ctx->prof_on ? ctx->prof_ev[cslot] : nullptr;
     if (pe) prof_collect(ctx, cslot);
-    // the previous step's mask stream work produced (part of) seg_prev
-    if (ctx->mask_event_used) CK(cudaStreamWaitEvent(s, ctx->mask_event, 0));
-    if (pe) CK(cudaEventRecord(pe[10], s));
-    if (launch_tile_list(seg_prev, (long long)ctx->HW, 1, ctx->g.HW, T, ctx->wt_count, ctx->wt_list, ctx->wt_n, nullptr, 0, s))
-        return fail(ctx, "launch_tile_list failed");
     MaskSyncArgs ma;
     memset(&ma, 0, sizeof(ma));
     ma.g = ctx->g; ma.ft = ctx->ft; ma.n_tracks = T;
     ma.new_mask = any_new_mask ? d_mask : nullptr; ma.new_stride = mask_stride;
     ma.state_src = seg_prev; ma.state_dst = seg_next; ma.winner = ctx->winner;
-    ma.ctl = ctx->d_wctl; ma.stat = ctx->stat; ma.plan = ctx->plan; ma.fbuf = ctx->fbuf;
+    ma.ctl = d_wctl; ma.stat = ctx->stat; ma.plan = plan; ma.fbuf = ctx->fbuf;
     ma.segm_delay = cfg.segm_delay;
-    ma.s_list = ctx->wt_list; ma.s_n = ctx->wt_n; ma.n_list = ctx->nl_list; ma.n_n = ctx->nl_n; ma.n_warp_tiles = ctx->n_units;
+    ma.s_list = wt_list; ma.s_n = wt_n; ma.n_list = nl_list; ma.n_n = nl_n; ma.n_warp_tiles = ctx->n_units;
     ma.fuse = 1;
-    if (launch_mask_plan_init(ma, s)) return fail(ctx, "launch_mask_plan_init failed");
-    if (any_new_mask &&
-        launch_tile_list(d_mask, mask_stride, 0, ctx->g.HW, T, ctx->nl_count, ctx->nl_list, ctx->nl_n,
-                         reinterpret_cast<const int32_t*>(ctx->d_wctl), (int)(sizeof(WarpCtl) / 4), s))
-        return fail(ctx, "launch_tile_list failed");
-    CK(cudaEventRecord(ctx->plan_event, s));
+    {
+        // prep stream: everything that only needs the mask state of this step (complete once the previous step's
+        // pass A and new-mask scatter are done) - it overlaps the previous step's select / pass B / epilogue.
+        // Worklists, plans and the mask planes are multi-buffered so nothing still being read is overwritten.
+        cudaStream_t ps = ctx->prep_stream;
+        if (ctx->pass_a_event_used) CK(cudaStreamWaitEvent(ps, ctx->pass_a_event, 0));
+        if (ctx->mask_event_used) CK(cudaStreamWaitEvent(ps, ctx->mask_event, 0));
+        if (pe) CK(cudaEventRecord(pe[10], ps));
+        if (launch_tile_list(seg_prev, (long long)ctx->HW, 1, ctx->g.HW, T, wt_count, wt_list, wt_n, nullptr, 0, ps))
+            return fail(ctx, "launch_tile_list failed");
+        if (launch_mask_plan_init(ma, ps)) return fail(ctx, "launch_mask_plan_init failed");
+        if (any_new_mask && launch_tile_list(d_mask, mask_stride, 0, ctx->g.HW, T, nl_count, nl_list, nl_n,
+                                             reinterpret_cast<const int32_t*>(d_wctl), (int)(sizeof(WarpCtl) / 4), ps))
+            return fail(ctx, "launch_tile_list failed");
+        if (pe) CK(cudaEventRecord(pe[0], ps));
+        CK(cudaEventRecord(ctx->prep_event[par], ps));
+    }
     {
         cudaStream_t ms = ctx->mask_stream;
-        CK(cudaStreamWaitEvent(ms, ctx->plan_event, 0));
+        CK(cudaStreamWaitEvent(ms, ctx->prep_event[par], 0));
         if (pe) CK(cudaEventRecord(pe[6], ms));
         if (launch_mask_scatter_gather(ma, ms)) return fail(ctx, "launch_mask_scatter_gather failed");
         if (pe) CK(cudaEventRecord(pe[7], ms));
         CK(cudaEventRecord(ctx->mask_event, ms));
         ctx->mask_event_used = true;
-        ctx->mask_cur ^= 1;
+        ctx->mask_cur = (ctx->mask_cur + 1) % 3;
     }
+    CK(cudaStreamWaitEvent(s, ctx->prep_event[par], 0));
     {
         VelocityArgs a;
         memset(&a, 0, sizeof(a));
         a.g = ctx->g; a.ft = ctx->ft; a.n_tracks = T;
         a.seg = seg_prev; a.seg_stride = (long long)ctx->HW; a.thr = 1;  // cv::threshold(> 1) applied on load
         a.ctl = ctx->d_vctl; a.weight_flow = cfg.weight_flow;
-        a.wt_count = ctx->wt_count; a.wt_list = ctx->wt_list; a.wt_n = ctx->wt_n; a.norms = ctx->norms; a.norm_count = ctx->norm_count; a.hist = ctx->hist;
+        a.wt_count = wt_count; a.wt_list = wt_list; a.wt_n = wt_n; a.norms = ctx->norms; a.norm_count = ctx->norm_count; a.hist = ctx->hist;
         a.sel = ctx->sel; a.wp = ctx->wp; a.partials = ctx->partials; a.max_blocks = ctx->max_blocks;
         a.v_mean = ctx->v_mean; a.v_cov = ctx->v_cov; a.q_diag = ctx->q_diag;
         a.r_flow[0] = cfg.cov_flow[0]; a.r_flow[1] = cfg.cov_flow[1];
@@ -730,8 +761,10 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
         a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
         a.out_count = ctx->d_count; a.out_lambda = ctx->d_lambda; a.out_eta = ctx->d_eta;
         a.update_state = 1;
-        a.fuse_scatter = 1; a.plan = ctx->plan; a.state_dst = seg_next; a.winner = ctx->winner;
+        a.fuse_scatter = 1; a.plan = plan; a.state_dst = seg_next; a.winner = ctx->winner;
         a.prof = pe;
+        a.ev_first_pass = ctx->pass_a_event;
+        ctx->pass_a_event_used = true;
         if (launch_velocity(a, s)) return fail(ctx, "launch_velocity failed");
         CK(cudaEventRecord(ctx->vel_event[cslot], s));
     }
