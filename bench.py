@@ -49,6 +49,8 @@ def parse_args():
                     help="precision of the per-pixel terms of the normal equations (roftb_config.accum_fp64)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-resync", action="store_true", help="diagnostic: pose re-sync replay off")
+    ap.add_argument("--per-step", action="store_true", help="diagnostic: print main-stream ms per step by phase of the mask period")
     ap.add_argument("--single-mask", action="store_true", help="diagnostic: deliver the mask / pose only at step 0")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -160,7 +162,8 @@ def run_own(args):
     T, F, D = args.tracks, args.frames, args.delay
 
     cfg = api.default_config(n_tracks=T, subsampling_radius=args.stride, segm_delay=D, pose_delay=D, device=local,
-                             accum_fp64={"fp32": 0, "fp64": 1, "auto": 2}[args.accum])
+                             accum_fp64={"fp32": 0, "fp64": 1, "auto": 2}[args.accum],
+                             **({"use_pose_resync": 0} if args.no_resync else {}))
     trk = api.Tracker(cfg)
     seq = build_frames(args, dev, rank * T)
     x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
@@ -210,8 +213,14 @@ def run_own(args):
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
     ext = torch.cuda.ExternalStream(trk.stream, device=dev)
     ev0.record(ext)
+    step_ev = []
+    host_t = [time.perf_counter()]
     for _ in range(args.steps):
         do_step(step); step += 1
+        host_t.append(time.perf_counter())
+        if args.per_step:  # diagnostic: main-stream time stamps per step (velocity chain only)
+            e = torch.cuda.Event(enable_timing=True); e.record(ext); step_ev.append((step - 1, e))
+    host_issue_ms = (host_t[-1] - host_t[0]) * 1e3 / args.steps
     trk.join()
     ev1.record(ext)
     barrier()
@@ -219,6 +228,16 @@ def run_own(args):
     dev_ms = ev0.elapsed_time(ev1)
     launches = trk.kernel_launches - l0
     phases, psteps = trk.profile(False)
+    if args.per_step and rank == 0:
+        prev = ev0
+        per = {}
+        for st_i, e in step_ev:
+            per.setdefault((st_i - D) % D, []).append(prev.elapsed_time(e)); prev = e
+        print("per-step ms by (step-D)%D:", {k: round(sum(v) / len(v), 3) for k, v in sorted(per.items())}, file=sys.stderr)
+        hper = {}
+        for i, (st_i, _) in enumerate(step_ev):
+            hper.setdefault((st_i - D) % D, []).append((host_t[i + 1] - host_t[i]) * 1e3)
+        print("host issue ms by (step-D)%D:", {k: round(sum(v) / len(v), 3) for k, v in sorted(hper.items())}, file=sys.stderr)
     clocks = sampler.finish(t0, t0 + wall) if sampler else None
     tms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -290,6 +309,7 @@ def run_own(args):
                      "algorithmic_bytes_per_track_frame": BYTES_PER_TRACK_FRAME},
         "phases_ms_per_step": phases,
         "gpu_launches": int(launches),
+        "host_issue_ms_per_step": round(host_issue_ms, 4),
         "clocks": clocks,
         "e2e": e2e,
         "wall_s": wall,

@@ -1,2 +1,6 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_flow_pass|k_warp_|k_sel_|k_tile_|k_ukf|k_vel_|k_mask_" -s 170 -c 204 --csv --log-file gpurun_out/launches_r1_final.csv python bench.py --no-cpu --no-e2e --steps 12 --warmup 12 > gpurun_out/b2.log 2>&1; tail -1 gpurun_out/b2.log | cut -c1-80
-ncu --set full --clock-control none --import-source on -k regex:"k_flow_pass" -s 24 -c 2 -o gpurun_out/prof_r1_final python bench.py --no-cpu --no-e2e --steps 2 --warmup 12 > gpurun_out/ncu_final.log 2>&1; tail -1 gpurun_out/ncu_final.log | cut -c1-100
+mkdir -p gpurun_out
+for extra in "" "--no-resync"; do
+timeout 800 python bench.py --no-cpu --no-e2e --per-step $extra --steps 48 --warmup 12 > gpurun_out/b.log 2>&1
+tail -5 gpurun_out/b.log | cut -c1-300
+grep -o '"host_issue_ms_per_step": [0-9.]*' gpurun_out/b.log
+done

@@ -524,51 +524,111 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
 }
 
 // ---- exact radix select of the upper median + Laplacian parameters ---------------------------
-__global__ void k_sel_init(int n_tracks, const int32_t* __restrict__ wt_n, int stride, SelState* __restrict__ sel,
-                           const VelCtl* __restrict__ ctl) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tracks) return;
-    SelState s;
-    s.prefix = 0;
-    // norm slots written by pass A: one per selected candidate (gated-out ones hold -1)
-    s.n_entries = !ctl[t].enable ? 0u : stride > 1 ? (uint32_t)((wt_n[n_tracks + t] + stride - 1) / stride)
-                                                   : (uint32_t)wt_n[t] * 128u;  // stride 1: 128 slots per listed unit
-    s.n = s.n_entries;  // valid count, fixed by the level-0 scan
-    s.k = 0;
-    s.less_cnt = 0;
-    s.less_sum = 0.0;
-    s.total_sum = 0.0;
-    s.less_max_bits = 0;
-    s.pad2 = 0;
-    sel[t] = s;
+// The select runs as three data passes over the norm slots; the per-track bookkeeping that used to be separate
+// one-block kernels (init, scan of the histogram, final parameters) is done by the LAST block of each pass to finish
+// for that track (ticket counter + __threadfence), which removes five dependent launches from the critical path.
+struct SelArgs {
+    const float* norms; long long norm_stride;
+    SelState* sel; uint32_t* hist; uint32_t* ticket;
+    const VelCtl* ctl; const int32_t* wt_n; int n_tracks; int stride;
+    WeightParams* wp;
+};
+
+__device__ __forceinline__ bool last_block_of_track(uint32_t* ticket, int t) {
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t v = atomicAdd(ticket + t, 1u);
+        is_last = (v == gridDim.x - 1);
+        if (is_last) ticket[t] = 0;
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last;
+}
+
+// histogram bin scan by the 256 threads of one block: finds the bin holding rank k, returns (bin, rank inside bin,
+// total count); the global histogram is read past L1 and zeroed for the next use
+template <int NB>
+__device__ __forceinline__ void scan_bins(uint32_t* gh, uint32_t k_or_half, bool k_is_half, uint32_t& bin_out, uint32_t& k_out,
+                                          uint32_t& total_out) {
+    constexpr int PER = NB / kThreads;
+    __shared__ uint32_t sh[kThreads / 32];
+    __shared__ uint32_t res[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t loc[PER];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        loc[i] = __ldcg(gh + threadIdx.x * PER + i);
+        gh[threadIdx.x * PER + i] = 0;
+        sum += loc[i];
+    }
+    const uint32_t incl = (uint32_t)warp_scan_incl((int)sum, lane);
+    if (lane == 31) sh[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+    for (int w = 0; w < kThreads / 32; ++w) {
+        if (w < warp) woff += sh[w];
+        total += sh[w];
+    }
+    uint32_t before = woff + incl - sum;
+    const uint32_t k = k_is_half ? (total >> 1) : k_or_half;
+    if (threadIdx.x == 0) { res[0] = 0; res[1] = 0; res[2] = total; }
+    __syncthreads();
+    if (k >= before && k < before + sum) {  // exactly one thread (if total > 0)
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            if (k < before + loc[i]) {
+                res[0] = threadIdx.x * PER + i;
+                res[1] = k - before;
+                break;
+            }
+            before += loc[i];
+        }
+    }
+    __syncthreads();
+    bin_out = res[0];
+    k_out = res[1];
+    total_out = res[2];
 }
 
 template <int LEVEL>
-__global__ void __launch_bounds__(kThreads) k_sel_hist(const float* __restrict__ norms, int HW, const SelState* __restrict__ sel,
-                                                      uint32_t* __restrict__ hist) {
+__global__ void __launch_bounds__(kThreads) k_sel_hist(SelArgs a) {
     const int t = blockIdx.y;
-    if (sel[t].n == 0) return;
-    const uint32_t n = sel[t].n_entries;
-    const uint32_t prefix = sel[t].prefix;
+    SelState& st = a.sel[t];
+    uint32_t n, prefix = 0;
+    if (LEVEL == 0) {
+        // norm slots written by pass A: 128 per listed unit (stride 1, gated-out / non-candidate slots hold -1) or one
+        // per selected candidate (stride > 1)
+        n = !a.ctl[t].enable ? 0u : a.stride > 1 ? (uint32_t)((a.wt_n[a.n_tracks + t] + a.stride - 1) / a.stride)
+                                                 : (uint32_t)a.wt_n[t] * 128u;
+        if (n == 0) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) { st.n = 0; st.n_entries = 0; }
+            return;
+        }
+    } else {
+        if (st.n == 0) return;
+        n = st.n_entries;
+        prefix = st.prefix;
+    }
     const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
-    const uint32_t lo = blockIdx.x * per;
-    if (lo >= n) return;
+    const uint32_t lo = min(n, blockIdx.x * per);
     const uint32_t hi = min(n, lo + per);
-    constexpr int NB = LEVEL == 2 ? 256 : kSelBins;
+    constexpr int NB = kSelBins;
     __shared__ uint32_t h[NB];
     for (int i = threadIdx.x; i < NB; i += kThreads) h[i] = 0;
     __syncthreads();
-    const uint32_t* keys = reinterpret_cast<const uint32_t*>(norms + (long long)t * HW);
+    const uint32_t* keys = reinterpret_cast<const uint32_t*>(a.norms + (long long)t * a.norm_stride);
     // 128-bit loads, two in flight per thread: a scalar loop keeps one 4-byte load in flight per thread, which is
     // ~10 % of the bytes in flight HBM3e needs (measured: 0.3 ms per pass instead of 0.06)
     auto count = [&](uint32_t key) {
         if (key >> 31) return;  // gated-out candidate
         if (LEVEL == 0) {
             atomicAdd(&h[key >> 20], 1u);
-        } else if (LEVEL == 1) {
-            if ((key >> 20) == (prefix >> 20)) atomicAdd(&h[(key >> 8) & 0xfffu], 1u);
         } else {
-            if ((key >> 8) == (prefix >> 8)) atomicAdd(&h[key & 0xffu], 1u);
+            if ((key >> 20) == (prefix >> 20)) atomicAdd(&h[(key >> 8) & 0xfffu], 1u);
         }
     };
     const uint4* keys4 = reinterpret_cast<const uint4*>(keys);
@@ -587,55 +647,27 @@ __global__ void __launch_bounds__(kThreads) k_sel_hist(const float* __restrict__
     if (hi4 >= lo4)
         for (uint32_t i = (hi4 << 2) + threadIdx.x; i < hi; i += kThreads) count(keys[i]);  // tail
     __syncthreads();
-    uint32_t* gh = hist + (long long)t * kSelBins;
+    uint32_t* gh = a.hist + (long long)t * kSelBins;
     for (int i = threadIdx.x; i < NB; i += kThreads)
         if (h[i]) atomicAdd(gh + i, h[i]);
-}
-
-template <int LEVEL>
-__global__ void __launch_bounds__(kThreads) k_sel_scan(SelState* __restrict__ sel, uint32_t* __restrict__ hist) {
-    const int t = blockIdx.x;
-    SelState& s = sel[t];
-    if (s.n == 0) return;
-    constexpr int NB = LEVEL == 2 ? 256 : kSelBins;
-    constexpr int PER = NB / kThreads;
-    __shared__ uint32_t sh[kThreads / 32];
-    uint32_t* gh = hist + (long long)t * kSelBins;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t loc[PER];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        loc[i] = gh[threadIdx.x * PER + i];
-        gh[threadIdx.x * PER + i] = 0;
-        sum += loc[i];
-    }
-    const uint32_t incl = (uint32_t)warp_scan_incl((int)sum, lane);
-    if (lane == 31) sh[warp] = incl;
-    __syncthreads();
-    uint32_t woff = 0, total = 0;
-    for (int w = 0; w < kThreads / 32; ++w) {
-        if (w < warp) woff += sh[w];
-        total += sh[w];
-    }
-    uint32_t before = woff + incl - sum;
-    // level 0 fixes the number of valid measurements and the rank of the upper median s[n/2]
-    const uint32_t k = LEVEL == 0 ? (total >> 1) : s.k;
-    __syncthreads();
-    if (LEVEL == 0) {
-        if (threadIdx.x == 0) s.n = total;
-        if (total == 0) return;
-    }
-    if (k >= before && k < before + sum) {  // exactly one thread
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            if (k < before + loc[i]) {
-                const uint32_t bin = threadIdx.x * PER + i;
-                s.prefix |= LEVEL == 0 ? bin << 20 : LEVEL == 1 ? bin << 8 : bin;
-                s.k = k - before;
-                break;
-            }
-            before += loc[i];
+    if (!last_block_of_track(a.ticket, t)) return;
+    // ---- last block of this track: locate the bin of the upper median s[n/2] ----
+    uint32_t bin, krem, total;
+    scan_bins<NB>(gh, LEVEL == 0 ? 0u : st.k, LEVEL == 0, bin, krem, total);
+    if (threadIdx.x == 0) {
+        if (LEVEL == 0) {
+            st.n = total;  // valid measurements
+            st.n_entries = n;
+            st.prefix = bin << 20;
+            st.k = krem;
+            st.pad2 = 0;
+            st.less_cnt = 0;
+            st.less_sum = 0.0;
+            st.total_sum = 0.0;
+            st.less_max_bits = 0;
+        } else {
+            st.prefix |= bin << 8;
+            st.k = krem;
         }
     }
 }
@@ -643,20 +675,26 @@ __global__ void __launch_bounds__(kThreads) k_sel_scan(SelState* __restrict__ se
 // Last pass over the norms, after two radix levels fixed the top 24 key bits of the upper median s[n/2]: histogram of
 // the low 8 bits of the keys inside that 24-bit bin (all keys with the same low bits are the SAME float, so counts are
 // enough to reconstruct sums there), and count / sum / max of everything below the bin, plus the grand total.
-__global__ void __launch_bounds__(kThreads) k_sel_l2stats(const float* __restrict__ norms, int HW, SelState* __restrict__ sel,
-                                                         uint32_t* __restrict__ hist) {
+__device__ void sel_finish_warp(int t, int lane, SelState* __restrict__ sel, uint32_t* __restrict__ hist,
+                                WeightParams* __restrict__ wp);
+
+__global__ void __launch_bounds__(kThreads) k_sel_l2stats(SelArgs a) {
     const int t = blockIdx.y;
-    if (sel[t].n == 0) return;
+    SelState* __restrict__ sel = a.sel;
+    uint32_t* __restrict__ hist = a.hist;
+    if (sel[t].n == 0) {  // nothing to weight: publish neutral parameters
+        if (blockIdx.x == 0 && threadIdx.x < 32) sel_finish_warp(t, threadIdx.x, sel, hist, a.wp);
+        return;
+    }
     const uint32_t n = sel[t].n_entries;
     const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
-    const uint32_t lo = blockIdx.x * per;
-    if (lo >= n) return;
+    const uint32_t lo = min(n, blockIdx.x * per);
     const uint32_t hi = min(n, lo + per);
     const uint32_t pbin = sel[t].prefix >> 8;
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t* keys = reinterpret_cast<const uint32_t*>(norms + (long long)t * (long long)HW);
+    const uint32_t* keys = reinterpret_cast<const uint32_t*>(a.norms + (long long)t * a.norm_stride);
     float tot = 0.f, ls = 0.f, lm = 0.f;  // per-thread FP32 partials (<= a few hundred terms), FP64 across threads
     unsigned lc = 0;
     auto visit = [&](uint32_t key) {
@@ -716,14 +754,26 @@ __global__ void __launch_bounds__(kThreads) k_sel_l2stats(const float* __restric
         atomicAdd(&sel[t].less_cnt, (unsigned long long)lc);
         atomicMax(&sel[t].less_max_bits, __float_as_uint(lm));
     }
+    if (!last_block_of_track(a.ticket, t)) return;
+    if (threadIdx.x < 32) sel_finish_warp(t, threadIdx.x, sel, hist, a.wp);
 }
 
-// one warp per track: finish the select from the 256-bin histogram and emit the Laplacian parameters
-__global__ void __launch_bounds__(32) k_sel_final(int n_tracks, SelState* __restrict__ sel, uint32_t* __restrict__ hist,
-                                                  WeightParams* __restrict__ wp) {
-    const int t = blockIdx.x;
-    const int lane = threadIdx.x;
-    SelState s = sel[t];
+// one warp per track (the last block of k_sel_l2stats to finish): complete the select from the 256-bin histogram and
+// emit the Laplacian parameters
+__device__ void sel_finish_warp(int t, int lane, SelState* __restrict__ sel, uint32_t* __restrict__ hist,
+                                WeightParams* __restrict__ wp) {
+    SelState s;  // read past L1: the statistics were accumulated by other blocks' atomics
+    {
+        const uint4* p = reinterpret_cast<const uint4*>(sel + t);
+        static_assert(sizeof(SelState) == 48, "SelState layout");
+        const uint4 q0 = __ldcg(p), q1 = __ldcg(p + 1), q2 = __ldcg(p + 2);
+        s.prefix = q0.x; s.k = q0.y; s.n = q0.z; s.n_entries = q0.w;
+        s.less_cnt = (unsigned long long)q1.x | ((unsigned long long)q1.y << 32);
+        s.less_sum = __hiloint2double((int)q1.w, (int)q1.z);
+        s.total_sum = __hiloint2double((int)q2.y, (int)q2.x);
+        s.less_max_bits = q2.z;
+        s.pad2 = 0;
+    }
     WeightParams w;
     w.m = 0.f;
     w.inv_b = 0.f;
@@ -739,7 +789,7 @@ __global__ void __launch_bounds__(32) k_sel_final(int n_tracks, SelState* __rest
         uint32_t sum = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            loc[i] = gh[lane * 8 + i];
+            loc[i] = __ldcg(gh + lane * 8 + i);
             gh[lane * 8 + i] = 0;
             sum += loc[i];
         }
@@ -802,45 +852,6 @@ __global__ void __launch_bounds__(32) k_sel_final(int n_tracks, SelState* __rest
     }
     if (lane == 0) wp[t] = w;
 }
-
-#if 0
-__global__ void k_sel_final(int n_tracks, const SelState* __restrict__ sel, WeightParams* __restrict__ wp) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tracks) return;
-    const SelState s = sel[t];
-    WeightParams w;
-    w.m = 0.f;
-    w.inv_b = 0.f;
-    w.coef = 0.f;
-    w.inv_lmax = 1.f;
-    w.use = 0;
-    w.n = (int32_t)s.n;
-    w.pad[0] = w.pad[1] = 0;
-    if (s.n > 0) {
-        // SKFCorrection.cpp:95-102: median (even: mean of the two middle values), b = mean |n - m|
-        const double n = (double)s.n;
-        const double k1 = (double)(s.n >> 1);
-        const double v1 = (double)__uint_as_float(s.prefix);
-        const double lower = (s.less_cnt == (unsigned long long)(s.n >> 1)) ? (double)__uint_as_float(s.less_max_bits) : v1;
-        const bool even = (s.n & 1u) == 0u;
-        const double m = even ? 0.5 * (lower + v1) : v1;
-        const double s_below = s.less_sum + (k1 - (double)s.less_cnt) * v1;  // sum of the k1 smallest
-        const double s_above = s.total_sum - s_below;
-        const double b = ((s_above - (n - k1) * m) + (k1 * m - s_below)) / n;
-        if (b > 1e-4) {  // SKFCorrection.cpp:106
-            const double dmin = even ? 0.5 * (v1 - lower) : 0.0;
-            const double lmax = fmax(exp(-dmin / b) / (2.0 * b), 1e-6);
-            w.m = (float)m;
-            w.inv_b = (float)(1.0 / b);
-            w.coef = (float)(1.0 / (2.0 * b));
-            w.inv_lmax = (float)(1.0 / lmax);
-            w.use = 1;
-        }
-    }
-    wp[t] = w;
-}
-
-#endif
 
 // ---- per-track epilogue: FP64 reduction of the block partials, 6x6 solve, gate, publish ------------
 // In-place Gauss-Jordan inverse of a symmetric positive definite 6x6 matrix held in shared memory
@@ -1049,15 +1060,14 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
             ROFTB_PASS(0, float, false);
         if (a.ev_first_pass) cudaEventRecord(a.ev_first_pass, s);
         if (a.prof) cudaEventRecord(a.prof[2], s);
-        ROFTB_LAUNCH(k_sel_init, (T + 127) / 128, 128, 0, s, T, a.wt_n, g.stride, a.sel, a.ctl);
         // enough blocks per track to spread the list, few enough that the per-block histogram flush stays cheap
         int sb = max(1, min(32, (148 * 8 + T - 1) / T));
-        ROFTB_LAUNCH(k_sel_hist<0>, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel, a.hist);
-        ROFTB_LAUNCH(k_sel_scan<0>, T, kThreads, 0, s, a.sel, a.hist);
-        ROFTB_LAUNCH(k_sel_hist<1>, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel, a.hist);
-        ROFTB_LAUNCH(k_sel_scan<1>, T, kThreads, 0, s, a.sel, a.hist);
-        ROFTB_LAUNCH(k_sel_l2stats, dim3(sb, T), kThreads, 0, s, a.norms, (int)pa.norm_stride, a.sel, a.hist);
-        ROFTB_LAUNCH(k_sel_final, T, 32, 0, s, T, a.sel, a.hist, a.wp);
+        SelArgs sa;
+        sa.norms = a.norms; sa.norm_stride = pa.norm_stride; sa.sel = a.sel; sa.hist = a.hist; sa.ticket = a.norm_count;
+        sa.ctl = a.ctl; sa.wt_n = a.wt_n; sa.n_tracks = T; sa.stride = g.stride; sa.wp = a.wp;
+        ROFTB_LAUNCH(k_sel_hist<0>, dim3(sb, T), kThreads, 0, s, sa);
+        ROFTB_LAUNCH(k_sel_hist<1>, dim3(sb, T), kThreads, 0, s, sa);
+        ROFTB_LAUNCH(k_sel_l2stats, dim3(sb, T), kThreads, 0, s, sa);
     } else if (a.prof) {
         cudaEventRecord(a.prof[2], s);
     }

@@ -20,8 +20,9 @@ using namespace roftb;
 namespace {
 
 std::string g_create_error;
-constexpr int kCtlRing = 8;    // in-flight per-step control blocks
-constexpr int kHistRing = 16;  // velocity history ring (> ROFTB_MAX_DELAY + 3)
+constexpr int kCtlRing = 16;   // in-flight per-step control blocks
+constexpr int kHistRing = 32;  // velocity history ring (> ROFTB_MAX_DELAY + 3 + kUkfLag)
+constexpr int kUkfLag = 10;    // steps the pose UKF stream may trail the streaming kernels (absorbs the re-sync replay burst)
 
 struct PoseMeasHost {          // CartesianQuaternionMeasurement state (.h:98-140), values replaced by slots
     std::deque<int> buffer;    // buffer_velocities_ as velocity-history slots
@@ -54,8 +55,8 @@ struct roftb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr, prep_stream = nullptr;
     cudaEvent_t prep_event[2] = {nullptr, nullptr}, pass_a_event = nullptr;
     bool pass_a_event_used = false;
-    cudaEvent_t vel_event[8], ukf_event[8], join_event = nullptr, plan_event = nullptr, mask_event = nullptr;
-    bool ukf_event_used[8];
+    cudaEvent_t vel_event[kCtlRing], ukf_event[kCtlRing], join_event = nullptr, plan_event = nullptr, mask_event = nullptr;
+    bool ukf_event_used[kCtlRing];
     bool mask_event_used = false;
     std::string err;
     long long launches0 = 0;
@@ -686,9 +687,10 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
     CK(cudaMemcpyAsync(d_ops, ops, sizeof(UkfOp) * T * kMaxUkfOps, cudaMemcpyHostToDevice, ctx->ukf_stream));
     CK(cudaMemcpyAsync(d_nops, nops, sizeof(int32_t) * T, cudaMemcpyHostToDevice, ctx->ukf_stream));
     CK(cudaEventRecord(ctx->ctl_event[cslot], s));
-    // the pose UKF trails on its own stream; keep it within 4 steps of the streaming kernels (velocity-history ring)
+    // the pose UKF trails on its own stream; keep it within kUkfLag steps of the streaming kernels (velocity-history
+    // ring): a pose re-sync replays pose_delay + 1 predict/correct pairs in one step, which the slack spreads out
     {
-        const int lag = (cslot + kCtlRing - 4) % kCtlRing;
+        const int lag = (cslot + kCtlRing - kUkfLag) % kCtlRing;
         if (ctx->ukf_event_used[lag]) CK(cudaStreamWaitEvent(s, ctx->ukf_event[lag], 0));
     }
     ctx->ctl_event_used[cslot] = true;
