@@ -28,6 +28,7 @@ namespace roftb {
 namespace {
 
 __device__ __forceinline__ float4 get4(const float4* p, bool ok) { return ok ? ld_nc_f4(p) : make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
 // ---- per-warp-tile counts of selected candidates (only needed when stride > 1 or for ordered output) ----
@@ -267,15 +268,25 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
     const int n_list = a.wt_n[t];
     const int32_t* list = a.wt_list + (long long)t * a.n_units;
     const int32_t* prefix = a.wt_prefix + (long long)t * a.n_units;
-    // each warp iteration takes four consecutive list entries (units of 128 px, one quad per lane each)
+    // each warp iteration takes four consecutive list entries (units of 128 px, one quad per lane each).
+    // The dependent chain list -> unit id -> mask word -> depth / flow / norm loads would cost three exposed memory
+    // latencies per group (a quarter of all stall samples in the ncu capture): unit ids are fetched two groups ahead
+    // by lanes 0..3, and every line the NEXT group will touch is pulled into L2 (prefetch.global.L2: no registers)
+    // while the current group is processed, so the chain only ever sees L2-hit latency.
+    const int gstep = gridDim.x * (kThreads / 32) * 4;
+    const int g_first = (blockIdx.x * (kThreads / 32) + warp) * 4;
+    const bool reuse = PASS == 1 && a.reuse_norms;
+    const float4* nq4 = reinterpret_cast<const float4*>(norms_t);
+    int my_unit = -1, my_rank = 0, nx_unit = -1, nx2_unit = -1;
+    if (lane < 4) {
+        if (g_first + lane < n_list) my_unit = list[g_first + lane];
+        if (g_first + gstep + lane < n_list) nx_unit = list[g_first + gstep + lane];
+    }
 #pragma unroll 1
-    for (int g0 = (blockIdx.x * (kThreads / 32) + warp) * 4; g0 < n_list; g0 += gridDim.x * (kThreads / 32) * 4) {
-        // lanes 0..3 fetch the unit ids and their rank bases; broadcast by shuffle inside the rolled loop
-        int my_unit = -1, my_rank = 0;
-        if (lane < 4 && g0 + lane < n_list) {
-            my_unit = list[g0 + lane];
-            my_rank = prefix[my_unit];
-        }
+    for (int g0 = g_first; g0 < n_list; g0 += gstep) {
+        // lanes 0..3 hold the unit ids (and rank bases); broadcast by shuffle inside the rolled loop
+        if (lane < 4 && g0 + 2 * gstep + lane < n_list) nx2_unit = list[g0 + 2 * gstep + lane];
+        if (g.stride > 1 && my_unit >= 0) my_rank = prefix[my_unit];
         // candidate bits of this lane's quad in each unit: bit (4j + i); scs: non-zero pixels to propagate
         uint32_t sel = 0, scs = 0;
 #pragma unroll
@@ -293,12 +304,26 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
         if (!c.enable) sel = 0;
         if (!do_sc) scs = 0;
         const uint32_t need = sel | scs;
+        if (g0 + gstep < n_list) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int unit = __shfl_sync(0xffffffffu, nx_unit, j);
+                const int q = unit * 32 + lane;
+                if (unit >= 0 && q < nq) {
+                    prefetch_l2(mq + q);
+                    prefetch_l2(dq + q);
+                    if (FAST) {
+                        prefetch_l2(fq + 2 * q);
+                        prefetch_l2(fq + 2 * q + 1);
+                    }
+                    if (reuse) prefetch_l2(nq4 + (g0 + gstep + j) * 32 + lane);
+                }
+            }
+        }
 
         // software pipeline over the four units: loads of unit j+1 are issued before unit j is processed
         float4 Dc, F0c, F1c, Dn, F0n, F1n;
         float4 Nc = make_float4(-1.f, -1.f, -1.f, -1.f), Nn = Nc;  // pass B: norms of pass A (negative: not a valid measurement)
-        const bool reuse = PASS == 1 && a.reuse_norms;
-        const float4* nq4 = reinterpret_cast<const float4*>(norms_t);
         {
             const int q = __shfl_sync(0xffffffffu, my_unit, 0) * 32 + lane;
             if (reuse) Nc = get4(nq4 + g0 * 32 + lane, (sel & 0xfu) != 0u);
@@ -497,6 +522,9 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
             F1c = F1n;
             Nc = Nn;
         }
+        my_unit = nx_unit;
+        nx_unit = nx2_unit;
+        nx2_unit = -1;
     }
 
     if (kPacked) {
