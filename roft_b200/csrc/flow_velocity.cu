@@ -1074,12 +1074,13 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     pa.winner = a.winner;
     const bool fast = (!g.flow_s16 && g.grid == 1 && g.scale_mode == 0);
     const bool fuse = a.fuse_scatter != 0;  // the first streaming pass also propagates the mask
+    cudaStream_t ps = s;                    // stream the ROFTB_PASS launches go to
 #define ROFTB_PASS(PASS, AT, SC)                                                                          \
     do {                                                                                                  \
         if (fast)                                                                                         \
-            ROFTB_LAUNCH((k_flow_pass<PASS, true, AT, SC>), dim3(bpt, T), kThreads, 0, s, pa);            \
+            ROFTB_LAUNCH((k_flow_pass<PASS, true, AT, SC>), dim3(bpt, T), kThreads, 0, ps, pa);           \
         else                                                                                              \
-            ROFTB_LAUNCH((k_flow_pass<PASS, false, AT, SC>), dim3(bpt, T), kThreads, 0, s, pa);           \
+            ROFTB_LAUNCH((k_flow_pass<PASS, false, AT, SC>), dim3(bpt, T), kThreads, 0, ps, pa);          \
     } while (0)
     if (a.weight_flow) {
         if (fuse)
@@ -1111,11 +1112,21 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
         pa.auto_threshold = kAutoFp64Candidates;
         pa.auto_take_small = 1;
     }
+    // auto: the FP64 launch only has the few small tracks to do (tens of microseconds of a mostly idle GPU) - it runs
+    // on the auxiliary stream beside the FP32 launch (disjoint tracks, disjoint partial slots)
+    const bool side = a.accum_fp64 == 2 && a.aux_stream && !fuse_b;
     if (a.accum_fp64 >= 1) {
+        if (side) {
+            cudaEventRecord(a.aux_fork, s);
+            cudaStreamWaitEvent(a.aux_stream, a.aux_fork, 0);
+            ps = a.aux_stream;
+        }
         if (fuse_b)
             ROFTB_PASS(1, double, true);
         else
             ROFTB_PASS(1, double, false);
+        if (side) cudaEventRecord(a.aux_join, a.aux_stream);
+        ps = s;
     }
     if (a.accum_fp64 == 2) pa.auto_take_small = 0;
     if (a.accum_fp64 != 1) {
@@ -1125,6 +1136,7 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
             ROFTB_PASS(1, float, false);
     }
 #undef ROFTB_PASS
+    if (side) cudaStreamWaitEvent(s, a.aux_join, 0);
     if (a.ev_first_pass && !a.weight_flow) cudaEventRecord(a.ev_first_pass, s);
     if (a.prof) cudaEventRecord(a.prof[4], s);
     EpiArgs e;

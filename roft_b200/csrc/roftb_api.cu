@@ -52,7 +52,9 @@ struct roftb_ctx {
     size_t HW = 0;
     size_t flow_elems = 0;  // scalar elements per track
     int dev = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr, prep_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr, prep_stream = nullptr,
+                 aux_stream = nullptr;
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     cudaEvent_t prep_event[2] = {nullptr, nullptr}, pass_a_event = nullptr;
     bool pass_a_event_used = false;
     cudaEvent_t vel_event[kCtlRing], ukf_event[kCtlRing], join_event = nullptr, plan_event = nullptr, mask_event = nullptr;
@@ -271,6 +273,9 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(cudaEventCreateWithFlags(&ctx->join_event, cudaEventDisableTiming));
     CKC(cudaStreamCreateWithFlags(&ctx->mask_stream, cudaStreamNonBlocking));
     CKC(cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->prep_event[0], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->prep_event[1], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->pass_a_event, cudaEventDisableTiming));
@@ -374,6 +379,9 @@ void roftb_destroy(roftb_ctx* ctx) {
     if (ctx->mask_event) cudaEventDestroy(ctx->mask_event);
     if (ctx->mask_stream) { cudaStreamSynchronize(ctx->mask_stream); cudaStreamDestroy(ctx->mask_stream); }
     if (ctx->prep_stream) { cudaStreamSynchronize(ctx->prep_stream); cudaStreamDestroy(ctx->prep_stream); }
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+    if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
     for (int i = 0; i < 2; ++i)
         if (ctx->prep_event[i]) cudaEventDestroy(ctx->prep_event[i]);
     if (ctx->pass_a_event) cudaEventDestroy(ctx->pass_a_event);
@@ -766,6 +774,7 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
         a.fuse_scatter = 1; a.plan = plan; a.state_dst = seg_next; a.winner = ctx->winner;
         a.prof = pe;
         a.ev_first_pass = ctx->pass_a_event;
+        a.aux_stream = ctx->aux_stream; a.aux_fork = ctx->aux_fork; a.aux_join = ctx->aux_join;
         ctx->pass_a_event_used = true;
         if (launch_velocity(a, s)) return fail(ctx, "launch_velocity failed");
         CK(cudaEventRecord(ctx->vel_event[cslot], s));

@@ -184,6 +184,8 @@ struct VelocityArgs {
     int32_t* out_count; double* out_lambda; double* out_eta;  // device [T], [T][36], [T][6]
     // fused mask propagation (see WarpPlan::fused)
     int fuse_scatter; const WarpPlan* plan; uint8_t* state_dst; int32_t* winner;
+    cudaStream_t aux_stream;           // optional: the FP64 small-track variant of pass B runs here, beside the FP32 one
+    cudaEvent_t aux_fork, aux_join;
     cudaEvent_t ev_first_pass;         // optional: recorded right after the first streaming pass (the one that also
                                        // propagates the mask): the next step's worklist may be built from then on
     cudaEvent_t* prof;                 // optional: 6 events recorded at the phase boundaries (start, rank, pass A,

@@ -90,6 +90,18 @@ __device__ void jacobi_warp(UkfSmem& s, int n, int lane) {
     const int ne = n + (n & 1);  // players (a dummy index n sits out when n is odd)
     const int np = ne >> 1;      // pairs per round
     const int nr = ne - 1;       // rounds per sweep
+    // work items of this lane in the update phases (n * np <= 72 items: at most three per lane), fixed for the call
+    int ck[3], cj[3], rj[3], rk[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int e = lane + 32 * i;
+        const bool on = e < n * np;
+        ck[i] = on ? e / np : -1;  // column phase: row k, pair j
+        cj[i] = on ? e % np : 0;
+        rj[i] = on ? e / n : -1;   // row phase: pair j, column k
+        rk[i] = on ? e % n : 0;
+    }
+    constexpr double kTol2 = kJacobiRelTol * kJacobiRelTol;
     for (int sweep = 0; sweep < kJacobiMaxSweeps; ++sweep) {
         bool rotated = false;
         for (int r = 0; r < nr; ++r) {
@@ -98,17 +110,23 @@ __device__ void jacobi_warp(UkfSmem& s, int n, int lane) {
             double c = 1.0, sn = 0.0;
             bool rot = false;
             if (lane < np) {
-                int a = lane == 0 ? r : (r + lane) % nr;
-                int b = lane == 0 ? ne - 1 : (r - lane + nr) % nr;
+                int a = r + lane;
+                a = a >= nr ? a - nr : a;
+                int b = r - lane;
+                b = b < 0 ? b + nr : b;
+                if (lane == 0) b = ne - 1;
                 p = min(a, b);
                 q = max(a, b);
                 if (q < n) {
                     const double apq = s.A[p][q], app = s.A[p][p], aqq = s.A[q][q];
-                    if (fabs(apq) > kJacobiRelTol * sqrt(fabs(app * aqq))) {
+                    // |apq| > tol * sqrt(|app aqq|), squared (no square root on the critical path)
+                    if (apq * apq > kTol2 * fabs(app * aqq)) {
                         rot = true;
-                        const double theta = (aqq - app) / (2.0 * apq);
-                        const double tt = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                        c = 1.0 / sqrt(tt * tt + 1.0);
+                        // t = sign(theta) / (|theta| + sqrt(theta^2 + 1)) with theta = (aqq - app) / (2 apq), written
+                        // with one square root and one division
+                        const double al = aqq - app, be = 2.0 * apq;
+                        const double tt = copysign(fabs(be), al * be) / (fabs(al) + sqrt(al * al + be * be));
+                        c = rsqrt(tt * tt + 1.0);
                         sn = tt * c;
                     }
                 }
@@ -123,27 +141,31 @@ __device__ void jacobi_warp(UkfSmem& s, int n, int lane) {
                 s.jq[lane] = q;
             }
             __syncwarp();
-            for (int e = lane; e < n * np; e += 32) {  // columns p, q of A and V
-                const int k = e / np, j = e - k * np;
-                const int pj = s.jp[j], qj = s.jq[j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {  // columns p, q of A and V
+                const int k = ck[i];
+                if (k < 0) continue;
+                const int pj = s.jp[cj[i]], qj = s.jq[cj[i]];
                 if (pj < 0) continue;
-                const double cj = s.jc[j], sj = s.js[j];
+                const double cc = s.jc[cj[i]], ss = s.js[cj[i]];
                 const double akp = s.A[k][pj], akq = s.A[k][qj];
-                s.A[k][pj] = cj * akp - sj * akq;
-                s.A[k][qj] = sj * akp + cj * akq;
                 const double vkp = s.V[k][pj], vkq = s.V[k][qj];
-                s.V[k][pj] = cj * vkp - sj * vkq;
-                s.V[k][qj] = sj * vkp + cj * vkq;
+                s.A[k][pj] = cc * akp - ss * akq;
+                s.A[k][qj] = ss * akp + cc * akq;
+                s.V[k][pj] = cc * vkp - ss * vkq;
+                s.V[k][qj] = ss * vkp + cc * vkq;
             }
             __syncwarp();
-            for (int e = lane; e < n * np; e += 32) {  // rows p, q of A
-                const int j = e / n, k = e - j * n;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {  // rows p, q of A
+                const int j = rj[i];
+                if (j < 0) continue;
                 const int pj = s.jp[j], qj = s.jq[j];
                 if (pj < 0) continue;
-                const double cj = s.jc[j], sj = s.js[j];
-                const double apk = s.A[pj][k], aqk = s.A[qj][k];
-                s.A[pj][k] = cj * apk - sj * aqk;
-                s.A[qj][k] = sj * apk + cj * aqk;
+                const double cc = s.jc[j], ss = s.js[j];
+                const double apk = s.A[pj][rk[i]], aqk = s.A[qj][rk[i]];
+                s.A[pj][rk[i]] = cc * apk - ss * aqk;
+                s.A[qj][rk[i]] = ss * apk + cc * aqk;
             }
             __syncwarp();
             if (rot) {
