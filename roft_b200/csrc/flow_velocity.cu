@@ -243,6 +243,9 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
     uint8_t* dst_t = SCATTER ? a.state_dst + (long long)t * g.HW : nullptr;
     float* norms_t = a.norms + (long long)t * a.norm_stride;
     const float inv_fx = g.inv_fx, max_d = g.max_depth_f;
+    const float inv_w = 1.0f / (float)g.W, Wf = (float)g.W, Hf = (float)g.H;
+    const bool small_hw = g.HW < (1 << 24);
+    const unsigned sc_bias = 0x4b000000u * (uW + 1u);  // see the scatter index below
 
     // predicted velocity (F = I: the predicted mean is the previous corrected mean) and FP32 row scales
     float x[6];
@@ -322,20 +325,21 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
         }
 
         // software pipeline over the four units: loads of unit j+1 are issued before unit j is processed
-        float4 Dc, F0c, F1c, Dn, F0n, F1n;
-        float4 Nc = make_float4(-1.f, -1.f, -1.f, -1.f), Nn = Nc;  // pass B: norms of pass A (negative: not a valid measurement)
+        // (two register sets used alternately - the rolled loop below runs two units per trip - so no copies)
+        float4 DA, F0A, F1A, DB, F0B, F1B;
+        float4 NA = make_float4(-1.f, -1.f, -1.f, -1.f), NB = NA;  // pass B: norms of pass A (negative: not a valid measurement)
         {
             const int q = __shfl_sync(0xffffffffu, my_unit, 0) * 32 + lane;
-            if (reuse) Nc = get4(nq4 + g0 * 32 + lane, (sel & 0xfu) != 0u);
-            Dc = get4(dq + q, (sel & 0xfu) != 0u);
+            if (reuse) NA = get4(nq4 + g0 * 32 + lane, (sel & 0xfu) != 0u);
+            DA = get4(dq + q, (sel & 0xfu) != 0u);
             if (FAST) {
                 const bool on = (need & 0xfu) != 0u;
-                F0c = get4(fq + 2 * q, on);
-                F1c = get4(fq + 2 * q + 1, on);
+                F0A = get4(fq + 2 * q, on);
+                F1A = get4(fq + 2 * q + 1, on);
             }
         }
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
+        auto unit_step = [&](const int j, const float4& Dc, const float4& F0c, const float4& F1c, const float4& Nc, float4& Dn,
+                             float4& F0n, float4& F1n, float4& Nn) -> bool {
             if (j < 3) {
                 const int qn = __shfl_sync(0xffffffffu, my_unit, j + 1) * 32 + lane;
                 if (reuse) Nn = get4(nq4 + (g0 + j + 1) * 32 + lane, ((sel >> (4 * (j + 1))) & 0xfu) != 0u);
@@ -347,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
                 }
             }
             const int unit = __shfl_sync(0xffffffffu, my_unit, j);
-            if (unit < 0) break;  // warp-uniform: past the end of the list
+            if (unit < 0) return false;  // warp-uniform: past the end of the list
             uint32_t nib = (sel >> (4 * j)) & 0xfu;
             const uint32_t snib = (scs >> (4 * j)) & 0xfu;
             int nslot = 0;  // stride > 1: compact norm slot of this lane's first selected candidate
@@ -370,9 +374,19 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
             float4 nv = make_float4(-1.f, -1.f, -1.f, -1.f);  // pass A: norms of this quad (-1: not a valid measurement)
             if ((nib | snib) != 0u) {
                 const int px = (unit * 32 + lane) << 2;
-                const int v = px / W;
-                const int u0 = px - v * W;
-                const float vf = (float)v;
+                // row / column of the quad: reciprocal multiply with a +-1 fix-up (exact for HW < 2^24; a 32-bit integer
+                // division is ~35 instructions per quad)
+                int v, u0;
+                if (small_hw) {
+                    v = (int)((float)px * inv_w);
+                    u0 = px - v * W;
+                    if (u0 < 0) { u0 += W; --v; }
+                    if (u0 >= W) { u0 -= W; ++v; }
+                } else {
+                    v = px / W;
+                    u0 = px - v * W;
+                }
+                const float vf = (float)v, u0f = (float)u0;
                 float yh, xh0;
                 double yhd = 0.0, xh0d = 0.0;
                 if (PASS == 1) {
@@ -384,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
                 } else {
                     // pass A only feeds the Laplacian weights: FP32 coordinates are plenty
                     yh = (vf - g.cy) * g.inv_fy;
-                    xh0 = ((float)u0 - g.cx) * inv_fx;
+                    xh0 = (u0f - g.cx) * inv_fx;
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -407,10 +421,15 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
                         // hpp:249-278 for a single flow: the source pixel is inside the frame and its flow element is the
                         // one just fetched; IEEE adds; C truncation (a NaN would convert to 0 on the GPU, so it is tested;
                         // +-inf / huge values saturate outside the frame exactly like x86's INT_MIN)
-                        const float tx = __fadd_rn((float)(u0 + i), dx), ty = __fadd_rn(vf, dy);
-                        const unsigned ix = (unsigned)(int)tx, iy = (unsigned)(int)ty;
-                        const bool ok = ((snib >> i) & 1u) && tx == tx && ty == ty && ix < uW && iy < uH;
-                        if (ok) dst_t[iy * uW + ix] = sc_val;
+                        // In-frame test on the floats: (int)t in [0, n) <=> -1 < t < n (truncation; NaN fails both).
+                        // trunc(max(t, 0)) without the conversion pipe: t + 2^23 rounded toward zero keeps floor(t) in the
+                        // mantissa, so the float bits are 0x4b000000 + floor(t); the bias of both terms is folded into one
+                        // constant (arithmetic mod 2^32).
+                        const float tx = __fadd_rn(u0f + (float)i, dx), ty = __fadd_rn(vf, dy);
+                        const bool ok = ((snib >> i) & 1u) && tx > -1.0f && tx < Wf && ty > -1.0f && ty < Hf;
+                        const unsigned bx = __float_as_uint(__fadd_rz(fmaxf(tx, 0.0f), 8388608.0f));
+                        const unsigned by = __float_as_uint(__fadd_rz(fmaxf(ty, 0.0f), 8388608.0f));
+                        if (ok) dst_t[by * uW + bx - sc_bias] = sc_val;
                     }
                     const float d = comp(Dc, i);
                     const float xh = fmaf((float)i, inv_fx, xh0);
@@ -517,10 +536,12 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
             }
             // pass A, stride 1: position-addressed norm slots, one coalesced 128-bit store per lane
             if (PASS == 0 && g.stride == 1) reinterpret_cast<float4*>(norms_t)[(g0 + j) * 32 + lane] = nv;
-            Dc = Dn;
-            F0c = F0n;
-            F1c = F1n;
-            Nc = Nn;
+            return true;
+        };
+#pragma unroll 1
+        for (int j = 0; j < 4; j += 2) {
+            if (!unit_step(j, DA, F0A, F1A, NA, DB, F0B, F1B, NB)) break;
+            if (!unit_step(j + 1, DB, F0B, F1B, NB, DA, F0A, F1A, NA)) break;
         }
         my_unit = nx_unit;
         nx_unit = nx2_unit;

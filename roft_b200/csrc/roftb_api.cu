@@ -267,13 +267,20 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
         }                                                                      \
     } while (0)
     CKC(cudaSetDevice(ctx->dev));
-    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&ctx->ukf_stream, cudaStreamNonBlocking));
+    // the velocity chain (pass A -> select -> pass B -> epilogue) is the critical path of a step: its blocks are
+    // dispatched first; mask / worklist preparation next; the latency-bound pose UKF fills what is left
+    int prio_lo = 0, prio_hi = 0;
+    CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // numerically lower = higher priority
+    const int prio_mid = prio_hi;  // (a lower priority for the mask chain delays the next step's worklist: measured slower)
+    const char* env_prio = getenv("ROFTB_STREAM_PRIORITIES");
+    if (env_prio && env_prio[0] == '0') prio_lo = prio_hi;  // diagnostic: all streams equal
+    CKC(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
+    CKC(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi));
+    CKC(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, env_prio && env_prio[0] == '0' ? prio_hi : prio_mid));
+    CKC(cudaStreamCreateWithPriority(&ctx->ukf_stream, cudaStreamNonBlocking, prio_lo));
     CKC(cudaEventCreateWithFlags(&ctx->join_event, cudaEventDisableTiming));
-    CKC(cudaStreamCreateWithFlags(&ctx->mask_stream, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&ctx->prep_stream, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithPriority(&ctx->mask_stream, cudaStreamNonBlocking, env_prio && env_prio[0] == '0' ? prio_hi : prio_mid));
+    CKC(cudaStreamCreateWithPriority(&ctx->prep_stream, cudaStreamNonBlocking, env_prio && env_prio[0] == '0' ? prio_hi : prio_mid));
     CKC(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->prep_event[0], cudaEventDisableTiming));
