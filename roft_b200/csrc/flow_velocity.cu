@@ -572,6 +572,279 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass(PassA
     }
 }
 
+// ---- the streaming pass, TMA-staged ------------------------------------------------------------
+// Same arithmetic as k_flow_pass<.., FAST = true, float, ..> at stride 1 with Laplacian weighting, but the operands
+// reach the SM through the bulk-copy engine instead of through registers: every warp owns a ring of kRingStages
+// shared-memory stages, one 128-px unit each (depth 512 B | flow 1 KiB | mask 128 B in pass A, pass-A norms 512 B in
+// pass B).  Three lanes issue one cp.async.bulk each per unit (completion on the stage's mbarrier), kRingStages units
+// ahead of the one being processed, so each warp keeps ~6-8 KB in flight without holding a single register for it -
+// the register-prefetch version above has 1.5-2 KB per warp in flight and was latency-bound (DRAM 45 % / 31 %, issue
+// 65 % / 54 %).  A warp takes a CONTIGUOUS chunk of its track's unit list; norm slots stay addressed by list position.
+constexpr int kRingStages = 4;
+template <int PASS>
+struct RingLayout {
+    static constexpr int kD = 0, kF = 512, kX = 1536;             // X: mask (pass A) / norms (pass B)
+    static constexpr int kStage = kX + (PASS == 0 ? 128 : 512);  // bytes per stage (multiple of 16)
+    static constexpr int kSmem = (kThreads / 32) * kRingStages * (kStage + 8);
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <int PASS, bool SCATTER>
+__global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass_ring(PassArgs a) {
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+    using L = RingLayout<PASS>;
+    const int t = blockIdx.y;
+    const VelCtl c = a.ctl[t];
+    bool do_sc = false;
+    uint8_t sc_val = 0;
+    if (SCATTER) {
+        const WarpPlan& p = a.plan[t];
+        do_sc = p.fused != 0;
+        sc_val = (uint8_t)p.uniform_val;
+    }
+    if (!c.enable && !do_sc) return;
+    if (PASS == 1) {
+        if (!c.enable) return;
+        if (a.auto_threshold >= 0) {
+            const bool small = a.wt_n[gridDim.y + t] < a.auto_threshold;
+            if (small != (a.auto_take_small != 0)) return;  // the FP64 variant handles this track
+        }
+    }
+    const Geom& g = a.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const char* mask_t = reinterpret_cast<const char*>(a.seg + (long long)t * a.seg_stride);
+    const char* depth_t = reinterpret_cast<const char*>(a.ft.depth[c.prev_slot] + (long long)t * a.ft.depth_stride);
+    const char* flow_t = reinterpret_cast<const char*>(a.ft.flow[c.cur_slot]) + (long long)t * a.ft.flow_stride * 4;
+    float* norms_t = a.norms + (long long)t * a.norm_stride;
+    const int HW = g.HW, W = g.W;
+    const unsigned uW = (unsigned)g.W;
+    uint8_t* dst_t = SCATTER ? a.state_dst + (long long)t * g.HW : nullptr;
+    const float inv_fx = g.inv_fx, max_d = g.max_depth_f;
+    const float inv_w = 1.0f / (float)g.W, Wf = (float)g.W, Hf = (float)g.H;
+    const bool small_hw = g.HW < (1 << 24);
+    const unsigned sc_bias = 0x4b000000u * (uW + 1u);
+    const uint32_t thr4 = (uint32_t)a.thr * 0x01010101u;
+
+    float x[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = (float)a.x_pred[(long long)t * a.x_stride + i];
+    const float c1 = (float)(a.fx * c.dt), c2 = (float)(a.fy * c.dt);
+    WeightParams wp;
+    wp.use = 0;
+    if (PASS == 1) wp = a.wp[t];
+    float2 acc2[PASS == 1 ? 20 : 1];
+    float cnt_acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < (PASS == 1 ? 20 : 1); ++i) acc2[i] = make_float2(0.f, 0.f);
+
+    // this warp's ring and barriers
+    unsigned char* my_ring = ring_smem + warp * kRingStages * L::kStage;
+    const uint32_t ring_s = smem_u32(my_ring);
+    const uint32_t bar_s = smem_u32(ring_smem + (kThreads / 32) * kRingStages * L::kStage) + warp * kRingStages * 8;
+    if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kRingStages; ++st) mbar_init(bar_s + 8 * st, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    // contiguous chunk of the track's list of non-empty units
+    const int n_list = a.wt_n[t];
+    const int n_warps = gridDim.x * (kThreads / 32);
+    const int chunk = (n_list + n_warps - 1) / n_warps;
+    const int k0 = (blockIdx.x * (kThreads / 32) + warp) * chunk;
+    const int cnt = max(0, min(n_list, k0 + chunk) - k0);
+    const int32_t* list = a.wt_list + (long long)t * a.n_units + k0;
+    // unit ids: two windows of 32 list entries, one per lane each, refilled a window ahead
+    int idsA = lane < cnt ? list[lane] : -1;
+    int idsB = 32 + lane < cnt ? list[32 + lane] : -1;
+    auto unit_of = [&](int k) { return __shfl_sync(0xffffffffu, (k & 32) ? idsB : idsA, k & 31); };
+    auto issue = [&](int kp) {
+        const int unit = unit_of(kp);
+        const int st = kp % kRingStages;
+        const uint32_t dst = ring_s + st * L::kStage, bar = bar_s + 8 * st;
+        const long long px0 = (long long)unit * kUnitPx;
+        const uint32_t npx = (uint32_t)min(kUnitPx, HW - unit * kUnitPx);  // multiple of 16 (checked by the launcher)
+        const uint32_t xbytes = PASS == 0 ? npx : (uint32_t)kUnitPx * 4u;
+        if (lane == 0) mbar_expect_tx(bar, npx * 12u + xbytes);
+        __syncwarp();
+        if (lane < 3) {
+            const char* src = lane == 0 ? depth_t + px0 * 4 : lane == 1 ? flow_t + px0 * 8
+                              : PASS == 0 ? mask_t + px0 : reinterpret_cast<const char*>(norms_t + (long long)(k0 + kp) * kUnitPx);
+            const uint32_t off = lane == 0 ? L::kD : lane == 1 ? L::kF : L::kX;
+            const uint32_t bytes = lane == 0 ? npx * 4u : lane == 1 ? npx * 8u : xbytes;
+            bulk_g2s(dst + off, src, bytes, bar);
+        }
+    };
+#pragma unroll 1
+    for (int kp = 0; kp < min(kRingStages, cnt); ++kp) issue(kp);
+
+#pragma unroll 1
+    for (int k = 0; k < cnt; ++k) {
+        if ((k & 31) == 0 && k > 0) {  // the window that just ran out gets the entries two windows ahead
+            const int v = k + 32 + lane < cnt ? list[k + 32 + lane] : -1;
+            if (k & 32) idsA = v; else idsB = v;
+        }
+        const int st = k % kRingStages;
+        mbar_wait(bar_s + 8 * st, (uint32_t)(k / kRingStages) & 1u);
+        const unsigned char* sp = my_ring + st * L::kStage;
+        const float4 Dc = *reinterpret_cast<const float4*>(sp + L::kD + lane * 16);
+        const float4 F0c = *reinterpret_cast<const float4*>(sp + L::kF + lane * 32);
+        const float4 F1c = *reinterpret_cast<const float4*>(sp + L::kF + lane * 32 + 16);
+        const int unit = unit_of(k);
+        const int q = unit * 32 + lane;
+        const bool in_plane = (q << 2) < HW;
+        uint32_t nib = 0, snib = 0;
+        float4 Nc = make_float4(-1.f, -1.f, -1.f, -1.f);
+        if (PASS == 0) {
+            const uint32_t m = in_plane ? *reinterpret_cast<const uint32_t*>(sp + L::kX + lane * 4) : 0u;
+            nib = c.enable ? nibble_of(__vcmpgtu4(m, thr4)) : 0u;
+            if (SCATTER && do_sc) {
+                snib = nibble_of(__vcmpne4(m, 0u));
+                if (q == 0) snib &= ~1u;  // mask_(0,0) = 0 (hpp:224)
+            }
+        } else {
+            Nc = *reinterpret_cast<const float4*>(sp + L::kX + lane * 16);
+            nib = in_plane ? ((Nc.x >= 0.f ? 1u : 0u) | (Nc.y >= 0.f ? 2u : 0u) | (Nc.z >= 0.f ? 4u : 0u) | (Nc.w >= 0.f ? 8u : 0u)) : 0u;
+        }
+        float4 nv = make_float4(-1.f, -1.f, -1.f, -1.f);
+        if ((nib | snib) != 0u) {
+            const int px = q << 2;
+            int v, u0;
+            if (small_hw) {
+                v = (int)((float)px * inv_w);
+                u0 = px - v * W;
+                if (u0 < 0) { u0 += W; --v; }
+                if (u0 >= W) { u0 -= W; ++v; }
+            } else {
+                v = px / W;
+                u0 = px - v * W;
+            }
+            const float vf = (float)v, u0f = (float)u0;
+            float yh, xh0;
+            if (PASS == 1) {
+                yh = (float)(((double)v - a.cyd) * a.inv_fyd);
+                xh0 = (float)(((double)u0 - a.cxd) * a.inv_fxd);
+            } else {
+                yh = (vf - g.cy) * g.inv_fy;
+                xh0 = (u0f - g.cx) * inv_fx;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool cand = (nib >> i) & 1u;
+                const float4 f = i < 2 ? F0c : F1c;
+                float dx = (i & 1) ? f.z : f.x;
+                float dy = (i & 1) ? f.w : f.y;
+                if (SCATTER) {
+                    const float tx = __fadd_rn(u0f + (float)i, dx), ty = __fadd_rn(vf, dy);
+                    const bool ok = ((snib >> i) & 1u) && tx > -1.0f && tx < Wf && ty > -1.0f && ty < Hf;
+                    const unsigned bx = __float_as_uint(__fadd_rz(fmaxf(tx, 0.0f), 8388608.0f));
+                    const unsigned by = __float_as_uint(__fadd_rz(fmaxf(ty, 0.0f), 8388608.0f));
+                    if (ok) dst_t[by * uW + bx - sc_bias] = sc_val;
+                }
+                const float d = comp(Dc, i);
+                const float xh = fmaf((float)i, inv_fx, xh0);
+                const float ia = rcp_approx(d);
+                float l1[5], l2[5];
+                l1[0] = ia; l1[1] = -xh * ia; l1[2] = -xh * yh; l1[3] = fmaf(xh, xh, 1.0f); l1[4] = -yh;
+                l2[0] = ia; l2[1] = -yh * ia; l2[2] = -fmaf(yh, yh, 1.0f); l2[3] = xh * yh; l2[4] = xh;
+                if (PASS == 0) {
+                    const bool valid = cand && fabsf(dx) < 1e9f && fabsf(dy) < 1e9f && d > 0.f && d < max_d;
+                    float2 pp = __fmul2_rn(make_float2(l1[0], l2[0]), make_float2(x[0], x[1]));
+                    pp = __ffma2_rn(make_float2(l1[1], l2[1]), make_float2(x[2], x[2]), pp);
+                    pp = __ffma2_rn(make_float2(l1[2], l2[2]), make_float2(x[3], x[3]), pp);
+                    pp = __ffma2_rn(make_float2(l1[3], l2[3]), make_float2(x[4], x[4]), pp);
+                    pp = __ffma2_rn(make_float2(l1[4], l2[4]), make_float2(x[5], x[5]), pp);
+                    const float2 nn = __ffma2_rn(make_float2(-c1, -c2), pp, make_float2(dx, dy));
+                    const float nr = sqrt_approx(fmaf(nn.x, nn.x, nn.y * nn.y));
+                    if (valid) {
+                        if (i == 0) nv.x = nr; else if (i == 1) nv.y = nr; else if (i == 2) nv.z = nr; else nv.w = nr;
+                    }
+                } else {
+                    const float nr = comp(Nc, i);
+                    const bool valid = cand;
+                    float l = 1.0f;
+                    if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
+                    l = valid ? l : 0.f;
+                    const float ias = valid ? ia : 0.f;
+                    dx = valid ? dx : 0.f;
+                    dy = valid ? dy : 0.f;
+                    const float2 e[5] = {make_float2(ias, ias), make_float2(-xh * ias, -yh * ias), make_float2(l1[2], l2[2]),
+                                         make_float2(l1[3], l2[3]), make_float2(l1[4], l2[4])};
+                    const float2 ll = make_float2(l, l);
+                    float2 w[5];
+#pragma unroll
+                    for (int kk = 0; kk < 5; ++kk) w[kk] = __fmul2_rn(ll, e[kk]);
+                    int o = 0;
+#pragma unroll
+                    for (int r = 0; r < 5; ++r)
+#pragma unroll
+                        for (int qq = r; qq < 5; ++qq) {
+                            acc2[o] = __ffma2_rn(w[r], e[qq], acc2[o]);
+                            ++o;
+                        }
+                    const float2 zz = make_float2(dx, dy);
+#pragma unroll
+                    for (int kk = 0; kk < 5; ++kk) acc2[15 + kk] = __ffma2_rn(w[kk], zz, acc2[15 + kk]);
+                    cnt_acc += valid ? 1.0f : 0.f;
+                }
+            }
+        }
+        if (PASS == 0 && c.enable) reinterpret_cast<float4*>(norms_t)[(long long)(k0 + k) * 32 + lane] = nv;
+        // every lane has consumed its part of the stage (the values above were used): hand it back to the copy engine
+        __syncwarp();
+        if (k + kRingStages < cnt) issue(k + kRingStages);
+    }
+
+    if (PASS == 1) {
+        double* out = a.partials + ((long long)t * a.max_blocks + blockIdx.x * (kThreads / 32) + warp) * kNAcc;
+#pragma unroll
+        for (int o = 0; o < 15; ++o) {
+            const float s1 = warp_sum(acc2[o].x), s2 = warp_sum(acc2[o].y);
+            if (lane == 0) {
+                out[o] = (double)s1;
+                out[15 + o] = (double)s2;
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 5; ++kk) {
+            const float s1 = warp_sum(acc2[15 + kk].x), s2 = warp_sum(acc2[15 + kk].y);
+            if (lane == 0) {
+                out[30 + kk] = (double)s1;
+                out[35 + kk] = (double)s2;
+            }
+        }
+        const float sc = warp_sum(cnt_acc);
+        if (lane == 0) out[40] = (double)sc;
+    }
+}
+
 // ---- exact radix select of the upper median + Laplacian parameters ---------------------------
 // The select runs as three data passes over the norm slots; the per-track bookkeeping that used to be separate
 // one-block kernels (init, scan of the histogram, final parameters) is done by the LAST block of each pass to finish
@@ -1061,6 +1334,10 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     // blocks per track: several waves over the machine in total; each warp walks the track's tile list with
     // a stride of (blocks x warps)
     int bpt = max(1, (148 * 16 + T - 1) / T);
+    {
+        static const int env_bpt = [] { const char* e = getenv("ROFTB_BPT"); return e ? atoi(e) : 0; }();
+        if (env_bpt > 0) bpt = env_bpt;  // tuning hook
+    }
     bpt = min(bpt, min(n_block_tiles, a.max_blocks / (kThreads / 32)));
 
     if (a.prof) cudaEventRecord(a.prof[1], s);
@@ -1103,15 +1380,36 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
         else                                                                                              \
             ROFTB_LAUNCH((k_flow_pass<PASS, false, AT, SC>), dim3(bpt, T), kThreads, 0, ps, pa);          \
     } while (0)
+    // TMA-staged variant of both passes for the common configuration (dense float2 flow, stride 1, weighting on)
+    static const int env_ring = [] { const char* e = getenv("ROFTB_RING"); return e ? atoi(e) : 1; }();
+    const bool ring = env_ring != 0 && fast && g.stride == 1 && a.weight_flow && (g.HW % 16) == 0;
+    if (ring) {
+        static bool attr_done = false;  // (per process; the attribute is per function)
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_flow_pass_ring<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingLayout<0>::kSmem);
+            cudaFuncSetAttribute(k_flow_pass_ring<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingLayout<0>::kSmem);
+            cudaFuncSetAttribute(k_flow_pass_ring<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RingLayout<1>::kSmem);
+            attr_done = true;
+        }
+    }
     if (a.weight_flow) {
-        if (fuse)
+        if (ring) {
+            if (fuse)
+                ROFTB_LAUNCH((k_flow_pass_ring<0, true>), dim3(bpt, T), kThreads, RingLayout<0>::kSmem, s, pa);
+            else
+                ROFTB_LAUNCH((k_flow_pass_ring<0, false>), dim3(bpt, T), kThreads, RingLayout<0>::kSmem, s, pa);
+        } else if (fuse)
             ROFTB_PASS(0, float, true);
         else
             ROFTB_PASS(0, float, false);
         if (a.ev_first_pass) cudaEventRecord(a.ev_first_pass, s);
         if (a.prof) cudaEventRecord(a.prof[2], s);
         // enough blocks per track to spread the list, few enough that the per-block histogram flush stays cheap
-        int sb = max(1, min(32, (148 * 8 + T - 1) / T));
+        int sb = max(1, min(32, (148 * 24 + T - 1) / T));
+        {
+            static const int env_sb = [] { const char* e = getenv("ROFTB_SB"); return e ? atoi(e) : 0; }();
+            if (env_sb > 0) sb = env_sb;  // tuning hook
+        }
         SelArgs sa;
         sa.norms = a.norms; sa.norm_stride = pa.norm_stride; sa.sel = a.sel; sa.hist = a.hist; sa.ticket = a.norm_count;
         sa.ctl = a.ctl; sa.wt_n = a.wt_n; sa.n_tracks = T; sa.stride = g.stride; sa.wp = a.wp;
@@ -1151,7 +1449,9 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     }
     if (a.accum_fp64 == 2) pa.auto_take_small = 0;
     if (a.accum_fp64 != 1) {
-        if (fuse_b)
+        if (ring)
+            ROFTB_LAUNCH((k_flow_pass_ring<1, false>), dim3(bpt, T), kThreads, RingLayout<1>::kSmem, s, pa);
+        else if (fuse_b)
             ROFTB_PASS(1, float, true);
         else
             ROFTB_PASS(1, float, false);
