@@ -657,6 +657,7 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass_ring(
     WeightParams wp;
     wp.use = 0;
     if (PASS == 1) wp = a.wp[t];
+    const float w_k2 = -wp.inv_b * 1.4426950408889634f, w_cl = wp.coef * wp.inv_lmax, w_floor = 1e-6f * wp.inv_lmax;
     float2 acc2[PASS == 1 ? 20 : 1];
     float cnt_acc = 0.f;
 #pragma unroll
@@ -685,22 +686,23 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass_ring(
     int idsA = lane < cnt ? list[lane] : -1;
     int idsB = 32 + lane < cnt ? list[32 + lane] : -1;
     auto unit_of = [&](int k) { return __shfl_sync(0xffffffffu, (k & 32) ? idsB : idsA, k & 31); };
+    // copy roles: lane 0 depth, lane 1 flow, lane 2 mask (pass A) / pass-A norms (pass B, addressed by list position)
+    const char* cp_base = lane == 0 ? depth_t : lane == 1 ? flow_t
+                          : PASS == 0 ? mask_t : reinterpret_cast<const char*>(norms_t + (long long)k0 * kUnitPx);
+    const uint32_t cp_bpp = lane == 0 ? 4u : lane == 1 ? 8u : PASS == 0 ? 1u : 4u;  // bytes per pixel
+    const uint32_t cp_off = lane == 0 ? L::kD : lane == 1 ? L::kF : L::kX;
+    const bool cp_by_pos = PASS == 1 && lane == 2;
+    constexpr uint32_t kTxPerPx = PASS == 0 ? 13u : 16u;
     auto issue = [&](int kp) {
         const int unit = unit_of(kp);
         const int st = kp % kRingStages;
-        const uint32_t dst = ring_s + st * L::kStage, bar = bar_s + 8 * st;
-        const long long px0 = (long long)unit * kUnitPx;
+        const uint32_t bar = bar_s + 8 * st;
         const uint32_t npx = (uint32_t)min(kUnitPx, HW - unit * kUnitPx);  // multiple of 16 (checked by the launcher)
-        const uint32_t xbytes = PASS == 0 ? npx : (uint32_t)kUnitPx * 4u;
-        if (lane == 0) mbar_expect_tx(bar, npx * 12u + xbytes);
+        if (lane == 0) mbar_expect_tx(bar, npx * kTxPerPx);
         __syncwarp();
-        if (lane < 3) {
-            const char* src = lane == 0 ? depth_t + px0 * 4 : lane == 1 ? flow_t + px0 * 8
-                              : PASS == 0 ? mask_t + px0 : reinterpret_cast<const char*>(norms_t + (long long)(k0 + kp) * kUnitPx);
-            const uint32_t off = lane == 0 ? L::kD : lane == 1 ? L::kF : L::kX;
-            const uint32_t bytes = lane == 0 ? npx * 4u : lane == 1 ? npx * 8u : xbytes;
-            bulk_g2s(dst + off, src, bytes, bar);
-        }
+        if (lane < 3)
+            bulk_g2s(ring_s + st * L::kStage + cp_off, cp_base + (long long)(cp_by_pos ? kp : unit) * (long long)(kUnitPx * cp_bpp),
+                     npx * cp_bpp, bar);
     };
 #pragma unroll 1
     for (int kp = 0; kp < min(kRingStages, cnt); ++kp) issue(kp);
@@ -789,8 +791,8 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass_ring(
                 } else {
                     const float nr = comp(Nc, i);
                     const bool valid = cand;
-                    float l = 1.0f;
-                    if (wp.use) l = fmaxf(wp.coef * __expf(-fabsf(nr - wp.m) * wp.inv_b), 1e-6f) * wp.inv_lmax;
+                    // max(coef exp(-|n - m| / b), 1e-6) / lmax with the constants folded per track
+                    float l = wp.use ? fmaxf(w_cl * ex2_approx(fabsf(nr - wp.m) * w_k2), w_floor) : 1.0f;
                     l = valid ? l : 0.f;
                     const float ias = valid ? ia : 0.f;
                     dx = valid ? dx : 0.f;
@@ -812,9 +814,9 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass_ring(
                     const float2 zz = make_float2(dx, dy);
 #pragma unroll
                     for (int kk = 0; kk < 5; ++kk) acc2[15 + kk] = __ffma2_rn(w[kk], zz, acc2[15 + kk]);
-                    cnt_acc += valid ? 1.0f : 0.f;
                 }
             }
+            if (PASS == 1) cnt_acc += (float)__popc(nib);
         }
         if (PASS == 0 && c.enable) reinterpret_cast<float4*>(norms_t)[(long long)(k0 + k) * 32 + lane] = nv;
         // every lane has consumed its part of the stage (the values above were used): hand it back to the copy engine
