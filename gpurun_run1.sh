@@ -1,11 +1,8 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -q -m gpu -x 2>&1 | tail -5
-for r in 1; do
-export ROFTB_RING=$r
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -q -m gpu -x 2>&1 | tail -3
 timeout 300 python bench.py --no-cpu --no-e2e --steps 48 --warmup 12 > gpurun_out/b.log 2>&1
-tail -1 gpurun_out/b.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('ring $r', round(d['value']), round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['phases_ms_per_step'].items()}, d['sanity'])"
-done
-timeout 900 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:"k_flow_pass_ring" -s 40 -c 4 --csv --log-file gpurun_out/passes.csv python bench.py --no-cpu --no-e2e --steps 12 --warmup 12 > gpurun_out/ncu_k.log 2>&1
+tail -1 gpurun_out/b.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['phases_ms_per_step'].items()}, d['roofline'], d['clocks'])"
+timeout 900 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:"k_sel" -s 30 -c 6 --csv --log-file gpurun_out/passes.csv python bench.py --no-cpu --no-e2e --steps 12 --warmup 12 > gpurun_out/ncu_k.log 2>&1
 python - <<'PY'
 import csv,re
 rows=[r for r in csv.reader(l for l in open('gpurun_out/passes.csv') if l.startswith('"'))]

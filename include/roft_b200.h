@@ -140,6 +140,11 @@ int roftb_get_mask(roftb_ctx* ctx, uint8_t* raw, uint8_t* thresholded);
  * (ImageOpticalFlowMeasurement.hpp:363-366), the accumulated information matrix
  * sum_j l_j H_j^T R^-1 H_j [T][36] and vector sum_j l_j H_j^T R^-1 z_j [T][6]. Blocking. */
 int roftb_get_velocity_info(roftb_ctx* ctx, int32_t* count, double* lambda, double* eta);
+/* Diagnostics of the last step's worklist: per track, the number of non-empty 128-pixel units of the
+ * synchronised mask (units[T]) and the number of segmentation pixels in them (pixels[T]; the
+ * findNonZero count of ImageOpticalFlowMeasurement.hpp:234 before subsampling and gates).  bench.py
+ * derives the bytes the streaming passes had to touch from it.  Either pointer may be NULL. Blocking. */
+int roftb_get_worklist(roftb_ctx* ctx, int32_t* units, int32_t* pixels);
 
 /* ---- operators (stateless; buffers are HOST memory, copied through ctx scratch) --------- */
 /* ImageSegmentationOFAidedSource<T>::map + cv::remap (ImageSegmentationOFAidedSource.hpp:

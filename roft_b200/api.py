@@ -25,7 +25,7 @@ MAX_DELAY = 8
 EXPORTED_SYMBOLS = [
     "roftb_config_default", "roftb_create", "roftb_destroy", "roftb_last_error", "roftb_sync", "roftb_join", "roftb_version",
     "roftb_kernel_launches", "roftb_stream", "roftb_profile", "roftb_filter_init", "roftb_filter_step", "roftb_get_state",
-    "roftb_get_mask", "roftb_get_velocity_info", "roftb_mask_sync", "roftb_flow_velocity", "roftb_velocity_kf",
+    "roftb_get_mask", "roftb_get_velocity_info", "roftb_get_worklist", "roftb_mask_sync", "roftb_flow_velocity", "roftb_velocity_kf",
     "roftb_flow_measurement_export", "roftb_masked_points", "roftb_masked_depth_l1", "roftb_ukf_predict",
     "roftb_ukf_correct",
 ]
@@ -92,6 +92,7 @@ def load_library() -> C.CDLL:
     lib.roftb_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 4
     lib.roftb_get_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.roftb_get_velocity_info.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.roftb_get_worklist.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.roftb_mask_sync.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.roftb_flow_velocity.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8
     lib.roftb_velocity_kf.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 7
@@ -241,6 +242,13 @@ class Tracker:
         cnt = np.empty(T, np.int32); lam = np.empty((T, 6, 6)); eta = np.empty((T, 6))
         self._check(self._lib.roftb_get_velocity_info(self._h, _ptr(cnt), _ptr(lam), _ptr(eta)), "roftb_get_velocity_info")
         return cnt, lam, eta
+
+    def worklist(self):
+        """(non-empty 128-px units, segmentation pixels) per track of the last step's synchronised mask."""
+        T = self.n_tracks
+        units = np.empty(T, np.int32); pixels = np.empty(T, np.int32)
+        self._check(self._lib.roftb_get_worklist(self._h, _ptr(units), _ptr(pixels)), "roftb_get_worklist")
+        return units, pixels
 
     def sync(self):
         self._check(self._lib.roftb_sync(self._h), "roftb_sync")

@@ -860,6 +860,19 @@ int roftb_get_velocity_info(roftb_ctx* ctx, int32_t* count, double* lambda, doub
     return 0;
 }
 
+int roftb_get_worklist(roftb_ctx* ctx, int32_t* units, int32_t* pixels) {
+    if (!ctx) return -2;
+    if (ctx->frame_idx == 0) return fail(ctx, "roftb_get_worklist: no step yet");
+    const size_t T = ctx->T;
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    const int32_t* wt_n = ctx->wt_n + (size_t)((ctx->frame_idx - 1) & 1) * 2 * T;  // (units[T], pixels[T]) of the last step
+    if (units) CK(cudaMemcpyAsync(units, wt_n, T * 4, cudaMemcpyDeviceToHost, s));
+    if (pixels) CK(cudaMemcpyAsync(pixels, wt_n + T, T * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
 }  // extern "C"
 
 // =============================================================================================
