@@ -757,6 +757,10 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass_ring(
                 yh = (vf - g.cy) * g.inv_fy;
                 xh0 = (u0f - g.cx) * inv_fx;
             }
+            // pass A: predicted flow H x^- as a polynomial in x^ with per-quad coefficients (y^ is constant over the quad):
+            //   p1 = a (x0 - x2 x^) + (x4 - y^ x5) + x^ (-y^ x3 + x^ x4)      p2 = a (x1 - y^ x2) - (1 + y^2) x3 + x^ (y^ x4 + x5)
+            const float pk0 = fmaf(-yh, x[5], x[4]), pk1 = -yh * x[3];
+            const float pq0 = fmaf(-yh, x[2], x[1]), pq1 = -fmaf(yh, yh, 1.0f) * x[3], pq2 = fmaf(yh, x[4], x[5]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const bool cand = (nib >> i) & 1u;
@@ -773,22 +777,19 @@ __global__ void __launch_bounds__(kThreads, PASS == 0 ? 3 : 2) k_flow_pass_ring(
                 const float d = comp(Dc, i);
                 const float xh = fmaf((float)i, inv_fx, xh0);
                 const float ia = rcp_approx(d);
-                float l1[5], l2[5];
-                l1[0] = ia; l1[1] = -xh * ia; l1[2] = -xh * yh; l1[3] = fmaf(xh, xh, 1.0f); l1[4] = -yh;
-                l2[0] = ia; l2[1] = -yh * ia; l2[2] = -fmaf(yh, yh, 1.0f); l2[3] = xh * yh; l2[4] = xh;
                 if (PASS == 0) {
                     const bool valid = cand && fabsf(dx) < 1e9f && fabsf(dy) < 1e9f && d > 0.f && d < max_d;
-                    float2 pp = __fmul2_rn(make_float2(l1[0], l2[0]), make_float2(x[0], x[1]));
-                    pp = __ffma2_rn(make_float2(l1[1], l2[1]), make_float2(x[2], x[2]), pp);
-                    pp = __ffma2_rn(make_float2(l1[2], l2[2]), make_float2(x[3], x[3]), pp);
-                    pp = __ffma2_rn(make_float2(l1[3], l2[3]), make_float2(x[4], x[4]), pp);
-                    pp = __ffma2_rn(make_float2(l1[4], l2[4]), make_float2(x[5], x[5]), pp);
-                    const float2 nn = __ffma2_rn(make_float2(-c1, -c2), pp, make_float2(dx, dy));
-                    const float nr = sqrt_approx(fmaf(nn.x, nn.x, nn.y * nn.y));
+                    const float p1 = fmaf(ia, fmaf(-x[2], xh, x[0]), fmaf(xh, fmaf(xh, x[4], pk1), pk0));
+                    const float p2 = fmaf(ia, pq0, fmaf(xh, pq2, pq1));
+                    const float n1 = fmaf(-c1, p1, dx), n2 = fmaf(-c2, p2, dy);
+                    const float nr = sqrt_approx(fmaf(n1, n1, n2 * n2));
                     if (valid) {
                         if (i == 0) nv.x = nr; else if (i == 1) nv.y = nr; else if (i == 2) nv.z = nr; else nv.w = nr;
                     }
                 } else {
+                    float l1[5], l2[5];
+                    l1[0] = ia; l1[1] = -xh * ia; l1[2] = -xh * yh; l1[3] = fmaf(xh, xh, 1.0f); l1[4] = -yh;
+                    l2[0] = ia; l2[1] = -yh * ia; l2[2] = -fmaf(yh, yh, 1.0f); l2[3] = xh * yh; l2[4] = xh;
                     const float nr = comp(Nc, i);
                     const bool valid = cand;
                     // max(coef exp(-|n - m| / b), 1e-6) / lmax with the constants folded per track
