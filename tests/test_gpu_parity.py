@@ -115,6 +115,25 @@ def test_flow_velocity_normal_equations(api, fmt, stride, weight):
         assert rel(eta[t], em) < TOL, (t, rel(eta[t], em))
 
 
+def test_flow_velocity_full_mask_ragged_plane(api):
+    """Every pixel selected on a 200 x 90 plane (140.625 units): the partial last unit carries candidates."""
+    cfg = small_cfg(W=200, H=90, subsampling_radius=1.0, weight_flow=True)
+    seq = sequence(cfg, 2, 3)
+    trk = make_tracker(api, cfg, 2)
+    masks = np.full((2, cfg.height, cfg.width), 255, np.uint8)
+    depth = seq.depth[1].numpy(); flow = seq.flow[2].numpy()
+    xp = np.array([[0.02, -0.3, 0.05, -0.5, 0.2, -0.3], [0.0] * 6])
+    dt = np.array([cfg.sample_time, 0.05])
+    lam, eta, cnt = trk.flow_velocity(masks, depth, flow, xp, dt)
+    R = np.diag(cfg.cov_flow)
+    for t in range(2):
+        z, H, _ = o.flow_velocity_measurement(masks[t], depth[t], flow[t], cfg, dt[t])
+        assert cnt[t] == z.shape[0] // 2
+        _, _, Lm, em = o.skf_correct_information(xp[t], np.eye(6), z, H, R, True)
+        assert rel(lam[t], Lm) < TOL, (t, rel(lam[t], Lm))
+        assert rel(eta[t], em) < TOL, (t, rel(eta[t], em))
+
+
 @pytest.mark.parametrize("stride", [1, 35])
 def test_velocity_kf_matches_sequential_reference(api, stride):
     """Information-form GPU result vs the SEQUENTIAL per-pixel Kalman loop of SKFCorrection.cpp:129-149."""
@@ -230,7 +249,17 @@ def test_ukf_predict_and_correct(api):
 def test_filter_loop_matches_oracle(api, fmt, stride, resync):
     cfg = small_cfg(flow_grid=1 if fmt == "f32" else 4, flow_scale=1.0 if fmt == "f32" else 32.0,
                     subsampling_radius=float(stride), use_pose_resync=resync, segm_delay=4, pose_delay=4)
-    T, F = 3, 22
+    _run_filter_loop(api, cfg, fmt, 3, 22)
+
+
+def test_filter_loop_ragged_last_unit(api):
+    """200 x 90 = 140.625 units of 128 px: the last unit of every plane is partial (bulk copies shorter than a stage,
+    norm slots past the plane) on the TMA-staged path (dense flow, stride 1, weighting on), with delayed masks / poses."""
+    cfg = small_cfg(W=200, H=90, subsampling_radius=1.0, use_pose_resync=True, segm_delay=3, pose_delay=3)
+    _run_filter_loop(api, cfg, "f32", 2, 14)
+
+
+def _run_filter_loop(api, cfg, fmt, T, F):
     seq = sequence(cfg, T, F, flow_format=fmt)
     x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
     trk = make_tracker(api, cfg, T, fmt)
