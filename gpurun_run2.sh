@@ -1,15 +1,6 @@
-python - <<'PY'
-import time, traceback
-try:
-    import pynvml as nv
-    nv.nvmlInit()
-    h = nv.nvmlDeviceGetHandleByIndex(0)
-    print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-    t=time.perf_counter()
-    for i in range(5):
-        print(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-    print("5 samples in", time.perf_counter()-t)
-    print([n for n in dir(nv) if 'ThrottleReason' in n][:12])
-except Exception:
-    traceback.print_exc()
-PY
+mkdir -p gpurun_out
+for pa in 0 1 2 0 2; do
+export ROFTB_PREP_AFTER=$pa
+timeout 300 python bench.py --no-cpu --no-e2e --per-step --steps 96 --warmup 12 > gpurun_out/b.log 2>&1
+tail -1 gpurun_out/b.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('prep_after $pa', round(d['value']), round(d['ms_per_step'],3), {k:round(v,3) for k,v in d['phases_ms_per_step'].items()})"
+done
