@@ -55,7 +55,7 @@ struct roftb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr, prep_stream = nullptr,
                  aux_stream = nullptr;
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
-    cudaEvent_t prep_event[2] = {nullptr, nullptr}, pass_a_event = nullptr;
+    cudaEvent_t prep_event[2] = {nullptr, nullptr}, prep2_event[2] = {nullptr, nullptr}, pass_a_event = nullptr;
     bool pass_a_event_used = false;
     cudaEvent_t vel_event[kCtlRing], ukf_event[kCtlRing], join_event = nullptr, plan_event = nullptr, mask_event = nullptr;
     bool ukf_event_used[kCtlRing];
@@ -285,6 +285,8 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->prep_event[0], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->prep_event[1], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->prep2_event[0], cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->prep2_event[1], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->pass_a_event, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->plan_event, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->mask_event, cudaEventDisableTiming));
@@ -389,8 +391,10 @@ void roftb_destroy(roftb_ctx* ctx) {
     if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
     if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
     if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i) {
         if (ctx->prep_event[i]) cudaEventDestroy(ctx->prep_event[i]);
+        if (ctx->prep2_event[i]) cudaEventDestroy(ctx->prep2_event[i]);
+    }
     if (ctx->pass_a_event) cudaEventDestroy(ctx->pass_a_event);
     if (ctx->ukf_stream) { cudaStreamSynchronize(ctx->ukf_stream); cudaStreamDestroy(ctx->ukf_stream); }
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
@@ -746,15 +750,18 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
         if (launch_tile_list(seg_prev, (long long)ctx->HW, 1, ctx->g.HW, T, wt_count, wt_list, wt_n, nullptr, 0, ps))
             return fail(ctx, "launch_tile_list failed");
         if (launch_mask_plan_init(ma, ps)) return fail(ctx, "launch_mask_plan_init failed");
+        // the velocity chain needs the worklist, the plan and the zeroed plane; the worklist of a NEW mask only feeds the
+        // scatter on the mask stream, so it goes behind the event the main stream waits for
+        CK(cudaEventRecord(ctx->prep_event[par], ps));
         if (any_new_mask && launch_tile_list(d_mask, mask_stride, 0, ctx->g.HW, T, nl_count, nl_list, nl_n,
                                              reinterpret_cast<const int32_t*>(d_wctl), (int)(sizeof(WarpCtl) / 4), ps))
             return fail(ctx, "launch_tile_list failed");
         if (pe) CK(cudaEventRecord(pe[0], ps));
-        CK(cudaEventRecord(ctx->prep_event[par], ps));
+        CK(cudaEventRecord(ctx->prep2_event[par], ps));
     }
     {
         cudaStream_t ms = ctx->mask_stream;
-        CK(cudaStreamWaitEvent(ms, ctx->prep_event[par], 0));
+        CK(cudaStreamWaitEvent(ms, ctx->prep2_event[par], 0));
         if (pe) CK(cudaEventRecord(pe[6], ms));
         if (launch_mask_scatter_gather(ma, ms)) return fail(ctx, "launch_mask_scatter_gather failed");
         if (pe) CK(cudaEventRecord(pe[7], ms));

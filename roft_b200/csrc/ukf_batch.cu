@@ -463,18 +463,26 @@ __device__ void ukf_correct_warp(UkfSmem& s, const UkfParams& p, int mtype, cons
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32) k_ukf_batch(UkfArgs a) {
-    const int t = blockIdx.x;
-    const int lane = threadIdx.x;
+// kUkfWarps tracks per block (one warp each, nothing shared between them): the latency-bound warps then sit on fewer
+// SMs, where they take register-file space from the streaming kernels of the other streams
+constexpr int kUkfWarps = 4;
+struct UkfWarpSmem { UkfSmem s; double meas[16]; };
+
+__global__ void __launch_bounds__(32 * kUkfWarps) k_ukf_batch(UkfArgs a) {
+    extern __shared__ __align__(16) unsigned char ukf_smem_raw[];
+    const int t = blockIdx.x * kUkfWarps + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= a.n_tracks) return;
     const int nops = a.n_ops[t];
     if (nops <= 0) return;
-    __shared__ UkfSmem s;
+    UkfWarpSmem& wsm = reinterpret_cast<UkfWarpSmem*>(ukf_smem_raw)[threadIdx.x >> 5];
+    UkfSmem& s = wsm.s;
+    double* meas = wsm.meas;
     double* gm = a.mean + (long long)t * 13;
     double* gc = a.cov + (long long)t * 144;
     if (lane < 13) s.mean[lane] = gm[lane];
     for (int i = lane; i < 144; i += 32) s.P[i / 12][i % 12] = gc[i];
     __syncwarp();
-    __shared__ double meas[13];
     for (int o = 0; o < nops; ++o) {
         const UkfOp* op = a.ops + (long long)t * a.max_ops + o;
         const int kind = op->kind;
@@ -513,7 +521,13 @@ __global__ void __launch_bounds__(32) k_ukf_batch(UkfArgs a) {
 }  // namespace
 
 int launch_ukf(const UkfArgs& a, cudaStream_t s) {
-    ROFTB_LAUNCH(k_ukf_batch, a.n_tracks, 32, 0, s, a);
+    static bool attr_done = false;
+    const int smem = (int)sizeof(UkfWarpSmem) * kUkfWarps;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_ukf_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_done = true;
+    }
+    ROFTB_LAUNCH(k_ukf_batch, (a.n_tracks + kUkfWarps - 1) / kUkfWarps, 32 * kUkfWarps, smem, s, a);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
