@@ -49,6 +49,7 @@ def parse_args():
                     help="precision of the per-pixel terms of the normal equations (roftb_config.accum_fp64)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the extra 512-tracks-per-GPU measurement (N=1 only)")
     ap.add_argument("--no-resync", action="store_true", help="diagnostic: pose re-sync replay off")
     ap.add_argument("--per-step", action="store_true", help="diagnostic: print main-stream ms per step by phase of the mask period")
     ap.add_argument("--single-mask", action="store_true", help="diagnostic: deliver the mask / pose only at step 0")
@@ -378,9 +379,60 @@ def run_own(args):
             out["cpu_baseline"] = cpu_baseline(args, seq, "port")
         except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
             out["cpu_baseline"] = {"error": repr(e)}
+    if world == 1 and not args.no_sweep and not args.single_mask and T == 256:
+        # Same workload at twice the batch: the per-step latencies that do not scale with the batch (pose re-sync replay,
+        # new-mask scatter chain, launch tails) amortise - reported beside the headline, never instead of it.
+        try:
+            del trk, seq
+            torch.cuda.empty_cache()
+            out["batch_sweep"] = [resident_throughput(args, api, dev, local, 512, 6, 60, 12, peak)]
+        except Exception as e:
+            out["batch_sweep"] = {"error": repr(e)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def resident_throughput(args, api, dev, local, T, F, steps, warmup, peak):
+    """Device-resident throughput of the default workload at another batch size (single GPU)."""
+    import numpy as np
+    import torch
+    from roft_b200.synthetic import make_sequence
+    D = args.delay
+    cfg = api.default_config(n_tracks=T, subsampling_radius=args.stride, segm_delay=D, pose_delay=D, device=local,
+                             accum_fp64={"fp32": 0, "fp64": 1, "auto": 2}[args.accum])
+    trk = api.Tracker(cfg)
+    seq = make_sequence(T, F + 1, W, H, device=dev, target_coverage=args.coverage, first_track_id=0, track_chunk=8)
+    torch.cuda.synchronize()
+    x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
+    trk.init(x0)
+    pose_np = seq.pose.numpy(); pv_np = seq.pose_valid.numpy().astype(np.uint8)
+
+    def do_step(step):
+        f = 0 if step == 0 else 1 + (step - 1) % F
+        idx = step - D
+        s = None if idx % D != 0 else (0 if idx <= 0 else 1 + (idx - 1) % F)
+        trk.step(seq.depth[f], seq.flow[f] if step > 0 else None, seq.mask[s] if s is not None else None,
+                 pose=pose_np[s] if s is not None else None, pose_valid=pv_np[s] if s is not None else None, device=True)
+
+    step = 0
+    for _ in range(warmup):
+        do_step(step); step += 1
+    torch.cuda.synchronize(); trk.sync()
+    ext = torch.cuda.ExternalStream(trk.stream, device=dev)
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record(ext)
+    for _ in range(steps):
+        do_step(step); step += 1
+    trk.join()
+    ev1.record(ext)
+    torch.cuda.synchronize(); trk.sync()
+    ms = ev0.elapsed_time(ev1) / steps
+    gbs = T * BYTES_PER_TRACK_FRAME / (ms * 1e-3) / 1e9
+    pm, vm = trk.state()
+    return {"tracks_per_gpu": T, "resident_frames": F, "steps": steps, "warmup": warmup, "value": T / (ms * 1e-3),
+            "unit": "tracked frames/s", "ms_per_step": ms, "roofline_achieved": gbs, "roofline_frac": gbs / peak,
+            "finite": bool(np.isfinite(pm).all() and np.isfinite(vm).all())}
 
 
 def cpu_baseline(args, seq, kind, threads=None, seconds=None):

@@ -1,8 +1,9 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 900 python bench.py > gpurun_out/bench_r1_own.json 2> gpurun_out/bench_r1_own.err; tail -c 3000 gpurun_out/bench_r1_own.json
-timeout 900 python bench.py --impl reference > gpurun_out/bench_r1_ref.json 2> gpurun_out/bench_r1_ref.err; tail -c 800 gpurun_out/bench_r1_ref.json
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_flow_pass|k_warp_|k_sel_|k_tile_|k_ukf|k_vel_|k_mask_" -s 190 -c 200 --csv --log-file gpurun_out/launches_r1_final.csv python bench.py --no-cpu --no-e2e --steps 12 --warmup 12 > gpurun_out/ncu_final.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_flow_pass_ring|k_sel_|k_warp_scatter|k_ukf_batch|k_tile_count" -s 80 -c 14 -o gpurun_out/prof_r1_final -f python bench.py --no-cpu --no-e2e --steps 12 --warmup 12 > gpurun_out/ncu_final2.log 2>&1
-ls -la gpurun_out | tail -5
+( time timeout 900 python bench.py > gpurun_out/bench_r1_own.json 2> gpurun_out/bench_r1_own.err ) 2>&1 | grep real
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_r1_own.json').read().strip().split('\n')[-1])
+print(round(d['value']), round(d['ms_per_step'],4), round(d['roofline']['frac'],4), d['clocks'], d['e2e'], d.get('batch_sweep'), d['cpu_baseline']['value'], d['gpu_launches'])
+print(d['roofline']['dominant_kernel'])
+PY
+tail -3 gpurun_out/bench_r1_own.err
