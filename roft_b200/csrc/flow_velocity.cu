@@ -1201,31 +1201,31 @@ __device__ void sel_finish_warp(int t, int lane, SelState* __restrict__ sel, uin
 }
 
 // ---- per-track epilogue: FP64 reduction of the block partials, 6x6 solve, gate, publish ------------
-// In-place Gauss-Jordan inverse of a symmetric positive definite 6x6 matrix held in shared memory
-// (no pivoting needed for SPD input). Executed by one thread.
-__device__ __noinline__ void spd6_inverse(double (*A)[6], double (*Ainv)[6]) {
-#pragma unroll 1
-    for (int i = 0; i < 6; ++i)
-#pragma unroll 1
-        for (int j = 0; j < 6; ++j) Ainv[i][j] = (i == j) ? 1.0 : 0.0;
+// Gauss-Jordan inverse of a symmetric positive definite 6x6 matrix (no pivoting needed for SPD input), by one warp:
+// M = [A | I] in shared memory, on exit the right half holds A^-1.  Same elimination order as the scalar algorithm; the
+// 72 entries of an elimination step are independent and spread over the lanes.
+__device__ __noinline__ void spd6_inverse_warp(double (*M)[12], int lane) {
 #pragma unroll 1
     for (int col = 0; col < 6; ++col) {
-        const double piv = 1.0 / A[col][col];
-#pragma unroll 1
-        for (int j = 0; j < 6; ++j) {
-            A[col][j] *= piv;
-            Ainv[col][j] *= piv;
+        const double piv = 1.0 / M[col][col];
+        __syncwarp();
+        if (lane < 12) M[col][lane] *= piv;
+        __syncwarp();
+        double f[3], m[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int e = lane + 32 * i, r = e / 12, c = e - r * 12;
+            const bool on = e < 72 && r != col;
+            f[i] = on ? M[r][col] : 0.0;
+            m[i] = on ? M[col][c] : 0.0;
         }
-#pragma unroll 1
-        for (int r = 0; r < 6; ++r) {
-            if (r == col) continue;
-            const double f = A[r][col];
-#pragma unroll 1
-            for (int j = 0; j < 6; ++j) {
-                A[r][j] -= f * A[col][j];
-                Ainv[r][j] -= f * Ainv[col][j];
-            }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int e = lane + 32 * i, r = e / 12, c = e - r * 12;
+            if (e < 72 && r != col) M[r][c] -= f[i] * m[i];
         }
+        __syncwarp();
     }
 }
 
@@ -1245,81 +1245,96 @@ __global__ void __launch_bounds__(32) k_vel_epilogue(EpiArgs a) {
     const int lane = threadIdx.x;
     const VelCtl c = a.ctl[t];
     __shared__ double sums[kNAcc];
+    __shared__ double sLm[36], sEta[6], sRhs[6];
+    __shared__ double M1[6][12], M2[6][12];
+    __shared__ int s_count;
     if (c.enable) {
+        // fixed summation order (deterministic): two interleaved chains per value keep the FP64 adds pipelined
         for (int i = lane; i < kNAcc; i += 32) {
-            double s = 0.0;
+            double s0 = 0.0, s1 = 0.0;
             const double* p = a.partials + (long long)t * a.max_blocks * kNAcc + i;
-            for (int b = 0; b < a.n_blocks; ++b) s += p[(long long)b * kNAcc];
-            sums[i] = s;
+            int b = 0;
+            for (; b + 1 < a.n_blocks; b += 2) {
+                s0 += p[(long long)b * kNAcc];
+                s1 += p[(long long)(b + 1) * kNAcc];
+            }
+            if (b < a.n_blocks) s0 += p[(long long)b * kNAcc];
+            sums[i] = s0 + s1;
         }
     }
     __syncwarp();
-    if (lane != 0) return;
     double* x = a.v_mean + (long long)t * 6;
     double* P = a.v_cov + (long long)t * 36;
-    int count = 0;
-    if (c.enable) {
-        const int i1[5] = {0, 2, 3, 4, 5}, i2[5] = {1, 2, 3, 4, 5};
-        const double k1 = (a.fx * c.dt) * (a.fx * c.dt) / a.r0, k2 = (a.fy * c.dt) * (a.fy * c.dt) / a.r1;
-        const double e1 = (a.fx * c.dt) / a.r0, e2 = (a.fy * c.dt) / a.r1;
-        double Lm[36], eta[6];
-        for (int i = 0; i < 36; ++i) Lm[i] = 0.0;
-        for (int i = 0; i < 6; ++i) eta[i] = 0.0;
-        int o = 0;
-        for (int r = 0; r < 5; ++r)
-            for (int s = r; s < 5; ++s) {
-                const double v1 = k1 * sums[o], v2 = k2 * sums[15 + o];
-                Lm[i1[r] * 6 + i1[s]] += v1;
-                if (r != s) Lm[i1[s] * 6 + i1[r]] += v1;
-                Lm[i2[r] * 6 + i2[s]] += v2;
-                if (r != s) Lm[i2[s] * 6 + i2[r]] += v2;
-                ++o;
+    if (lane == 0) {
+        int count = 0;
+        for (int i = 0; i < 36; ++i) sLm[i] = 0.0;
+        for (int i = 0; i < 6; ++i) sEta[i] = 0.0;
+        if (c.enable) {
+            const int i1[5] = {0, 2, 3, 4, 5}, i2[5] = {1, 2, 3, 4, 5};
+            const double k1 = (a.fx * c.dt) * (a.fx * c.dt) / a.r0, k2 = (a.fy * c.dt) * (a.fy * c.dt) / a.r1;
+            const double e1 = (a.fx * c.dt) / a.r0, e2 = (a.fy * c.dt) / a.r1;
+            int o = 0;
+            for (int r = 0; r < 5; ++r)
+                for (int q = r; q < 5; ++q) {
+                    const double v1 = k1 * sums[o], v2 = k2 * sums[15 + o];
+                    sLm[i1[r] * 6 + i1[q]] += v1;
+                    if (r != q) sLm[i1[q] * 6 + i1[r]] += v1;
+                    sLm[i2[r] * 6 + i2[q]] += v2;
+                    if (r != q) sLm[i2[q] * 6 + i2[r]] += v2;
+                    ++o;
+                }
+            for (int k = 0; k < 5; ++k) {
+                sEta[i1[k]] += e1 * sums[30 + k];
+                sEta[i2[k]] += e2 * sums[35 + k];
             }
-        for (int k = 0; k < 5; ++k) {
-            eta[i1[k]] += e1 * sums[30 + k];
-            eta[i2[k]] += e2 * sums[35 + k];
+            count = (int)(sums[40] + 0.5);
         }
-        count = (int)(sums[40] + 0.5);
-        if (a.out_lambda)
-            for (int i = 0; i < 36; ++i) a.out_lambda[(long long)t * 36 + i] = Lm[i];
-        if (a.out_eta)
-            for (int i = 0; i < 6; ++i) a.out_eta[(long long)t * 6 + i] = eta[i];
-        // ROFTFilter.cpp:294-301: fewer than 3 valid pixels (or an empty measurement, SKFCorrection.cpp:60-68 keeps
-        // the PREDICTED state, which the observability gate then reverts) -> the belief is left untouched.
-        if (a.update_state && count >= 3) {
-            __shared__ double sW[6][6], sPinv[6][6], sPn[6][6];
-            for (int i = 0; i < 36; ++i) sW[i / 6][i % 6] = P[i];
-            for (int i = 0; i < 6; ++i) sW[i][i] += a.q_diag[i];  // KFPrediction: P + Q, F = I
-            spd6_inverse(sW, sPinv);
-            for (int i = 0; i < 36; ++i) sW[i / 6][i % 6] = sPinv[i / 6][i % 6] + Lm[i];
-            spd6_inverse(sW, sPn);
-            double rhs[6], xn[6];
-            for (int i = 0; i < 6; ++i) {
-                double v = eta[i];
-                for (int j = 0; j < 6; ++j) v += sPinv[i][j] * x[j];
-                rhs[i] = v;
-            }
-            for (int i = 0; i < 6; ++i) {
-                double v = 0.0;
-                for (int j = 0; j < 6; ++j) v += sPn[i][j] * rhs[j];
-                xn[i] = v;
-            }
-            for (int i = 0; i < 6; ++i) x[i] = xn[i];
-            // symmetrise the information-form covariance (exactly symmetric in exact arithmetic)
-            for (int i = 0; i < 6; ++i)
-                for (int j = 0; j < 6; ++j) P[i * 6 + j] = 0.5 * (sPn[i][j] + sPn[j][i]);
-        }
-    } else {
-        if (a.out_lambda)
-            for (int i = 0; i < 36; ++i) a.out_lambda[(long long)t * 36 + i] = 0.0;
-        if (a.out_eta)
-            for (int i = 0; i < 6; ++i) a.out_eta[(long long)t * 6 + i] = 0.0;
+        s_count = count;
     }
-    if (a.out_count) a.out_count[t] = count;
+    __syncwarp();
+    const int count = s_count;
+    if (a.out_lambda)
+        for (int i = lane; i < 36; i += 32) a.out_lambda[(long long)t * 36 + i] = sLm[i];
+    if (a.out_eta && lane < 6) a.out_eta[(long long)t * 6 + lane] = sEta[lane];
+    // ROFTFilter.cpp:294-301: fewer than 3 valid pixels (or an empty measurement, SKFCorrection.cpp:60-68 keeps
+    // the PREDICTED state, which the observability gate then reverts) -> the belief is left untouched.
+    if (c.enable && a.update_state && count >= 3) {  // warp-uniform
+        for (int e = lane; e < 72; e += 32) {
+            const int r = e / 12, cc = e - r * 12;
+            // KFPrediction: P + Q, F = I
+            M1[r][cc] = cc < 6 ? P[r * 6 + cc] + (r == cc ? a.q_diag[r] : 0.0) : (cc - 6 == r ? 1.0 : 0.0);
+        }
+        __syncwarp();
+        spd6_inverse_warp(M1, lane);  // right half: (P + Q)^-1
+        for (int e = lane; e < 72; e += 32) {
+            const int r = e / 12, cc = e - r * 12;
+            M2[r][cc] = cc < 6 ? M1[r][6 + cc] + sLm[r * 6 + cc] : (cc - 6 == r ? 1.0 : 0.0);
+        }
+        __syncwarp();
+        spd6_inverse_warp(M2, lane);  // right half: the corrected covariance
+        if (lane < 6) {
+            double v = sEta[lane];
+            for (int j = 0; j < 6; ++j) v += M1[lane][6 + j] * x[j];
+            sRhs[lane] = v;
+        }
+        __syncwarp();
+        if (lane < 6) {
+            double v = 0.0;
+            for (int j = 0; j < 6; ++j) v += M2[lane][6 + j] * sRhs[j];
+            x[lane] = v;
+        }
+        // symmetrise the information-form covariance (exactly symmetric in exact arithmetic)
+        for (int e = lane; e < 36; e += 32) {
+            const int i = e / 6, j = e - i * 6;
+            P[e] = 0.5 * (M2[i][6 + j] + M2[j][6 + i]);
+        }
+    }
+    __syncwarp();
+    if (lane == 0 && a.out_count) a.out_count[t] = count;
     // velocity_->set_twist(v_corr_belief_.mean()) every frame (ROFTFilter.cpp:305)
-    if (a.vel_hist && c.hist_slot >= 0) {
+    if (a.vel_hist && c.hist_slot >= 0 && lane < 6) {
         double* h = a.vel_hist + ((long long)t * a.hist_ring + c.hist_slot) * 6;
-        for (int i = 0; i < 6; ++i) h[i] = x[i];
+        h[lane] = x[lane];
     }
 }
 
