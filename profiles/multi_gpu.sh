@@ -1,3 +1,5 @@
+#!/bin/bash
+# torchrun launch of bench.py on N GPUs of one box, as the driver does: `gpurun --gpus N -- "bash profiles/multi_gpu.sh N"`
 mkdir -p gpurun_out
 N=$1
 nvidia-smi -L
