@@ -19,9 +19,12 @@
 // No atomics in the accumulation path.
 //
 // Laplacian re-weighting (SKFCorrection.cpp:91-116) needs the median of the innovation norms: pass A
-// streams the frame once and writes the compact list of norms; an exact 3-level radix select finds the
-// middle order statistic(s), one more pass over the norms gives b = mean|n - m|; pass B streams the frame
-// again and accumulates with the weights.
+// streams the listed units of the frame once and writes the norms to position-addressed slots (128 per
+// listed unit, -1 = not a valid measurement); an exact 3-level radix select (12 + 12 + 8 key bits) finds
+// the middle order statistic(s), its last pass also gathers what b = mean|n - m| needs; pass B streams the
+// listed units again (depth, flow and the pass-A norms) and accumulates with the weights.
+// Two implementations of the passes: k_flow_pass_ring (TMA-staged, the common configuration) and the
+// generic register-prefetch k_flow_pass (everything else); see DESIGN.md 4.
 #include "roftb_internal.cuh"
 
 namespace roftb {
@@ -194,12 +197,14 @@ struct PassArgs {
 // AT = accumulation type of pass B: float (per-pixel terms and partial sums in FP32) or double (per-pixel terms
 // and sums in FP64: forward error ~ cond(Lambda) * 1e-16 instead of cond * 1e-7 / sqrt(N)).
 //
-// Each warp walks its track's worklist of non-empty warp tiles (512 px: 4 sub-tiles of one quad per lane).  The
+// Each warp walks its track's worklist of non-empty units, four list entries (4 x 128 px, one quad per lane each) per
+// trip.  The
 // sub-tile loop is kept ROLLED with the loads of the next quad in flight while the current one is processed: the
 // kernel stays a few hundred SASS instructions (a fully unrolled body was 8k instructions and stalled on
 // instruction fetch), registers stay below 128 and three 128-bit loads per lane are always outstanding.
-// Innovation norms are written to rank-addressed slots (base = number of selected candidates before the tile,
-// from the worklist prefix), so pass A needs no atomics; gated-out candidates are marked with -1.
+// Innovation norms are written to position-addressed slots (list position x 128 + pixel; one coalesced 128-bit store
+// per lane, gated-out / non-candidate pixels marked with -1) at stride 1, and to rank-addressed compact slots (rank base
+// of the unit from the worklist prefix) when stride > 1; either way pass A needs no atomics.
 // SCATTER: the same walk also forward-scatters every non-zero mask pixel through the current flow (the "no new mask"
 // propagation of the mask synchronisation) - it needs exactly the mask words and flow values this pass loads anyway.
 //

@@ -163,8 +163,8 @@ struct VelocityArgs {
     const VelCtl* ctl;                                    // device
     int weight_flow;
     // scratch
-    int32_t* wt_count;      // [T][n_warp_tiles] row-major rank base of each warp tile   } built by
-    int32_t* wt_list;       // [T][n_warp_tiles] non-empty warp tiles of the mask        } launch_tile_list
+    int32_t* wt_count;      // [T][n_units] row-major rank base of each 128-px unit      } built by
+    int32_t* wt_list;       // [T][n_units] non-empty units of the mask                  } launch_tile_list
     int32_t* wt_n;          // [2T] their number, then the candidate totals              }
     float* norms;           // [T][HW]
     uint32_t* norm_count;   // [T]
@@ -194,7 +194,7 @@ struct VelocityArgs {
     const double* x_pred_override;     // operator mode: [T][6] predicted mean for the norms (else v_mean)
 };
 int launch_velocity(const VelocityArgs& a, cudaStream_t s);
-// worklist of the non-empty warp tiles of a byte plane (+ rank base of the bytes > thr); active: optional per-item
+// worklist of the non-empty 128-px units of a byte plane (+ rank base of the bytes > thr); active: optional per-item
 // flags, item i is processed iff active[i * active_stride] != 0
 int launch_tile_list(const uint8_t* plane, long long stride, int thr, int HW, int n_items, int32_t* wt_count, int32_t* wt_list,
                      int32_t* wt_n, const int32_t* active, int active_stride, cudaStream_t s);
