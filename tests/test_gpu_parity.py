@@ -346,3 +346,42 @@ def test_full_resolution_filter_loop_vs_sequential_cpp(api, accum):
             assert cnt[t] == en, (k, t, cnt[t], en)
             assert rel(vm[t], evm) < TOL or np.linalg.norm(vm[t] - evm) < 1e-9, (accum, k, t, rel(vm[t], evm))
             assert rel(pm[t, :9], epm[:9]) < TOL and quat_close(pm[t, 9:], epm[9:]) < TOL, (accum, k, t)
+
+
+def test_ho3d_format_single_track(api):
+    """BASELINE configs[2]: HO-3D-format 640x480 single track (SURVEY 8d intrinsics fx = fy = 617, cx = 312, cy = 241),
+    every masked pixel, masks and poses delayed by 4 frames - parity of the whole filter loop against the sequential
+    C++ restatement, and the per-frame latency of the C-ABI step with HOST buffers (upload + step + read-back)."""
+    import time
+    import cpu_ref
+    cfg = o.RoftConfig(width=640, height=480, fx=617.0, fy=617.0, cx=312.0, cy=241.0, subsampling_radius=1.0,
+                       segm_delay=4, pose_delay=4)
+    T, F = 1, 14
+    seq = sequence(cfg, T, F, target_coverage=0.2)
+    x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
+    trk = api.Tracker(to_roftb_config(cfg, T))
+    trk.init(x0)
+    ref = cpu_ref.CFilter(cfg, x0[0])
+    lat = []
+    for k in range(F):
+        fr = frame_inputs(seq, cfg, k, 0)
+        mask = fr.mask[None] if fr.mask is not None else None
+        pose = (fr.pose if fr.pose is not None else np.zeros(7))[None]
+        pv = np.array([fr.pose is not None], np.uint8)
+        flow = fr.flow[None] if k > 0 else None
+        t0 = time.perf_counter()
+        trk.step(fr.depth[None], flow, mask, pose=pose, pose_valid=pv)
+        pm, vm = trk.state()
+        lat.append((time.perf_counter() - t0) * 1e3)
+        raw, thr = trk.mask()
+        cnt, _, _ = trk.velocity_info()
+        ref.step(fr.depth, fr.flow, fr.mask, fr.pose, fr.dt)
+        epm, _, evm, _, en = ref.state()
+        eraw, ethr = ref.mask()
+        assert np.array_equal(raw[0], eraw) and np.array_equal(thr[0], ethr), k
+        assert cnt[0] == en, (k, cnt[0], en)
+        assert rel(vm[0], evm) < TOL or np.linalg.norm(vm[0] - evm) < 1e-9, (k, rel(vm[0], evm))
+        assert rel(pm[0, :9], epm[:9]) < TOL and quat_close(pm[0, 9:], epm[9:]) < TOL, k
+    lat = np.sort(np.array(lat[2:]))
+    print(f"\nHO-3D-format single track, host buffers: p50 {lat[len(lat) // 2]:.3f} ms, max {lat[-1]:.3f} ms per frame")
+    assert np.isfinite(lat).all()
