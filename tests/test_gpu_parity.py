@@ -385,3 +385,33 @@ def test_ho3d_format_single_track(api):
     lat = np.sort(np.array(lat[2:]))
     print(f"\nHO-3D-format single track, host buffers: p50 {lat[len(lat) // 2]:.3f} ms, max {lat[-1]:.3f} ms per frame")
     assert np.isfinite(lat).all()
+
+
+def test_worklist_diagnostics(api):
+    """roftb_get_worklist: non-empty 128-px units and segmentation pixels (byte > 1) of the mask the last step used."""
+    cfg = small_cfg(subsampling_radius=1.0, segm_delay=2, pose_delay=2)
+    T = 2
+    seq = sequence(cfg, T, 4)
+    x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
+    trk = make_tracker(api, cfg, T)
+    trk.init(x0)
+    orc = [o.RoftFilterOracle(cfg, x0[t]) for t in range(T)]
+    for k in range(4):
+        frs = [frame_inputs(seq, cfg, k, t) for t in range(T)]
+        prev_seg = [None if orc[t].seg is None else orc[t].seg.copy() for t in range(T)]
+        mask = np.stack([f.mask for f in frs]) if frs[0].mask is not None else None
+        pose = np.stack([f.pose if f.pose is not None else np.zeros(7) for f in frs])
+        pv = np.array([f.pose is not None for f in frs], np.uint8)
+        trk.step(np.stack([f.depth for f in frs]), np.stack([f.flow for f in frs]) if k > 0 else None, mask, pose=pose,
+                 pose_valid=pv)
+        units, pixels = trk.worklist()
+        for t in range(T):
+            orc[t].step(frs[t])
+            if prev_seg[t] is None:
+                continue
+            # the velocity pass of step k reads the segmentation synchronised at step k-1
+            flat = (prev_seg[t].reshape(-1) > 1)
+            assert pixels[t] == int(flat.sum()), (k, t)
+            pad = (-flat.size) % 128
+            u = np.pad(flat, (0, pad)).reshape(-1, 128).any(axis=1).sum()
+            assert units[t] == int(u), (k, t)
