@@ -374,7 +374,7 @@ def run_own(args):
         "sanity": {"mean_valid_pixels": float(cnt.mean()), "mean_abs_w": float(np.abs(vm[:, 3:]).mean()),
                    "finite": bool(np.isfinite(pm).all() and np.isfinite(vm).all())},
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # reported at N = 1 only (rank 0)
         try:
             out["cpu_baseline"] = cpu_baseline(args, seq, "port")
         except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
