@@ -107,17 +107,18 @@ void skf_correct(const Cfg& c, double* x, double* P, const std::vector<double>& 
     if (n == 0) return;
     std::vector<double> lik;
     if (c.weight_flow) {
-        std::vector<double> norms(n), sorted;
-        for (int j = 0; j < n; ++j) {
-            double in[2];
+        // innovations w.r.t. the predicted mean, interleaved [dx_0, dy_0, dx_1, dy_1, ...] (:74-84)
+        std::vector<double> nu(2 * std::size_t(n)), norms(n), sorted(n);
+        for (int j = 0; j < n; ++j)
             for (int r = 0; r < 2; ++r) {
                 double p = 0;
                 for (int k = 0; k < 6; ++k) p += Hm[(2 * j + r) * 6 + k] * x[k];
-                in[r] = z[2 * j + r] - p;
+                nu[2 * j + r] = z[2 * j + r] - p;
             }
-            norms[j] = std::sqrt(in[0] * in[0] + in[1] * in[1]);
-        }
-        sorted = norms;
+        // Reference quirk Q3 (:93-94): Map<MatrixXd>(nu.data(), n, 2) is COLUMN-major, so the row norms that feed the
+        // median and b are sqrt(nu[i]^2 + nu[n + i]^2); the per-pixel norm is only used for the likelihoods (:111).
+        for (int i = 0; i < n; ++i) sorted[i] = std::sqrt(nu[i] * nu[i] + nu[n + i] * nu[n + i]);
+        for (int j = 0; j < n; ++j) norms[j] = std::sqrt(nu[2 * j] * nu[2 * j] + nu[2 * j + 1] * nu[2 * j + 1]);
         std::sort(sorted.begin(), sorted.end());
         double mi = sorted[n / 2];
         if (n % 2 == 0) mi = 0.5 * (sorted[n / 2 - 1] + sorted[n / 2]);

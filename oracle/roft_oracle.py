@@ -175,17 +175,36 @@ def kf_predict(x: np.ndarray, P: np.ndarray, Q: np.ndarray) -> Tuple[np.ndarray,
     return x.copy(), P + Q
 
 
-def laplacian_likelihoods(norms: np.ndarray) -> np.ndarray:
-    """SKFCorrection.cpp:91-116: median / mean-absolute-deviation Laplacian re-weighting."""
-    n = norms.shape[0]
-    s = np.sort(norms)
+def laplacian_stat_norms(innov: np.ndarray) -> np.ndarray:
+    """The N "norms" whose median / mean absolute deviation fit the Laplacian (SKFCorrection.cpp:93-94).
+
+    Reference quirk Q3 (replicated, not fixed): the reference views the interleaved innovation vector
+    nu = [dx_0, dy_0, dx_1, dy_1, ...] (2N x 1) as ``Map<MatrixXd>(nu.data(), N, 2)``.  Eigen's MatrixXd is
+    COLUMN-major, so row i of that map is (nu[i], nu[N + i]) - a component of valid pixel i // 2 paired with a
+    component of valid pixel (N + i) // 2 - and ``rowwise().norm()`` gives r_i = sqrt(nu[i]^2 + nu[N+i]^2), NOT the
+    per-pixel norm.  Only the likelihood loop (:111) uses the properly paired ``segment(2j, 2).norm()``.
+    """
+    n = innov.shape[0] // 2
+    return np.sqrt(innov[:n] ** 2 + innov[n:2 * n] ** 2)
+
+
+def laplacian_likelihoods(innov: np.ndarray) -> np.ndarray:
+    """SKFCorrection.cpp:91-116: median / mean-absolute-deviation Laplacian re-weighting.
+
+    ``innov`` is the interleaved 2N innovation vector of the valid pixels in selection order.  The median m and the
+    scale b come from the column-major-mapped norms (Q3, ``laplacian_stat_norms``); the likelihood of pixel j is
+    evaluated at its own norm ||(nu[2j], nu[2j+1])|| (:111) and the vector is divided by its true maximum (:114).
+    """
+    n = innov.shape[0] // 2
+    s = np.sort(laplacian_stat_norms(innov))
     m = s[n // 2]
     if n % 2 == 0:
         m = 0.5 * (s[n // 2 - 1] + s[n // 2])
     b = np.abs(s - m).sum() / n
     lik = np.ones(n, np.float64)
     if b > 1e-4:
-        lik = np.maximum(1.0 / (2 * b) * np.exp(-np.abs(norms - m) / b), 1e-6)
+        pix = np.sqrt(innov[0::2] ** 2 + innov[1::2] ** 2)
+        lik = np.maximum(1.0 / (2 * b) * np.exp(-np.abs(pix - m) / b), 1e-6)
         lik = lik / lik.max()
     return lik
 
@@ -199,7 +218,7 @@ def skf_correct(x_pred: np.ndarray, P_pred: np.ndarray, z: np.ndarray, H: np.nda
     lik = None
     if weighting:
         innov = z - H @ x_pred  # innovations w.r.t. the predicted mean, computed once (:44,:74)
-        lik = laplacian_likelihoods(np.sqrt(innov[0::2] ** 2 + innov[1::2] ** 2))
+        lik = laplacian_likelihoods(innov)
     x = x_pred.astype(np.float64).copy()
     P = P_pred.astype(np.float64).copy()
     I6 = np.eye(6)
@@ -224,7 +243,7 @@ def skf_correct_information(x_pred, P_pred, z, H, R, weighting):
     lik = np.ones(n)
     if weighting:
         innov = z - H @ x_pred
-        lik = laplacian_likelihoods(np.sqrt(innov[0::2] ** 2 + innov[1::2] ** 2))
+        lik = laplacian_likelihoods(innov)
     rinv = 1.0 / np.diag(R)
     w = np.empty(2 * n)
     w[0::2] = lik * rinv[0]

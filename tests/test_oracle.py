@@ -143,16 +143,64 @@ def test_sequential_skf_equals_information_form_and_cpp():
         assert rel(xc, xs) < 1e-12 and rel(Pc, Ps) < 1e-12
 
 
+def _skf_weights_transcribed(innov):
+    """SKFCorrection.cpp:91-116 line by line, with Eigen's semantics spelled out in numpy: MatrixXd and
+    Map<MatrixXd> are COLUMN-major (``order="F"``), ``rowwise().norm()`` is the 2-norm of each row."""
+    sub = 2                                                                     # measurement_sub_size_
+    rows = innov.shape[0]
+    innovation_vector = innov[:rows].reshape((rows // sub, sub), order="F")      # :93  Map<MatrixXd>(data, rows/2, 2)
+    norms = np.sqrt((innovation_vector ** 2).sum(axis=1))                       # :94  rowwise().norm()
+    norms = np.sort(norms)                                                      # :95  std::sort
+    mi = norms[norms.size // 2]                                                 # :98
+    if norms.size % 2 == 0:                                                     # :99-100
+        mi = 0.5 * (norms[norms.size // 2 - 1] + norms[norms.size // 2])
+    b = np.abs(norms - mi).sum() / norms.size                                   # :102
+    lik = np.ones(norms.size)                                                   # :104
+    if b > 1e-4:                                                                # :106
+        for j in range(norms.size):                                             # :108-112
+            seg = innov[j * sub:j * sub + sub]                                  #      col(0).segment(j*2, 2)
+            lik[j] = max(1.0 / (2 * b) * math.exp(-abs(np.sqrt((seg ** 2).sum()) - mi) / b), 1e-6)
+        lik /= lik.max()                                                        # :114
+    return lik, mi, b
+
+
 def test_laplacian_weights_reference_rules():
-    # SKFCorrection.cpp:95-116: even/odd median, b <= 1e-4 -> all ones, floor 1e-6, max-normalised
-    n = np.array([0.1, 0.5, 0.2, 0.9])
-    lik = o.laplacian_likelihoods(n)
-    m = 0.35; b = np.abs(n - m).mean()
-    e = np.maximum(np.exp(-np.abs(n - m) / b) / (2 * b), 1e-6)
-    assert np.allclose(lik, e / e.max())
-    assert np.all(o.laplacian_likelihoods(np.full(5, 0.3)) == 1.0)
-    far = o.laplacian_likelihoods(np.array([0.1, 0.1, 0.1, 0.1001, 0.1, 50.0, 0.1002]))
+    # SKFCorrection.cpp:95-116: even/odd median, b <= 1e-4 -> all ones, floor 1e-6, max-normalised.
+    # Q3: the median / b come from the COLUMN-major view of the interleaved innovations: r_i = |(nu[i], nu[N+i])|
+    nu = np.array([0.3, -0.4, 0.1, 0.2, -0.6, 0.8, 0.05, 0.0])           # 4 pixels
+    r = np.sqrt(nu[:4] ** 2 + nu[4:] ** 2)
+    assert np.allclose(o.laplacian_stat_norms(nu), r)
+    s = np.sort(r); m = 0.5 * (s[1] + s[2]); b = np.abs(r - m).mean()
+    pix = np.sqrt(nu[0::2] ** 2 + nu[1::2] ** 2)
+    e = np.maximum(np.exp(-np.abs(pix - m) / b) / (2 * b), 1e-6)
+    assert np.allclose(o.laplacian_likelihoods(nu), e / e.max(), rtol=1e-15)
+    # it is NOT the median of the per-pixel norms
+    assert abs(m - np.median(pix)) > 1e-2
+    # identical innovations: b = 0 -> all ones
+    assert np.all(o.laplacian_likelihoods(np.tile([0.3, 0.4], 5)) == 1.0)
+    far = o.laplacian_likelihoods(np.array([0.1, 0.0, 0.1, 0.0, 0.1, 0.0, 0.1001, 0.0, 0.1, 0.0, 50.0, 0.0, 0.1002, 0.0]))
     assert far.max() == 1.0 and far.min() > 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 64, 257, 1000])
+def test_laplacian_weights_match_line_by_line_transcription(n):
+    """Odd and even N (the column-major pairing differs: for odd N a dx is paired with a dy of another pixel)."""
+    rng = np.random.default_rng(n)
+    nu = rng.laplace(0.0, 0.4, 2 * n) + rng.normal(0, 0.05, 2 * n)
+    nu[rng.integers(0, 2 * n, max(1, n // 10))] += 25.0  # outliers
+    lik, mi, b = _skf_weights_transcribed(nu)
+    assert np.allclose(o.laplacian_likelihoods(nu), lik, rtol=1e-14, atol=0)
+    # explicit element pairing for both parities: r_i = |(nu[i], nu[N + i])|
+    r = np.array([math.hypot(nu[i], nu[n + i]) for i in range(n)])
+    assert np.allclose(np.sort(o.laplacian_stat_norms(nu)), np.sort(r), rtol=1e-15)
+    # and the C++ restatement agrees through the full correction
+    if n >= 3:
+        H = rng.normal(size=(2 * n, 6)); xp = rng.normal(size=6) * 0.1; Pp = np.eye(6) * 0.1
+        z = nu + H @ xp
+        cfg = small_cfg(weight_flow=True)
+        xs, Ps = o.skf_correct(xp, Pp, z, H, np.diag(cfg.cov_flow), True)
+        xc, Pc = cpu_ref.skf_correct(cfg, xp, Pp, z, H)
+        assert rel(xc, xs) < 1e-10 and rel(Pc, Ps) < 1e-10
 
 
 # ---- bfl pieces (UPSTREAM-RECALL): properties --------------------------------------------------------
