@@ -12,9 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "roft_b200", "csrc")
 LIB = os.path.join(ROOT, "roft_b200", "libroft_b200.so")
-SOURCES = ["roftb_api.cu", "mask_sync.cu", "flow_velocity.cu", "ukf_batch.cu", "extract.cu"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--use_fast_math=false" if False else "-Xptxas", "-v" if False else "-O3"]
+SOURCES = ["roftb_api.cu", "mask_sync.cu", "worklist.cu", "velocity_track.cu", "ukf_batch.cu", "extract.cu"]
 
 
 def needs_build() -> bool:

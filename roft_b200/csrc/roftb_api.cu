@@ -6,6 +6,7 @@
 //   CartesianQuaternionMeasurement::freeze mode machine   src/roft-lib/src/CartesianQuaternionMeasurement.cpp:92-348
 // Everything value-dependent (empty masks, observability, the filters) runs on the device, so a step
 // never synchronises with the GPU.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -55,8 +56,8 @@ struct roftb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr, prep_stream = nullptr,
                  aux_stream = nullptr;
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
-    cudaEvent_t prep_event[2] = {nullptr, nullptr}, prep2_event[2] = {nullptr, nullptr}, pass_a_event = nullptr;
-    bool pass_a_event_used = false;
+    cudaEvent_t prep_event[2] = {nullptr, nullptr}, prep2_event[2] = {nullptr, nullptr}, vel_done_event = nullptr;
+    bool vel_done_event_used = false;
     cudaEvent_t vel_event[kCtlRing], ukf_event[kCtlRing], join_event = nullptr, plan_event = nullptr, mask_event = nullptr;
     bool ukf_event_used[kCtlRing];
     bool mask_event_used = false;
@@ -65,17 +66,16 @@ struct roftb_ctx {
 
     // device state
     uint8_t* mask_state[3] = {nullptr, nullptr, nullptr};  // ring of 3: step k reads [k%3], writes [(k+1)%3]
+    uint8_t* mask_occ[3] = {nullptr, nullptr, nullptr};    // occupancy flags of the three planes: [T][n_units]
     int mask_cur = 0;
     int32_t* winner = nullptr;
-    float* norms = nullptr;
-    uint32_t* norm_count = nullptr;
-    uint32_t* hist = nullptr;
-    SelState* sel = nullptr;
-    WeightParams* wp = nullptr;
-    double* partials = nullptr;
-    int max_blocks = 0;
-    int32_t* wt_count = nullptr;    // state-mask worklist: rank base, list, length
-    int32_t* wt_list = nullptr;
+    VelScratch scratch;             // scratch-slot pool of the velocity kernel
+    int32_t* wl_units = nullptr;    // [T] listed units / candidate pixels of the last step (diagnostics)
+    int32_t* wl_pixels = nullptr;
+    unsigned long long* phase_clock = nullptr;  // [T][8] phase stamps of the velocity kernel (profiling)
+    int32_t* vel_order = nullptr;   // [2][T] scheduling order of the velocity kernel (by step parity), largest worklist first
+    uint32_t* vel_ticket = nullptr;
+    int32_t* wt_list = nullptr;     // state-mask worklist (only for masks scattered by the stand-alone kernel)
     int32_t* wt_n = nullptr;
     int32_t* nl_count = nullptr;    // newly delivered mask worklist
     int32_t* nl_list = nullptr;
@@ -113,6 +113,7 @@ struct roftb_ctx {
     cudaEvent_t prof_ev[kCtlRing][11];
     bool prof_used[kCtlRing];
     double prof_ms[7];
+    double prof_phase[4];   // time of the velocity kernel's phases summed over tracks (ns): A, select, B, epilogue
     long long prof_steps = 0;
 };
 
@@ -255,8 +256,8 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     ctx->n_warp_tiles = (int)((HW + kWarpTilePx - 1) / kWarpTilePx);
     ctx->n_units = (int)((HW + kUnitPx - 1) / kUnitPx);
     const int n_block_tiles = (int)((HW + kBlockTilePx - 1) / kBlockTilePx);
-    ctx->max_blocks = 256;  // warp partials per track (32 blocks x 8 warps)
     (void)n_block_tiles;
+    memset(&ctx->scratch, 0, sizeof(ctx->scratch));
 #define CKC(call)                                                              \
     do {                                                                       \
         cudaError_t e__ = (call);                                              \
@@ -267,27 +268,31 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
         }                                                                      \
     } while (0)
     CKC(cudaSetDevice(ctx->dev));
-    // the velocity chain (pass A -> select -> pass B -> epilogue) is the critical path of a step: its blocks are
-    // dispatched first; mask / worklist preparation next; the latency-bound pose UKF fills what is left
+    // Stream priorities: all equal by default.  Measured on B200: the velocity kernel keeps blocks
+    // pending for most of a step, and whichever way the other streams are ranked around it (above: their blocks displace
+    // its clusters; below: they wait for its tail) the step takes as long or longer - the work of an event step
+    // (new-mask scatter, pose re-sync replay) has to be paid in machine time either way.
+    // ROFTB_STREAM_PRIORITIES=1: scatter / preparation / UKF above the velocity kernel (diagnostic).
     int prio_lo = 0, prio_hi = 0;
     CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // numerically lower = higher priority
-    const int prio_mid = prio_hi;  // (a lower priority for the mask chain delays the next step's worklist: measured slower)
     const char* env_prio = getenv("ROFTB_STREAM_PRIORITIES");
-    if (env_prio && env_prio[0] == '0') prio_lo = prio_hi;  // diagnostic: all streams equal
-    CKC(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
-    CKC(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi));
-    CKC(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, env_prio && env_prio[0] == '0' ? prio_hi : prio_mid));
-    CKC(cudaStreamCreateWithPriority(&ctx->ukf_stream, cudaStreamNonBlocking, prio_lo));
+    const bool flat = !(env_prio && env_prio[0] == '1');
+    const int prio_main = flat ? prio_hi : std::min(prio_lo, prio_hi + 1);
+    const int prio_ukf = prio_hi;
+    CKC(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_main));
+    CKC(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_main));
+    CKC(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_hi));
+    CKC(cudaStreamCreateWithPriority(&ctx->ukf_stream, cudaStreamNonBlocking, prio_ukf));
     CKC(cudaEventCreateWithFlags(&ctx->join_event, cudaEventDisableTiming));
-    CKC(cudaStreamCreateWithPriority(&ctx->mask_stream, cudaStreamNonBlocking, env_prio && env_prio[0] == '0' ? prio_hi : prio_mid));
-    CKC(cudaStreamCreateWithPriority(&ctx->prep_stream, cudaStreamNonBlocking, env_prio && env_prio[0] == '0' ? prio_hi : prio_mid));
+    CKC(cudaStreamCreateWithPriority(&ctx->mask_stream, cudaStreamNonBlocking, prio_hi));
+    CKC(cudaStreamCreateWithPriority(&ctx->prep_stream, cudaStreamNonBlocking, prio_hi));
     CKC(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->prep_event[0], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->prep_event[1], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->prep2_event[0], cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->prep2_event[1], cudaEventDisableTiming));
-    CKC(cudaEventCreateWithFlags(&ctx->pass_a_event, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->vel_done_event, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->plan_event, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->mask_event, cudaEventDisableTiming));
     for (int i = 0; i < kCtlRing; ++i) {
@@ -302,15 +307,40 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(dalloc(&ctx->mask_state[1], T * HW));
     CKC(dalloc(&ctx->mask_state[2], T * HW));
     CKC(dalloc(&ctx->winner, T * HW));
-    CKC(dalloc(&ctx->norms, (size_t)T * ctx->n_units * kUnitPx));
-    CKC(dalloc(&ctx->norm_count, (size_t)T));
-    CKC(dalloc(&ctx->hist, (size_t)T * kSelBins));
-    CKC(dalloc(&ctx->sel, (size_t)T));
-    CKC(dalloc(&ctx->wp, (size_t)T));
-    CKC(dalloc(&ctx->partials, (size_t)T * ctx->max_blocks * kNAcc));
-    CKC(dalloc(&ctx->wt_count, (size_t)2 * T * ctx->n_units));   // x2: worklists / plans are double-buffered by step parity
+    for (int i = 0; i < 3; ++i) CKC(dalloc(&ctx->mask_occ[i], (size_t)T * ctx->n_units));
+    {
+        // velocity kernel: shared-memory / cluster attributes are per device; one scratch slot per cluster that can
+        // be resident at once
+        int max_clusters = 0;
+        if (velocity_prepare_device(ctx->g, ctx->n_units, &max_clusters)) {
+            g_create_error = std::string("velocity kernel set-up failed: ") + cudaGetErrorString(cudaGetLastError());
+            roftb_destroy(ctx);
+            return -1;
+        }
+        VelScratch& sc = ctx->scratch;
+        sc.n_slots = std::max(1, std::min(T, max_clusters));
+        sc.n_slot_words = (sc.n_slots + 31) / 32;
+        sc.cap = (long long)ctx->n_units * kUnitPx + 64;
+        const size_t S = (size_t)sc.n_slots;
+        CKC(dalloc(&sc.nu, S * (size_t)sc.cap));
+        CKC(dalloc(&sc.dp, S * (size_t)sc.cap));
+        CKC(dalloc(&sc.r, S * (size_t)sc.cap));
+        CKC(dalloc(&sc.hist, S * 3 * kSelBins));
+        CKC(dalloc(&sc.chunk_cnt, S * kVtMaxChunks));
+        CKC(dalloc(&sc.part, (size_t)T * kVtMaxCluster * kVtPartN));
+        CKC(dalloc(&sc.track_sel, (size_t)T * 4));
+        CKC(dalloc(&sc.sel_part, S * kVtMaxCluster * 4));
+        CKC(dalloc(&sc.slot_bitmap, (size_t)sc.n_slot_words));
+        CKC(dalloc(&sc.track_slot, (size_t)T));
+        CKC(dalloc(&sc.chunk_aux, (size_t)T * kVtMaxChunks));
+    }
+    CKC(dalloc(&ctx->wl_units, (size_t)T));
+    CKC(dalloc(&ctx->wl_pixels, (size_t)T));
+    CKC(dalloc(&ctx->phase_clock, (size_t)T * 8));
+    CKC(dalloc(&ctx->vel_order, (size_t)2 * T));
+    CKC(dalloc(&ctx->vel_ticket, (size_t)1));
     CKC(dalloc(&ctx->wt_count2, (size_t)T * ctx->n_warp_tiles));
-    CKC(dalloc(&ctx->wt_list, (size_t)2 * T * ctx->n_units));
+    CKC(dalloc(&ctx->wt_list, (size_t)2 * T * ctx->n_units));   // x2: worklists / plans are double-buffered by step parity
     CKC(dalloc(&ctx->wt_n, (size_t)4 * T));
     CKC(dalloc(&ctx->nl_count, (size_t)2 * T * ctx->n_units));
     CKC(dalloc(&ctx->nl_list, (size_t)2 * T * ctx->n_units));
@@ -361,10 +391,14 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
 void roftb_destroy(roftb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->dev);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->mask_state[2], ctx->winner, ctx->norms, ctx->norm_count, ctx->hist, ctx->sel,
-                     ctx->wp, ctx->partials, ctx->wt_count, ctx->wt_count2, ctx->wt_list, ctx->wt_n, ctx->nl_count, ctx->nl_list, ctx->nl_n, ctx->stat, ctx->plan, ctx->fbuf, ctx->v_mean,
+    // nothing may still be running on any of the streams when the buffers go away
+    for (cudaStream_t st : {ctx->copy_stream, ctx->prep_stream, ctx->stream, ctx->aux_stream, ctx->mask_stream, ctx->ukf_stream})
+        if (st) cudaStreamSynchronize(st);
+    void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->mask_state[2], ctx->mask_occ[0], ctx->mask_occ[1], ctx->mask_occ[2],
+                     ctx->winner, ctx->scratch.nu, ctx->scratch.dp, ctx->scratch.r, ctx->scratch.hist, ctx->scratch.chunk_cnt,
+                     ctx->scratch.part, ctx->scratch.track_sel, ctx->scratch.sel_part, ctx->scratch.slot_bitmap, ctx->scratch.track_slot, ctx->scratch.chunk_aux,
+                     ctx->wl_units, ctx->wl_pixels, ctx->phase_clock, ctx->vel_order, ctx->vel_ticket,
+                     ctx->wt_count2, ctx->wt_list, ctx->wt_n, ctx->nl_count, ctx->nl_list, ctx->nl_n, ctx->stat, ctx->plan, ctx->fbuf, ctx->v_mean,
                      ctx->v_cov, ctx->p_mean, ctx->p_cov, ctx->pb_mean, ctx->pb_cov, ctx->vel_hist, ctx->q_diag,
                      ctx->d_count, ctx->d_lambda, ctx->d_eta, ctx->d_wctl, ctx->d_vctl, ctx->d_ops, ctx->d_nops,
                      ctx->stage_depth, ctx->stage_flow, ctx->stage_mask, ctx->thr_tmp};
@@ -395,7 +429,7 @@ void roftb_destroy(roftb_ctx* ctx) {
         if (ctx->prep_event[i]) cudaEventDestroy(ctx->prep_event[i]);
         if (ctx->prep2_event[i]) cudaEventDestroy(ctx->prep2_event[i]);
     }
-    if (ctx->pass_a_event) cudaEventDestroy(ctx->pass_a_event);
+    if (ctx->vel_done_event) cudaEventDestroy(ctx->vel_done_event);
     if (ctx->ukf_stream) { cudaStreamSynchronize(ctx->ukf_stream); cudaStreamDestroy(ctx->ukf_stream); }
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -425,15 +459,24 @@ int roftb_join(roftb_ctx* ctx) {
 
 static void prof_collect(roftb_ctx* ctx, int slot) {
     if (!ctx->prof_used[slot]) return;
-    cudaEventSynchronize(ctx->prof_ev[slot][5]);
+    cudaEventSynchronize(ctx->prof_ev[slot][2]);
     cudaEventSynchronize(ctx->prof_ev[slot][7]);
     cudaEventSynchronize(ctx->prof_ev[slot][9]);
-    // phases: prep (worklist + mask plan/init), pass A, select, pass B, epilogue, mask scatter (own stream), UKF (own stream)
-    static const int kE0[7] = {10, 1, 2, 3, 4, 6, 8}, kE1[7] = {0, 2, 3, 4, 5, 7, 9};
-    for (int j = 0; j < 7; ++j) {
+    // event pairs: prep stream (10 -> 0), velocity kernel (1 -> 2), new-mask scatter (6 -> 7), pose UKF (8 -> 9)
+    static const int kE0[4] = {10, 1, 6, 8}, kE1[4] = {0, 2, 7, 9}, kDst[4] = {0, 1, 5, 6};
+    for (int j = 0; j < 4; ++j) {
         float ms = 0.f;
-        const int e0 = kE0[j], e1 = kE1[j];
-        if (cudaEventElapsedTime(&ms, ctx->prof_ev[slot][e0], ctx->prof_ev[slot][e1]) == cudaSuccess) ctx->prof_ms[j] += ms;
+        if (cudaEventElapsedTime(&ms, ctx->prof_ev[slot][kE0[j]], ctx->prof_ev[slot][kE1[j]]) == cudaSuccess) ctx->prof_ms[kDst[j]] += ms;
+    }
+    if (getenv("ROFTB_TIMELINE")) {
+        // start / end of the step's kernels on their streams, relative to the first profiled step (diagnostic)
+        static cudaEvent_t base = nullptr;
+        if (!base) base = ctx->prof_ev[slot][1];
+        float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        static const int ev[8] = {10, 0, 1, 2, 6, 7, 8, 9};
+        for (int j = 0; j < 8; ++j) cudaEventElapsedTime(&t[j], base, ctx->prof_ev[slot][ev[j]]);
+        fprintf(stderr, "[timeline] slot %2d  init+list %.3f-%.3f | velocity %.3f-%.3f | scatter %.3f-%.3f | ukf %.3f-%.3f\n", slot,
+                t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7]);
     }
     ctx->prof_steps++;
     ctx->prof_used[slot] = false;
@@ -443,12 +486,75 @@ int roftb_profile(roftb_ctx* ctx, int32_t enable, double* ms_per_step, int64_t* 
     if (!ctx) return -2;
     CK(cudaSetDevice(ctx->dev));
     for (int i = 0; i < kCtlRing; ++i) prof_collect(ctx, i);
-    if (ms_per_step)
-        for (int j = 0; j < 7; ++j) ms_per_step[j] = ctx->prof_steps ? ctx->prof_ms[j] / (double)ctx->prof_steps : 0.0;
+    if (ms_per_step) {
+        // the velocity kernel is ONE launch: its device time (prof_ms[1]) is split over pass A / select / pass B /
+        // epilogue in proportion to the per-track phase stamps of the last profiled step
+        double ph[4] = {0, 0, 0, 0};
+        if (ctx->prof_steps) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            std::vector<unsigned long long> clk((size_t)ctx->T * 8);
+            CK(cudaMemcpy(clk.data(), ctx->phase_clock, clk.size() * 8, cudaMemcpyDeviceToHost));
+            for (int t = 0; t < ctx->T; ++t) {
+                const unsigned long long* c = &clk[(size_t)t * 8];
+                if (!c[0] || c[7] < c[0]) continue;  // track took no part (or only propagated)
+                ph[0] += (double)(c[2] - c[0]);
+                ph[1] += (double)(c[5] >= c[2] ? c[5] - c[2] : 0);
+                ph[2] += (double)(c[5] >= c[2] ? c[6] - c[5] : c[6] - c[2]);
+                ph[3] += (double)(c[7] - c[6]);
+            }
+        }
+        if (getenv("ROFTB_PHASE_DEBUG") && ctx->prof_steps) {
+            // mean per-track latency of each interval between the phase stamps (ns) and the concurrency available
+            double iv[7] = {0, 0, 0, 0, 0, 0, 0};
+            int nt = 0;
+            std::vector<unsigned long long> clk((size_t)ctx->T * 8);
+            cudaMemcpy(clk.data(), ctx->phase_clock, clk.size() * 8, cudaMemcpyDeviceToHost);
+            unsigned long long first = ~0ull, last = 0;
+            for (int t = 0; t < ctx->T; ++t) {
+                const unsigned long long* c = &clk[(size_t)t * 8];
+                if (!c[0] || c[7] < c[0]) continue;
+                ++nt;
+                for (int j = 0; j < 7; ++j) iv[j] += (c[j + 1] >= c[j] && c[j]) ? (double)(c[j + 1] - c[j]) : 0.0;
+                first = std::min(first, c[0]);
+                last = std::max(last, c[7]);
+            }
+            {
+                std::vector<int32_t> wu(ctx->T);
+                cudaMemcpy(wu.data(), ctx->wl_units, wu.size() * 4, cudaMemcpyDeviceToHost);
+                double tmax = 0, tsum = 0;
+                int umax = 0, umin = 1 << 30, t_of_max = 0;
+                long long usum = 0;
+                for (int t = 0; t < ctx->T; ++t) {
+                    const unsigned long long* c = &clk[(size_t)t * 8];
+                    if (!c[0] || c[7] < c[0]) continue;
+                    const double d = (double)(c[7] - c[0]);
+                    tsum += d;
+                    if (d > tmax) { tmax = d; t_of_max = t; }
+                    umax = std::max(umax, wu[t]); umin = std::min(umin, wu[t]); usum += wu[t];
+                }
+                fprintf(stderr, "[roftb] units per track min %d mean %.0f max %d; track latency mean %.1f us max %.1f us (track %d, %d units)\n",
+                        umin, nt ? (double)usum / nt : 0.0, umax, nt ? tsum / nt * 1e-3 : 0.0, tmax * 1e-3, t_of_max, wu[t_of_max]);
+            }
+            fprintf(stderr, "[roftb] velocity kernel: cluster %d, slots %d, tracks %d, kernel span %.1f us; per-track mean ns:"
+                            " prologue %.0f | passA %.0f | pair %.0f | level1 %.0f | level2 %.0f | passB %.0f | epilogue %.0f\n",
+                    velocity_cluster_size(), ctx->scratch.n_slots, nt, nt ? (double)(last - first) * 1e-3 : 0.0,
+                    iv[0] / std::max(nt, 1), iv[1] / std::max(nt, 1), iv[2] / std::max(nt, 1), iv[3] / std::max(nt, 1),
+                    iv[4] / std::max(nt, 1), iv[5] / std::max(nt, 1), iv[6] / std::max(nt, 1));
+        }
+        const double tot = ph[0] + ph[1] + ph[2] + ph[3];
+        const double n = ctx->prof_steps ? (double)ctx->prof_steps : 1.0;
+        const double vel = ctx->prof_ms[1] / n;
+        ms_per_step[0] = ctx->prof_ms[0] / n;
+        for (int j = 0; j < 4; ++j) ms_per_step[1 + j] = tot > 0 ? vel * ph[j] / tot : (j == 0 ? vel : 0.0);
+        ms_per_step[5] = ctx->prof_ms[5] / n;
+        ms_per_step[6] = ctx->prof_ms[6] / n;
+    }
     if (steps) *steps = ctx->prof_steps;
     if (enable != (ctx->prof_on ? 1 : 0) || enable) {
         for (int j = 0; j < 7; ++j) ctx->prof_ms[j] = 0.0;
         ctx->prof_steps = 0;
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemset(ctx->phase_clock, 0, (size_t)ctx->T * 8 * sizeof(unsigned long long)));
     }
     ctx->prof_on = enable != 0;
     return 0;
@@ -464,7 +570,7 @@ int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mea
     CK(cudaStreamSynchronize(ctx->mask_stream));
     CK(cudaStreamSynchronize(ctx->ukf_stream));
     ctx->mask_event_used = false;
-    ctx->pass_a_event_used = false;
+    ctx->vel_done_event_used = false;
     // ROFTFilter::initialization_step (ROFTFilter.cpp:216-237)
     std::vector<double> pm((size_t)T * 13, 0.0), pc((size_t)T * 144, 0.0), vm((size_t)T * 6, 0.0), vc((size_t)T * 36, 0.0);
     for (int t = 0; t < T; ++t) {
@@ -485,7 +591,21 @@ int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mea
     CK(cudaMemset(ctx->mask_state[1], 0, (size_t)T * ctx->HW));
     CK(cudaMemset(ctx->mask_state[2], 0, (size_t)T * ctx->HW));
     CK(cudaMemset(ctx->fbuf, 0, sizeof(FlowBuf) * T));
-    CK(cudaMemset(ctx->norm_count, 0, sizeof(uint32_t) * T));
+    for (int i = 0; i < 3; ++i) CK(cudaMemset(ctx->mask_occ[i], 0, (size_t)T * ctx->n_units));
+    {
+        // every scratch slot free; the bits past the last slot stay set so they are never handed out
+        std::vector<uint32_t> bm(ctx->scratch.n_slot_words, 0u);
+        for (int b = ctx->scratch.n_slots; b < ctx->scratch.n_slot_words * 32; ++b) bm[b >> 5] |= 1u << (b & 31);
+        CK(cudaMemcpy(ctx->scratch.slot_bitmap, bm.data(), bm.size() * 4, cudaMemcpyHostToDevice));
+    }
+    CK(cudaMemset(ctx->wl_units, 0, sizeof(int32_t) * T));
+    CK(cudaMemset(ctx->wl_pixels, 0, sizeof(int32_t) * T));
+    {
+        std::vector<int32_t> ord((size_t)2 * T);
+        for (int t = 0; t < T; ++t) ord[t] = ord[(size_t)T + t] = t;
+        CK(cudaMemcpy(ctx->vel_order, ord.data(), ord.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemset(ctx->vel_ticket, 0, 4));
+    }
     CK(cudaMemset(ctx->d_count, 0, sizeof(int32_t) * T));
     ctx->mask_cur = 0;
     ctx->frame_idx = 0;
@@ -715,13 +835,17 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
     ctx->ctl_event_used[cslot] = true;
 
     // ---- device work ------------------------------------------------------------------------------
-    // main stream : worklist -> mask plan/init -> velocity passes (the first pass also propagates the mask of
-    //               the tracks that received no new mask) -> 6x6 epilogue
+    // prep stream : mask stats / plan (needs nothing from the other streams), then - behind the previous step's
+    //               velocity kernel and scatter - the initialisation of the destination plane of the tracks whose mask
+    //               is NOT propagated by the velocity kernel, and the worklist of a newly delivered mask
+    // main stream : the velocity kernel: worklist, pass A (+ propagation of the mask of the tracks that received no
+    //               new one), pairing, median select, pass B, 6x6 epilogue - one cluster per track, one launch
     // mask stream : scatter/gather of the tracks with a NEW mask (chained through the buffered flows)
-    // ukf stream  : pose UKF (needs only the twist published by the epilogue and the host-built op list)
+    // ukf stream  : pose UKF (needs only the twist published by the velocity kernel and the host-built op list)
     const uint8_t* seg_prev = ctx->mask_state[ctx->mask_cur];
     uint8_t* seg_next = ctx->mask_state[(ctx->mask_cur + 1) % 3];
-    int32_t* wt_count = ctx->wt_count + (size_t)par * T * ctx->n_units;
+    const uint8_t* occ_prev = ctx->mask_occ[ctx->mask_cur];
+    uint8_t* occ_next = ctx->mask_occ[(ctx->mask_cur + 1) % 3];
     int32_t* wt_list = ctx->wt_list + (size_t)par * T * ctx->n_units;
     int32_t* wt_n = ctx->wt_n + (size_t)par * 2 * T;
     int32_t* nl_count = ctx->nl_count + (size_t)par * T * ctx->n_units;
@@ -735,62 +859,66 @@ int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
     ma.g = ctx->g; ma.ft = ctx->ft; ma.n_tracks = T;
     ma.new_mask = any_new_mask ? d_mask : nullptr; ma.new_stride = mask_stride;
     ma.state_src = seg_prev; ma.state_dst = seg_next; ma.winner = ctx->winner;
+    ma.occ_src = occ_prev; ma.occ_dst = occ_next;
     ma.ctl = d_wctl; ma.stat = ctx->stat; ma.plan = plan; ma.fbuf = ctx->fbuf;
     ma.segm_delay = cfg.segm_delay;
     ma.s_list = wt_list; ma.s_n = wt_n; ma.n_list = nl_list; ma.n_n = nl_n; ma.n_warp_tiles = ctx->n_units;
     ma.fuse = 1;
     {
-        // prep stream: everything that only needs the mask state of this step (complete once the previous step's
-        // pass A and new-mask scatter are done) - it overlaps the previous step's select / pass B / epilogue.
-        // Worklists, plans and the mask planes are multi-buffered so nothing still being read is overwritten.
         cudaStream_t ps = ctx->prep_stream;
-        if (ctx->pass_a_event_used) CK(cudaStreamWaitEvent(ps, ctx->pass_a_event, 0));
+        // worklist of a newly delivered mask; the same read gathers the statistics the plan needs
+        if (any_new_mask && launch_tile_list(d_mask, mask_stride, 0, ctx->g.HW, T, nl_count, nl_list, nl_n,
+                                             reinterpret_cast<const int32_t*>(d_wctl), (int)(sizeof(WarpCtl) / 4), ps, ctx->stat))
+            return fail(ctx, "launch_tile_list failed");
+        if (launch_mask_plan(ma, ps, true)) return fail(ctx, "launch_mask_plan failed");
+        CK(cudaEventRecord(ctx->prep_event[par], ps));  // the velocity kernel only needs the plan
+        // the planes this step initialises were last read by the previous step; a copied state was written by it
+        if (ctx->vel_done_event_used) CK(cudaStreamWaitEvent(ps, ctx->vel_done_event, 0));
         if (ctx->mask_event_used) CK(cudaStreamWaitEvent(ps, ctx->mask_event, 0));
         if (pe) CK(cudaEventRecord(pe[10], ps));
-        if (launch_tile_list(seg_prev, (long long)ctx->HW, 1, ctx->g.HW, T, wt_count, wt_list, wt_n, nullptr, 0, ps))
-            return fail(ctx, "launch_tile_list failed");
-        if (launch_mask_plan_init(ma, ps)) return fail(ctx, "launch_mask_plan_init failed");
-        // the velocity chain needs the worklist, the plan and the zeroed plane; the worklist of a NEW mask only feeds the
-        // scatter on the mask stream, so it goes behind the event the main stream waits for
-        CK(cudaEventRecord(ctx->prep_event[par], ps));
-        if (any_new_mask && launch_tile_list(d_mask, mask_stride, 0, ctx->g.HW, T, nl_count, nl_list, nl_n,
-                                             reinterpret_cast<const int32_t*>(d_wctl), (int)(sizeof(WarpCtl) / 4), ps))
-            return fail(ctx, "launch_tile_list failed");
+        if (launch_mask_init(ma, ps)) return fail(ctx, "launch_mask_init failed");
         if (pe) CK(cudaEventRecord(pe[0], ps));
         CK(cudaEventRecord(ctx->prep2_event[par], ps));
     }
+    CK(cudaStreamWaitEvent(s, ctx->prep_event[par], 0));
+    if (ctx->mask_event_used) CK(cudaStreamWaitEvent(s, ctx->mask_event, 0));  // the previous step's scatter wrote seg_prev
     {
         cudaStream_t ms = ctx->mask_stream;
         CK(cudaStreamWaitEvent(ms, ctx->prep2_event[par], 0));
         if (pe) CK(cudaEventRecord(pe[6], ms));
+        // worklist of the state mask for the (rare) tracks that propagate a mixed-valued mask outside the velocity kernel
+        if (launch_flag_list(occ_prev, ctx->n_units, T, wt_list, wt_n, plan, ms)) return fail(ctx, "launch_flag_list failed");
         if (launch_mask_scatter_gather(ma, ms)) return fail(ctx, "launch_mask_scatter_gather failed");
         if (pe) CK(cudaEventRecord(pe[7], ms));
         CK(cudaEventRecord(ctx->mask_event, ms));
         ctx->mask_event_used = true;
         ctx->mask_cur = (ctx->mask_cur + 1) % 3;
     }
-    CK(cudaStreamWaitEvent(s, ctx->prep_event[par], 0));
     {
         VelocityArgs a;
         memset(&a, 0, sizeof(a));
         a.g = ctx->g; a.ft = ctx->ft; a.n_tracks = T;
         a.seg = seg_prev; a.seg_stride = (long long)ctx->HW; a.thr = 1;  // cv::threshold(> 1) applied on load
+        a.occ_src = occ_prev;
         a.ctl = ctx->d_vctl; a.weight_flow = cfg.weight_flow;
-        a.wt_count = wt_count; a.wt_list = wt_list; a.wt_n = wt_n; a.norms = ctx->norms; a.norm_count = ctx->norm_count; a.hist = ctx->hist;
-        a.sel = ctx->sel; a.wp = ctx->wp; a.partials = ctx->partials; a.max_blocks = ctx->max_blocks;
+        a.scratch = ctx->scratch;
         a.v_mean = ctx->v_mean; a.v_cov = ctx->v_cov; a.q_diag = ctx->q_diag;
         a.r_flow[0] = cfg.cov_flow[0]; a.r_flow[1] = cfg.cov_flow[1];
         a.fx = cfg.fx; a.fy = cfg.fy; a.cx = cfg.cx; a.cy = cfg.cy;
         a.accum_fp64 = cfg.accum_fp64;
         a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
         a.out_count = ctx->d_count; a.out_lambda = ctx->d_lambda; a.out_eta = ctx->d_eta;
+        a.wl_units = ctx->wl_units; a.wl_pixels = ctx->wl_pixels;
+        a.phase_clock = pe ? ctx->phase_clock : nullptr;
+        a.order = ctx->vel_order + (size_t)par * T; a.order_next = ctx->vel_order + (size_t)(par ^ 1) * T;
+        a.done_ticket = ctx->vel_ticket;
         a.update_state = 1;
-        a.fuse_scatter = 1; a.plan = plan; a.state_dst = seg_next; a.winner = ctx->winner;
-        a.prof = pe;
-        a.ev_first_pass = ctx->pass_a_event;
-        a.aux_stream = ctx->aux_stream; a.aux_fork = ctx->aux_fork; a.aux_join = ctx->aux_join;
-        ctx->pass_a_event_used = true;
+        a.fuse_scatter = 1; a.plan = plan; a.state_dst = seg_next; a.occ_dst = occ_next;
+        if (pe) CK(cudaEventRecord(pe[1], s));
         if (launch_velocity(a, s)) return fail(ctx, "launch_velocity failed");
+        if (pe) CK(cudaEventRecord(pe[2], s));
+        CK(cudaEventRecord(ctx->vel_done_event, s));
+        ctx->vel_done_event_used = true;
         CK(cudaEventRecord(ctx->vel_event[cslot], s));
     }
     {
@@ -873,9 +1001,8 @@ int roftb_get_worklist(roftb_ctx* ctx, int32_t* units, int32_t* pixels) {
     const size_t T = ctx->T;
     CK(cudaSetDevice(ctx->dev));
     cudaStream_t s = ctx->stream;
-    const int32_t* wt_n = ctx->wt_n + (size_t)((ctx->frame_idx - 1) & 1) * 2 * T;  // (units[T], pixels[T]) of the last step
-    if (units) CK(cudaMemcpyAsync(units, wt_n, T * 4, cudaMemcpyDeviceToHost, s));
-    if (pixels) CK(cudaMemcpyAsync(pixels, wt_n + T, T * 4, cudaMemcpyDeviceToHost, s));
+    if (units) CK(cudaMemcpyAsync(units, ctx->wl_units, T * 4, cudaMemcpyDeviceToHost, s));
+    if (pixels) CK(cudaMemcpyAsync(pixels, ctx->wl_pixels, T * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return 0;
 }
@@ -952,6 +1079,7 @@ int roftb_mask_sync(roftb_ctx* ctx, int32_t n_masks, const uint8_t* mask, const 
     a.ft.flow_stride = (long long)ctx->flow_elems;
     a.new_mask = d_mask; a.new_stride = (long long)HW;
     a.state_src = d_mask; a.state_dst = d_out; a.winner = d_win; a.plan = d_plan;
+    a.occ_src = nullptr; a.occ_dst = nullptr;
     {
         const int nwt = ctx->n_units;
         int32_t* cnt = tb.alloc<int32_t>(N * nwt);
@@ -1000,17 +1128,15 @@ static int velocity_operator(roftb_ctx* ctx, int32_t n, const uint8_t* mask, con
     a.ft.depth[0] = d_depth; a.ft.flow[0] = d_flow;
     a.ft.depth_stride = (long long)HW; a.ft.flow_stride = (long long)ctx->flow_elems;
     a.seg = d_mask; a.seg_stride = (long long)HW; a.thr = 0;  // previous_segmentation_ is used through findNonZero
+    uint8_t* d_occ = tb.alloc<uint8_t>(N * nwt);
+    a.occ_src = d_occ;
     a.ctl = d_ctl; a.weight_flow = ctx->cfg.weight_flow;
-    a.wt_count = tb.alloc<int32_t>(N * nwt);
-    a.wt_list = tb.alloc<int32_t>(N * nwt);
-    a.wt_n = tb.alloc<int32_t>(2 * N);
-    a.norms = tb.alloc<float>(N * (size_t)nwt * kUnitPx);
-    a.norm_count = tb.alloc<uint32_t>(N, true);
-    a.hist = tb.alloc<uint32_t>(N * kSelBins, true);
-    a.sel = tb.alloc<SelState>(N, true);
-    a.wp = tb.alloc<WeightParams>(N, true);
-    a.max_blocks = ctx->max_blocks;
-    a.partials = tb.alloc<double>(N * a.max_blocks * kNAcc);
+    // the scratch pool of the context (this operator runs on the context's main stream); per-item arrays are sized here
+    a.scratch = ctx->scratch;
+    a.scratch.track_slot = tb.alloc<int32_t>(N);
+    a.scratch.chunk_aux = tb.alloc<int32_t>(N * kVtMaxChunks);
+    a.scratch.part = tb.alloc<double>(N * kVtMaxCluster * kVtPartN);
+    a.scratch.track_sel = tb.alloc<double>(N * 4);
     a.v_mean = d_x; a.v_cov = d_P; a.q_diag = ctx->q_diag;
     a.r_flow[0] = ctx->cfg.cov_flow[0]; a.r_flow[1] = ctx->cfg.cov_flow[1];
     a.fx = ctx->cfg.fx; a.fy = ctx->cfg.fy; a.cx = ctx->cfg.cx; a.cy = ctx->cfg.cy;
@@ -1020,12 +1146,11 @@ static int velocity_operator(roftb_ctx* ctx, int32_t n, const uint8_t* mask, con
     a.out_eta = tb.alloc<double>(N * 6);
     a.update_state = update ? 1 : 0;
     a.x_pred_override = d_xp;
-    if (!d_mask || !d_depth || !d_flow || !d_ctl || !d_x || !d_P || !a.wt_count || !a.norms || !a.norm_count || !a.hist ||
-        !a.sel || !a.wp || !a.partials || !a.out_count || !a.out_lambda || !a.out_eta)
+    if (!d_mask || !d_depth || !d_flow || !d_ctl || !d_x || !d_P || !d_occ || !a.scratch.track_slot || !a.scratch.chunk_aux ||
+        !a.scratch.part || !a.scratch.track_sel ||
+        !a.out_count || !a.out_lambda || !a.out_eta)
         return fail(ctx, "velocity operator: out of device memory");
-    if (!a.wt_list || !a.wt_n) return fail(ctx, "velocity operator: out of device memory");
-    if (launch_tile_list(d_mask, (long long)HW, 0, ctx->g.HW, (int)N, a.wt_count, a.wt_list, a.wt_n, nullptr, 0, s))
-        return fail(ctx, "launch_tile_list failed");
+    if (launch_unit_flags(d_mask, (long long)HW, ctx->g.HW, (int)N, d_occ, s)) return fail(ctx, "launch_unit_flags failed");
     if (launch_velocity(a, s)) return fail(ctx, "launch_velocity failed");
     if (update && x) CK(cudaMemcpyAsync(x, d_x, N * 6 * 8, cudaMemcpyDeviceToHost, s));
     if (update && P) CK(cudaMemcpyAsync(P, d_P, N * 36 * 8, cudaMemcpyDeviceToHost, s));

@@ -15,14 +15,20 @@ constexpr int kThreads = 256;                // streaming kernels: 8 warps
 constexpr int kWarpTilePx = 512;             // extract kernels: one warp covers 4 sub-tiles of 128 px
 constexpr int kUnitPx = 128;                 // worklist granularity: 128 consecutive px = one quad per lane of a warp
 constexpr int kBlockTilePx = kThreads / 32 * kWarpTilePx;  // 4096 px
-// accumulators of the flow->velocity normal equations:
+// velocity kernel (velocity_track.cu): one cluster of up to kVtMaxCluster CTAs of kVtThreads threads per track
+constexpr int kVtThreads = 256;
+constexpr int kVtMaxCluster = 16;
+constexpr int kVtMaxChunks = kVtMaxCluster * (kVtThreads / 32);   // one chunk of the unit list per warp
+// per-CTA partials of the flow->velocity normal equations:
 //   S1 = sum l L1^T L1 over index set {0,2,3,4,5} (15 upper-triangular entries)
 //   S2 = sum l L2^T L2 over index set {1,2,3,4,5} (15)
-//   g1 = sum l L1^T dx (5), g2 = sum l L2^T dy (5), count (1)
-constexpr int kNAcc = 41;
-constexpr int kAutoFp64Candidates = 32768;   // accum_fp64 == 2: tracks with fewer candidate pixels accumulate in FP64
+//   g1 = sum l L1^T nu1 (5), g2 = sum l L2^T nu2 (5), count (1), min |n - m| (1)
+constexpr int kVtPartN = 42;
+constexpr int kAutoFp64Candidates = 32768;   // accum_fp64 == 2: tracks with fewer valid pixels accumulate in FP64
 constexpr int kSelBins = 4096;               // radix-select histogram bins per level
-constexpr int kMaxUkfOps = 2 * (ROFTB_MAX_DELAY + 2) + 2;
+// buffered velocities are capped at ROFTB_MAX_DELAY + 3 on the host: swap + (predict, correct) per buffered entry
+constexpr int kMaxUkfBuffered = ROFTB_MAX_DELAY + 3;
+constexpr int kMaxUkfOps = 2 * kMaxUkfBuffered + 2;
 
 // ---- geometry / format of one batch of planes ----------------------------------------------
 struct Geom {
@@ -92,24 +98,23 @@ struct VelCtl {            // host-built, one per track per step
     double dt;
 };
 
-struct WeightParams {      // Laplacian re-weighting parameters (SKFCorrection.cpp:91-116)
-    float m, inv_b, coef, inv_lmax;
-    int32_t use;           // b > 1e-4
-    int32_t n;             // number of valid measurements
-    int32_t pad[2];
-};
-
-struct SelState {          // radix-select state (upper median = s[n/2])
-    uint32_t prefix;       // key bits fixed so far
-    uint32_t k;            // remaining rank inside the prefix
-    uint32_t n;            // valid measurements
-    uint32_t n_entries;    // norm slots (valid + gated-out)
-    // statistics gathered by the last pass
-    unsigned long long less_cnt;
-    double less_sum;
-    double total_sum;
-    uint32_t less_max_bits;
-    uint32_t pad2;
+// pool of scratch slots of the velocity kernel: a cluster claims one while it processes a track.  All of it is
+// written and re-read within one kernel by the same cluster and overwritten in place by later tracks (L2-resident).
+struct VelScratch {
+    float2* nu;             // [S][cap] innovations (nu1, nu2) of the valid pixels, compacted per chunk, selection order
+    uint2* dp;              // [S][cap] (depth bits, v << 16 | u) of the same pixels
+    float* r;               // [S][cap] column-major pair norms r_i = |(nu[i], nu[N+i])| (SKFCorrection.cpp:93-94), compact
+    long long cap;          // entries per slot (n_units * 128 + padding; a multiple of 4)
+    uint32_t* hist;         // [S][3][kSelBins] radix-select histograms, one per level
+    int32_t* chunk_cnt;     // [S][kVtMaxChunks] valid pixels per chunk
+    double* part;           // [T][kVtMaxCluster][kVtPartN] per-CTA partial sums of pass B (per track: read by the epilogue kernel)
+    double* track_sel;      // [T][4] (weights in use, b, valid pixels, CTAs) handed to the epilogue kernel
+    double* sel_part;       // [S][kVtMaxCluster][4] per-CTA select statistics
+    uint32_t* slot_bitmap;  // allocation bitmap (bits >= n_slots are pre-set)
+    int n_slot_words;
+    int n_slots;
+    int32_t* track_slot;    // [T] slot claimed for a track (rank 0 -> the other CTAs)
+    int32_t* chunk_aux;     // [T][kVtMaxChunks] candidate pixels per chunk (stride > 1)
 };
 
 // ---- pose UKF -----------------------------------------------------------------------------
@@ -144,11 +149,16 @@ struct MaskSyncArgs {
     // worklists (launch_tile_list) of the state mask and of the newly delivered mask
     const int32_t* s_list; const int32_t* s_n;
     const int32_t* n_list; const int32_t* n_n;
-    int n_warp_tiles;
+    int n_warp_tiles;      // 128-px units per plane
     int fuse;              // allow k_warp_plan to hand single-flow propagation to the velocity pass
+    // occupancy flags [T][n_units] of the two state planes (may be null in operator mode)
+    const uint8_t* occ_src; uint8_t* occ_dst;
 };
 // the mask synchronisation in two halves: (stats, plan, init) must precede a fused velocity pass; (scatter of the
 // non-fused tracks, gather) may run concurrently with the velocity passes
+// stats of a new mask (unless the caller gathered them with launch_tile_list) + the per-track plan
+int launch_mask_plan(const MaskSyncArgs& a, cudaStream_t s, bool have_stats = false);
+int launch_mask_init(const MaskSyncArgs& a, cudaStream_t s);   // destination plane / winner plane / flags of the non-fused tracks
 int launch_mask_plan_init(const MaskSyncArgs& a, cudaStream_t s, bool planned = false);
 int launch_mask_scatter_gather(const MaskSyncArgs& a, cudaStream_t s);
 // planned = true: a.plan was filled by the caller (operator mode), skip the stats / plan kernels
@@ -160,44 +170,43 @@ struct VelocityArgs {
     FrameTable ft;
     int n_tracks;
     const uint8_t* seg; long long seg_stride; int thr;   // selected iff byte > thr
+    const uint8_t* occ_src;                               // [T][n_units] occupancy flags of seg (1: the unit holds a non-zero byte)
     const VelCtl* ctl;                                    // device
     int weight_flow;
-    // scratch
-    int32_t* wt_count;      // [T][n_units] row-major rank base of each 128-px unit      } built by
-    int32_t* wt_list;       // [T][n_units] non-empty units of the mask                  } launch_tile_list
-    int32_t* wt_n;          // [2T] their number, then the candidate totals              }
-    float* norms;           // [T][HW]
-    uint32_t* norm_count;   // [T]
-    uint32_t* hist;         // [T][kSelBins]
-    SelState* sel;          // [T]
-    WeightParams* wp;       // [T]
-    double* partials;       // [T][max_blocks][kNAcc]
-    int max_blocks;
+    VelScratch scratch;
     // state
     double* v_mean; double* v_cov;     // [T][6], [T][36]
     const double* q_diag;              // [6] process noise (device)
     double r_flow[2];
     double fx, fy, cx, cy;
-    int accum_fp64;                    // pass B per-pixel terms and sums in FP64 (else FP32)
+    int accum_fp64;                    // pass B per-pixel terms and sums in FP64 (else FP32 terms)
     double* vel_hist; int hist_ring;   // [T][ring][6]
     // diagnostics
     int32_t* out_count; double* out_lambda; double* out_eta;  // device [T], [T][36], [T][6]
-    // fused mask propagation (see WarpPlan::fused)
-    int fuse_scatter; const WarpPlan* plan; uint8_t* state_dst; int32_t* winner;
-    cudaStream_t aux_stream;           // optional: the FP64 small-track variant of pass B runs here, beside the FP32 one
-    cudaEvent_t aux_fork, aux_join;
-    cudaEvent_t ev_first_pass;         // optional: recorded right after the first streaming pass (the one that also
-                                       // propagates the mask): the next step's worklist may be built from then on
-    cudaEvent_t* prof;                 // optional: 6 events recorded at the phase boundaries (start, rank, pass A,
-                                       // select, pass B, epilogue)
+    int32_t* wl_units; int32_t* wl_pixels;                    // device [T]: listed units, candidate pixels (may be null)
+    // largest-first scheduling (may be null): clusters take the tracks in `order`; the last cluster to finish writes
+    // `order_next` from wl_units for the following step; done_ticket is a zero-initialised counter
+    const int32_t* order; int32_t* order_next; uint32_t* done_ticket;
+    unsigned long long* phase_clock;                          // device [T][8] globaltimer stamps at the phase boundaries (may be null)
+    // fused mask propagation (see WarpPlan::fused): destination plane and its occupancy flags
+    int fuse_scatter; const WarpPlan* plan; uint8_t* state_dst; uint8_t* occ_dst;
     int update_state;                  // 0: only compute lambda/eta/count (operator mode)
-    const double* x_pred_override;     // operator mode: [T][6] predicted mean for the norms (else v_mean)
+    const double* x_pred_override;     // operator mode: [T][6] predicted mean for the innovations (else v_mean)
 };
 int launch_velocity(const VelocityArgs& a, cudaStream_t s);
+// per-device set-up of the velocity kernel (shared-memory opt-in, cluster attributes); returns the number of clusters
+// that can be resident at once = the number of scratch slots worth allocating
+int velocity_prepare_device(const Geom& g, int n_units, int* max_active_clusters);
+int velocity_cluster_size();
+// occupancy flags of a plane that comes from outside, and the list of flagged units
+int launch_unit_flags(const uint8_t* plane, long long stride, int HW, int n_items, uint8_t* flags, cudaStream_t s);
+int launch_flag_list(const uint8_t* flags, int n_units, int n_items, int32_t* wt_list, int32_t* wt_n, const WarpPlan* plan,
+                     cudaStream_t s);
 // worklist of the non-empty 128-px units of a byte plane (+ rank base of the bytes > thr); active: optional per-item
 // flags, item i is processed iff active[i * active_stride] != 0
+// stat (optional): non-zero count / min / max of every processed plane, accumulated in the same read
 int launch_tile_list(const uint8_t* plane, long long stride, int thr, int HW, int n_items, int32_t* wt_count, int32_t* wt_list,
-                     int32_t* wt_n, const int32_t* active, int active_stride, cudaStream_t s);
+                     int32_t* wt_n, const int32_t* active, int active_stride, cudaStream_t s, MaskStat* stat = nullptr);
 // per-warp-tile exclusive prefix of the number of pixels with byte > thr (row-major rank base); ctl may be null
 int launch_mask_rank(const uint8_t* seg, long long seg_stride, int thr, int HW, int n_items, int32_t* wt_count, int32_t* total,
                      const VelCtl* ctl, cudaStream_t s);

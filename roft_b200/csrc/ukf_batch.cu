@@ -463,9 +463,10 @@ __device__ void ukf_correct_warp(UkfSmem& s, const UkfParams& p, int mtype, cons
     __syncwarp();
 }
 
-// kUkfWarps tracks per block (one warp each, nothing shared between them): the latency-bound warps then sit on fewer
-// SMs, where they take register-file space from the streaming kernels of the other streams
-constexpr int kUkfWarps = 4;
+// One track (one warp) per block: 27 KB of shared memory and 32 threads - small enough to be resident BESIDE the two
+// CTAs per SM of the velocity kernel (which leaves a quarter of the registers and a third of the shared memory free),
+// so the latency-bound pose filter runs in the issue slots the streaming kernel leaves idle instead of after it.
+constexpr int kUkfWarps = 1;
 struct UkfWarpSmem { UkfSmem s; double meas[16]; };
 
 __global__ void __launch_bounds__(32 * kUkfWarps) k_ukf_batch(UkfArgs a) {
@@ -521,12 +522,8 @@ __global__ void __launch_bounds__(32 * kUkfWarps) k_ukf_batch(UkfArgs a) {
 }  // namespace
 
 int launch_ukf(const UkfArgs& a, cudaStream_t s) {
-    static bool attr_done = false;
-    const int smem = (int)sizeof(UkfWarpSmem) * kUkfWarps;
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_ukf_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_done = true;
-    }
+    const int smem = (int)sizeof(UkfWarpSmem) * kUkfWarps;  // (below the 48 KB that need no opt-in)
+    static_assert(sizeof(UkfWarpSmem) * kUkfWarps <= 48 * 1024, "k_ukf_batch would need the shared-memory opt-in per device");
     ROFTB_LAUNCH(k_ukf_batch, (a.n_tracks + kUkfWarps - 1) / kUkfWarps, 32 * kUkfWarps, smem, s, a);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
