@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ROFTB_VERSION 1
+#define ROFTB_VERSION 2
 
 /* flow formats: the two cv::Mat types ROFT accepts (ImageOpticalFlowSource.h:44-45) */
 #define ROFTB_FLOW_F32 13 /* CV_32FC2: float2 per element, grid 1, scale 1            */
@@ -73,7 +73,6 @@ typedef struct roftb_config {
     int32_t segm_delay;              /* int(original_fps / desired_fps) of segmentation_dataset    */
     int32_t pose_delay;              /* same for pose_dataset                                      */
     int32_t device;                  /* CUDA device ordinal                                        */
-    int32_t use_cuda_graph;          /* reserved                                                   */
     int32_t accum_fp64;              /* precision of the per-pixel Jacobian terms / normal-equation sums:
                                         1: FP64; 0: FP32 terms, FP64 reduction (agreement with the FP64 reference then
                                         scales as cond(Lambda)*6e-8/sqrt(N)); 2 (default): FP64 for tracks with fewer
@@ -84,8 +83,14 @@ typedef struct roftb_config {
  * ROFTFilter::filtering_step (ROFTFilter.cpp:255-367).  Image pointers are host or device
  * memory according to `memory`; the small per-track arrays are ALWAYS host memory.
  * With ROFTB_MEM_DEVICE the depth plane must stay valid and unmodified for 1 further step and
- * the flow plane for max(segm_delay,1) further steps (the reference clones them instead:
- * ImageOpticalFlowMeasurement.hpp:286, ImageSegmentationOFAidedSource.hpp:208). */
+ * the flow plane for segm_delay further steps - ROFTB_MAX_DELAY further steps when segm_delay <= 0
+ * (delay unknown: every flow since the last mask is chained) - (the reference clones them instead:
+ * ImageOpticalFlowMeasurement.hpp:286, ImageSegmentationOFAidedSource.hpp:208).
+ * Two buffers that are unbounded in the reference are bounded here: at most ROFTB_MAX_DELAY flows
+ * are chained behind a new mask (with segm_delay <= 0 the oldest are dropped when more accumulate
+ * between two masks), and at most ROFTB_MAX_DELAY + 3 buffered velocities are replayed by a pose
+ * re-synchronisation (CartesianQuaternionMeasurement.cpp:100-104 trims to pose_delay + 1 anyway;
+ * the cap only matters for pose_delay <= 0). */
 typedef struct roftb_frame {
     int32_t memory;
     const float* depth;              /* [n_tracks][H][W] metres (CameraMeasurement.h:57)            */
@@ -115,19 +120,23 @@ int roftb_version(void);
 int64_t roftb_kernel_launches(const roftb_ctx* ctx);
 /* CUDA stream the kernels are enqueued on (cudaStream_t as void*), for event timing */
 void* roftb_stream(roftb_ctx* ctx);
-/* Device-side phase timing of roftb_filter_step with CUDA events on that stream.  Reads the averages
- * (ms per step since profiling was enabled) of the 7 phases {prep (tile worklist + mask plan/init), flow
- * pass A (innovation norms + fused mask propagation), median select, flow pass B (normal equations), 6x6
- * epilogue, new-mask scatter (own stream), pose UKF (own stream)} into
- * ms_per_step[7] / steps (either may be NULL), then enables (1) or disables (0) profiling; enabling
- * resets the averages. */
+/* Device-side phase timing of roftb_filter_step with CUDA events.  Reads the averages (ms per step since
+ * profiling was enabled) of 7 phases into ms_per_step[7] / steps (either may be NULL), then enables (1) or
+ * disables (0) profiling; enabling resets the averages.  Phases: {preparation of the tracks with a new mask
+ * (plane initialisation; prep stream), then the velocity kernel's device time split over its four stages in
+ * proportion to per-track time stamps taken inside the kernel - worklist + pass A (gates, innovations, fused
+ * mask propagation), pairing + median select, pass B (normal equations), kernel tail -, new-mask scatter
+ * (own stream), pose UKF (own stream)}. */
 int roftb_profile(roftb_ctx* ctx, int32_t enable, double* ms_per_step, int64_t* steps);
 
 /* ---- the filter loop: ROFTFilter::initialization_step / filtering_step ----------------- */
 /* ROFTFilter.cpp:216-237.  p_mean0: host [n_tracks][13] or NULL (zeros, q = identity);
  * v_mean0: host [n_tracks][6] or NULL. */
 int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mean0);
-/* ROFTFilter.cpp:255-367 for every track; asynchronous (returns once work is enqueued). */
+/* ROFTFilter.cpp:255-367 for every track; asynchronous (returns once work is enqueued).
+ * Argument errors (< 0) leave the context untouched; a CUDA failure in the middle of a step leaves the
+ * per-track state machines ahead of the device work, so every later step fails until
+ * roftb_filter_init() is called again. */
 int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* frame);
 /* Blocking read-back of the beliefs (any pointer may be NULL): pose mean [T][13], pose
  * covariance [T][144], velocity mean [T][6], velocity covariance [T][36]. */

@@ -45,7 +45,7 @@ class RoftbConfig(C.Structure):
         ("ut_alpha", C.c_double), ("ut_beta", C.c_double), ("ut_kappa", C.c_double),
         ("use_pose", C.c_int32), ("use_pose_resync", C.c_int32), ("use_velocity", C.c_int32), ("flow_aided", C.c_int32),
         ("segm_delay", C.c_int32), ("pose_delay", C.c_int32),
-        ("device", C.c_int32), ("use_cuda_graph", C.c_int32), ("accum_fp64", C.c_int32),
+        ("device", C.c_int32), ("accum_fp64", C.c_int32),
     ]
 
 

@@ -23,7 +23,7 @@
 
 namespace roftb {
 
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 
 namespace {
 

@@ -63,6 +63,7 @@ struct roftb_ctx {
     bool mask_event_used = false;
     std::string err;
     long long launches0 = 0;
+    bool poisoned = false;  // a hard error inside roftb_filter_step left the host state machines ahead of the device
 
     // device state
     uint8_t* mask_state[3] = {nullptr, nullptr, nullptr};  // ring of 3: step k reads [k%3], writes [(k+1)%3]
@@ -215,7 +216,7 @@ void roftb_config_default(roftb_config* c) {
 
 const char* roftb_last_error(const roftb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-int64_t roftb_kernel_launches(const roftb_ctx* ctx) { return ctx ? (int64_t)(g_launch_count - ctx->launches0) : 0; }
+int64_t roftb_kernel_launches(const roftb_ctx* ctx) { return ctx ? (int64_t)(g_launch_count.load() - ctx->launches0) : 0; }
 
 void* roftb_stream(roftb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
@@ -609,6 +610,7 @@ int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mea
     CK(cudaMemset(ctx->d_count, 0, sizeof(int32_t) * T));
     ctx->mask_cur = 0;
     ctx->frame_idx = 0;
+    ctx->poisoned = false;
     ctx->th.assign(T, TrackHost());  // segmentation_->reset() etc.
     return 0;
 }
@@ -651,8 +653,22 @@ static int stage_host_frame(roftb_ctx* ctx, const roftb_frame* f, int slot, cons
     return 0;
 }
 
+// A hard (< 0) error after the host state machines have advanced leaves them ahead of the device work: the context is
+// marked and every later step fails until roftb_filter_init() re-synchronises both sides.
+static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f);
+
 int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
     if (!ctx || !f) return -2;
+    if (ctx->poisoned) return fail(ctx, "roftb_filter_step: a previous step failed; call roftb_filter_init first");
+    const long long idx0 = ctx->frame_idx;
+    const int rc = filter_step_impl(ctx, f);
+    if (rc < 0 && ctx->frame_idx == idx0 && ctx->err.find("roftb_filter_step:") != 0 && ctx->err.find("device planes") != 0 &&
+        ctx->err.find("track strides") != 0)
+        ctx->poisoned = true;  // (argument errors are reported before anything is touched)
+    return rc;
+}
+
+static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
     if (!f->depth) return fail(ctx, "roftb_filter_step: depth is required (ROFTFilter.cpp:261-266 tears down without it)");
     const int T = ctx->T;
     const roftb_config& cfg = ctx->cfg;

@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "roft_b200.h"
 
 namespace roftb {
@@ -239,7 +241,7 @@ int launch_masked_depth_l1(const SelectArgs& a, const float* rendered, long long
                            double* err_sum, int32_t* samples, cudaStream_t s);
 
 // number of kernel launches issued through ROFTB_LAUNCH (for bench.py "gpu_launches")
-extern long long g_launch_count;
+extern std::atomic<long long> g_launch_count;
 
 }  // namespace roftb
 

@@ -348,6 +348,75 @@ def test_full_resolution_filter_loop_vs_sequential_cpp(api, accum):
             assert rel(pm[t, :9], epm[:9]) < TOL and quat_close(pm[t, 9:], epm[9:]) < TOL, (accum, k, t)
 
 
+@pytest.mark.parametrize("fmt,stride,coverage,delay", [("f32", 1, 0.45, 4), ("s16", 35, 0.25, 6), ("f32", 35, 0.25, 6)])
+def test_full_resolution_baseline_configs(api, fmt, stride, coverage, delay):
+    """1280x720 at the parameters of BASELINE configs[4] (large masks >= 40 % of the frame, 4-frame mask-sync delay) and
+    at the reference's own defaults (test/test.sh:63 nvof_1_slow = CV_16SC2 on a 4-px grid; config_fast_ycb.cfg:83
+    subsampling_radius 35): the whole filter loop against the sequential C++ restatement, through two mask deliveries."""
+    import cpu_ref
+    cfg = o.RoftConfig(subsampling_radius=float(stride), segm_delay=delay, pose_delay=delay,
+                       flow_grid=1 if fmt == "f32" else 4, flow_scale=1.0 if fmt == "f32" else 32.0)
+    T, F = 2, 2 * delay + 2
+    seq = sequence(cfg, T, F, target_coverage=coverage, flow_format=fmt)
+    assert float((seq.mask[0] > 0).float().mean()) > 0.9 * coverage - 0.05
+    x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
+    trk = api.Tracker(to_roftb_config(cfg, T, fmt))
+    trk.init(x0)
+    refs = [cpu_ref.CFilter(cfg, x0[t]) for t in range(T)]
+    for k in range(F):
+        frs = [frame_inputs(seq, cfg, k, t) for t in range(T)]
+        mask = np.stack([f.mask for f in frs]) if frs[0].mask is not None else None
+        pose = np.stack([f.pose if f.pose is not None else np.zeros(7) for f in frs])
+        pv = np.array([f.pose is not None for f in frs], np.uint8)
+        flow = np.stack([f.flow for f in frs]) if k > 0 else None
+        trk.step(np.stack([f.depth for f in frs]), flow, mask, pose=pose, pose_valid=pv)
+        pm, vm = trk.state()
+        raw, thr = trk.mask()
+        cnt, _, _ = trk.velocity_info()
+        for t in range(T):
+            refs[t].step(frs[t].depth, frs[t].flow, frs[t].mask, frs[t].pose, frs[t].dt)
+            epm, _, evm, _, en = refs[t].state()
+            eraw, ethr = refs[t].mask()
+            assert np.array_equal(raw[t], eraw) and np.array_equal(thr[t], ethr), (k, t)
+            assert cnt[t] == en, (k, t, cnt[t], en)
+            assert rel(vm[t], evm) < TOL or np.linalg.norm(vm[t] - evm) < 1e-9, (fmt, stride, k, t, rel(vm[t], evm))
+            assert rel(pm[t, :9], epm[:9]) < TOL and quat_close(pm[t, 9:], epm[9:]) < TOL, (fmt, stride, k, t)
+
+
+def test_batch_of_many_tracks_matches_single_track_runs(api):
+    """The batch is only a batch: 24 tracks stepped together (several clusters in flight, scratch slots reused, tracks
+    scheduled largest first) give bit-identical beliefs and masks to the same tracks stepped one context at a time."""
+    cfg = small_cfg(subsampling_radius=1.0, segm_delay=3, pose_delay=3)
+    T, F = 24, 9
+    seq = sequence(cfg, T, F)
+    x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
+
+    def run(tracks):
+        n = len(tracks)
+        trk = make_tracker(api, cfg, n)
+        trk.init(x0[tracks])
+        outs = []
+        for k in range(F):
+            frs = [frame_inputs(seq, cfg, k, t) for t in tracks]
+            mask = np.stack([f.mask for f in frs]) if frs[0].mask is not None else None
+            pose = np.stack([f.pose if f.pose is not None else np.zeros(7) for f in frs])
+            pv = np.array([f.pose is not None for f in frs], np.uint8)
+            trk.step(np.stack([f.depth for f in frs]), np.stack([f.flow for f in frs]) if k > 0 else None, mask, pose=pose,
+                     pose_valid=pv)
+            pm, vm = trk.state()
+            raw, _ = trk.mask(thresholded=False)
+            outs.append((pm.copy(), vm.copy(), raw.copy()))
+        return outs
+
+    batch = run(list(range(T)))
+    for t in (0, 7, 23):
+        single = run([t])
+        for k in range(F):
+            assert np.array_equal(batch[k][0][t], single[k][0][0]), (t, k)
+            assert np.array_equal(batch[k][1][t], single[k][1][0]), (t, k)
+            assert np.array_equal(batch[k][2][t], single[k][2][0]), (t, k)
+
+
 def test_ho3d_format_single_track(api):
     """BASELINE configs[2]: HO-3D-format 640x480 single track (SURVEY 8d intrinsics fx = fy = 617, cx = 312, cy = 241),
     every masked pixel, masks and poses delayed by 4 frames - parity of the whole filter loop against the sequential
