@@ -106,7 +106,7 @@ struct roftb_ctx {
     std::vector<TrackHost> th;
     // host-path staging ring (lazily allocated)
     float* stage_depth = nullptr; void* stage_flow = nullptr; uint8_t* stage_mask = nullptr;
-    cudaEvent_t copy_done = nullptr;
+    cudaEvent_t copy_done = nullptr, stage_event = nullptr;
     uint8_t* thr_tmp = nullptr;
 
     // optional per-phase device timing (bench.py roofline): 8 events per in-flight step
@@ -301,6 +301,7 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
         CKC(cudaEventCreateWithFlags(&ctx->ukf_event[i], cudaEventDisableTiming));
     }
     CKC(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&ctx->stage_event, cudaEventDisableTiming));
     for (int i = 0; i < kCtlRing; ++i) CKC(cudaEventCreateWithFlags(&ctx->ctl_event[i], cudaEventDisableTiming));
     for (int i = 0; i < kCtlRing; ++i)
         for (int j = 0; j < 11; ++j) CKC(cudaEventCreate(&ctx->prof_ev[i][j]));
@@ -433,6 +434,7 @@ void roftb_destroy(roftb_ctx* ctx) {
     if (ctx->vel_done_event) cudaEventDestroy(ctx->vel_done_event);
     if (ctx->ukf_stream) { cudaStreamSynchronize(ctx->ukf_stream); cudaStreamDestroy(ctx->ukf_stream); }
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->stage_event) cudaEventDestroy(ctx->stage_event);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
@@ -629,24 +631,31 @@ static int stage_host_frame(roftb_ctx* ctx, const roftb_frame* f, int slot, cons
     char* df = reinterpret_cast<char*>(ctx->stage_flow) + (size_t)slot * T * ctx->flow_elems * fb;
     // the slot was last read kFrameRing steps ago on ctx->stream; copies run on the copy stream after that work
     CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_done, 0));
+    // one copy per plane when the caller's tracks are contiguous (the usual case), else one per track
+    const bool depth_dense = (size_t)f->depth_track_stride == HW;
+    const bool flow_dense = (size_t)f->flow_track_stride == ctx->flow_elems;
+    bool all_masks = f->mask != nullptr && (size_t)f->mask_track_stride == HW;
+    for (size_t t = 0; all_masks && f->mask_valid && t < T; ++t) all_masks = f->mask_valid[t] != 0;
+    if (depth_dense) CK(cudaMemcpyAsync(dd, f->depth, sizeof(float) * T * HW, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (f->flow && flow_dense) CK(cudaMemcpyAsync(df, f->flow, T * ctx->flow_elems * fb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (all_masks) CK(cudaMemcpyAsync(ctx->stage_mask, f->mask, T * HW, cudaMemcpyHostToDevice, ctx->copy_stream));
     for (size_t t = 0; t < T; ++t) {
-        CK(cudaMemcpyAsync(dd + t * HW, f->depth + t * f->depth_track_stride, sizeof(float) * HW, cudaMemcpyHostToDevice,
-                           ctx->copy_stream));
-        if (f->flow)
+        if (!depth_dense)
+            CK(cudaMemcpyAsync(dd + t * HW, f->depth + t * f->depth_track_stride, sizeof(float) * HW, cudaMemcpyHostToDevice,
+                               ctx->copy_stream));
+        if (f->flow && !flow_dense)
             CK(cudaMemcpyAsync(df + t * ctx->flow_elems * fb,
                                reinterpret_cast<const char*>(f->flow) + t * f->flow_track_stride * fb, ctx->flow_elems * fb,
                                cudaMemcpyHostToDevice, ctx->copy_stream));
-        if (f->mask && (!f->mask_valid || f->mask_valid[t]))
+        if (f->mask && !all_masks && (!f->mask_valid || f->mask_valid[t]))
             CK(cudaMemcpyAsync(ctx->stage_mask + t * HW, f->mask + t * f->mask_track_stride, HW, cudaMemcpyHostToDevice,
                                ctx->copy_stream));
     }
-    cudaEvent_t ev;
-    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CK(cudaEventRecord(ev, ctx->copy_stream));
-    CK(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    CK(cudaEventRecord(ctx->stage_event, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->stage_event, 0));
+    CK(cudaStreamWaitEvent(ctx->prep_stream, ctx->stage_event, 0));  // (the new mask is read on the prep / mask streams)
     // the caller may reuse its host buffers as soon as this call returns
-    CK(cudaEventSynchronize(ev));
-    CK(cudaEventDestroy(ev));
+    CK(cudaEventSynchronize(ctx->stage_event));
     *d_depth = dd;
     *d_flow = f->flow ? df : nullptr;
     *d_mask = f->mask ? ctx->stage_mask : nullptr;

@@ -94,3 +94,41 @@ def test_tracker_executable_matches_oracle(hostlib, tmp_path, fmt):
             q_log = np.concatenate([[np.cos(pose_log[k, 12] / 2)], np.sin(pose_log[k, 12] / 2) * pose_log[k, 9:12]])
             q_exp = np.concatenate([[np.cos(eaa[3] / 2)], np.sin(eaa[3] / 2) * eaa[:3]])
             assert quat_close(q_log, q_exp) < 1e-4, (k, t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt,stride", [("f32", 1), ("s16", 4)])
+def test_reference_call_sequence_over_adapters_matches_fused_step(hostlib, tmp_path, fmt, stride):
+    """The fine-grained boundary: ROFTFilter::filtering_step (ROFTFilter.cpp:255-367) transcribed over the adapter classes
+    that carry the reference's names (ROFT::ImageOpticalFlowMeasurement<T>, SKFCorrection, UKFCorrection,
+    ImageSegmentationOFAidedSource<T>, CartesianQuaternionMeasurement ...) gives the same beliefs, frame by frame, as the
+    fused batched loop (roftb_filter_step) - tests/cpp/adapter_check.cpp."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = small_cfg(flow_grid=1 if fmt == "f32" else 4, flow_scale=1.0 if fmt == "f32" else 32.0, subsampling_radius=float(stride),
+                    segm_delay=3, pose_delay=3, sample_time=1.0 / 30.0)
+    F = 14
+    seq = sequence(cfg, 1, F, flow_format=fmt, target_coverage=0.3)
+    root = str(tmp_path / "seq0")
+    dataset_io.write_sequence(root, seq, 0, fx=cfg.fx, fy=cfg.fy, cx=cfg.cx, cy=cfg.cy)
+    out = subprocess.run([os.path.join(HOST, "adapter_check"), "--sequence", root, "--stride", str(stride), "--desired-fps", "10"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert f"adapter_check: {F} frames" in out.stdout, out.stdout
+
+
+def test_adapter_headers_carry_the_reference_names():
+    """The adapter header declares every class / virtual the reference's L2 interfaces name."""
+    h = open(os.path.join(HOST, "roft_adapters.h")).read()
+    for cls in ("class ImageSegmentationOFAidedSource", "class ImageSegmentationMeasurement", "class ImageOpticalFlowMeasurement",
+                "class SKFCorrection : public bfl::GaussianCorrection", "class UKFCorrection : public bfl::GaussianCorrection",
+                "class CartesianQuaternionModel : public bfl::StateModel", "class CartesianQuaternionMeasurement : public bfl::MeasurementModel",
+                "class SpatialVelocityModel : public bfl::LinearStateModel"):
+        assert cls in h, cls
+    for virt in ("bool freeze(const bfl::Data& data = bfl::Data()) override", "predictedMeasure(const Eigen::Ref<const Eigen::MatrixXd>&",
+                 "getMeasurementMatrix() const override", "getNoiseCovarianceMatrix() const override", "setProperty(const std::string& property) override",
+                 "void correctStep(const bfl::GaussianMixture& pred_state, bfl::GaussianMixture& corr_state) override",
+                 "enum class MeasurementMode { Standard, RepeatOnlyVelocity, PopBufferedMeasurement }",
+                 "enum class FreezeType { OnlyStepSource, ExceptStepSource, Complete }"):
+        assert virt in h, virt
