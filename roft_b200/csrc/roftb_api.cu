@@ -56,6 +56,8 @@ struct roftb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr, prep_stream = nullptr,
                  aux_stream = nullptr;
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+    cudaStream_t vel_side[2] = {nullptr, nullptr};   // larger-cluster launches of the velocity kernel (biggest tracks)
+    cudaEvent_t vel_fork = nullptr, vel_join[2] = {nullptr, nullptr};
     cudaEvent_t prep_event[2] = {nullptr, nullptr}, prep2_event[2] = {nullptr, nullptr}, vel_done_event = nullptr;
     bool vel_done_event_used = false;
     cudaEvent_t vel_event[kCtlRing], ukf_event[kCtlRing], join_event = nullptr, plan_event = nullptr, mask_event = nullptr;
@@ -287,6 +289,11 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(cudaEventCreateWithFlags(&ctx->join_event, cudaEventDisableTiming));
     CKC(cudaStreamCreateWithPriority(&ctx->mask_stream, cudaStreamNonBlocking, prio_hi));
     CKC(cudaStreamCreateWithPriority(&ctx->prep_stream, cudaStreamNonBlocking, prio_hi));
+    for (int i = 0; i < 2; ++i) {
+        CKC(cudaStreamCreateWithPriority(&ctx->vel_side[i], cudaStreamNonBlocking, prio_main));
+        CKC(cudaEventCreateWithFlags(&ctx->vel_join[i], cudaEventDisableTiming));
+    }
+    CKC(cudaEventCreateWithFlags(&ctx->vel_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&ctx->prep_event[0], cudaEventDisableTiming));
@@ -394,8 +401,14 @@ void roftb_destroy(roftb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->dev);
     // nothing may still be running on any of the streams when the buffers go away
-    for (cudaStream_t st : {ctx->copy_stream, ctx->prep_stream, ctx->stream, ctx->aux_stream, ctx->mask_stream, ctx->ukf_stream})
+    for (cudaStream_t st : {ctx->copy_stream, ctx->prep_stream, ctx->stream, ctx->aux_stream, ctx->mask_stream, ctx->ukf_stream,
+                            ctx->vel_side[0], ctx->vel_side[1]})
         if (st) cudaStreamSynchronize(st);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->vel_side[i]) cudaStreamDestroy(ctx->vel_side[i]);
+        if (ctx->vel_join[i]) cudaEventDestroy(ctx->vel_join[i]);
+    }
+    if (ctx->vel_fork) cudaEventDestroy(ctx->vel_fork);
     void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->mask_state[2], ctx->mask_occ[0], ctx->mask_occ[1], ctx->mask_occ[2],
                      ctx->winner, ctx->scratch.nu, ctx->scratch.dp, ctx->scratch.r, ctx->scratch.hist, ctx->scratch.chunk_cnt,
                      ctx->scratch.part, ctx->scratch.track_sel, ctx->scratch.sel_part, ctx->scratch.slot_bitmap, ctx->scratch.track_slot, ctx->scratch.chunk_aux,
@@ -937,6 +950,8 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
         a.phase_clock = pe ? ctx->phase_clock : nullptr;
         a.order = ctx->vel_order + (size_t)par * T; a.order_next = ctx->vel_order + (size_t)(par ^ 1) * T;
         a.done_ticket = ctx->vel_ticket;
+        a.side_stream[0] = ctx->vel_side[0]; a.side_stream[1] = ctx->vel_side[1];
+        a.side_fork = ctx->vel_fork; a.side_join[0] = ctx->vel_join[0]; a.side_join[1] = ctx->vel_join[1];
         a.update_state = 1;
         a.fuse_scatter = 1; a.plan = plan; a.state_dst = seg_next; a.occ_dst = occ_next;
         if (pe) CK(cudaEventRecord(pe[1], s));

@@ -189,6 +189,8 @@ struct VelocityArgs {
     // largest-first scheduling (may be null): clusters take the tracks in `order`; the last cluster to finish writes
     // `order_next` from wl_units for the following step; done_ticket is a zero-initialised counter
     const int32_t* order; int32_t* order_next; uint32_t* done_ticket;
+    // optional: two more streams (+ fork / join events) so that the biggest tracks run in larger clusters beside the rest
+    cudaStream_t side_stream[2]; cudaEvent_t side_fork; cudaEvent_t side_join[2];
     unsigned long long* phase_clock;                          // device [T][8] globaltimer stamps at the phase boundaries (may be null)
     // fused mask propagation (see WarpPlan::fused): destination plane and its occupancy flags
     int fuse_scatter; const WarpPlan* plan; uint8_t* state_dst; uint8_t* occ_dst;

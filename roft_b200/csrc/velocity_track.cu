@@ -202,6 +202,8 @@ struct VtArgs {
     // scheduling order: cluster y processes track order[y] (largest worklist first, from the previous step's sizes);
     // the last cluster to finish writes the order of the next step
     const int32_t* order; int32_t* order_next; uint32_t* done_ticket;
+    int first;                                            // this launch covers order[first .. first + gridDim.y)
+    int total_tracks;                                     // tracks of the step over all launches (ticket target)
     unsigned long long* phase_clock;                      // optional [T][8]
     int l2_hint;
     int dbg;                                              // knock-out experiments (timing only, WRONG results): 1 no mask stores, 2 no record stores, 4 no flag stores
@@ -254,7 +256,7 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
     __shared__ SelParams s_sp;
 
     __shared__ int s_bucket[129];
-    const int t = a.order ? a.order[blockIdx.y] : (int)blockIdx.y;
+    const int t = a.order ? a.order[a.first + blockIdx.y] : a.first + (int)blockIdx.y;
     const VelCtl c = a.ctl[t];
     bool do_sc = false;
     uint8_t sc_val = 0;
@@ -272,12 +274,12 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
         unsigned last = 0;
         if (lane == 0) {
             __threadfence();
-            last = atomicAdd(a.done_ticket, 1u) == gridDim.y - 1 ? 1u : 0u;
+            last = atomicAdd(a.done_ticket, 1u) == (unsigned)a.total_tracks - 1u ? 1u : 0u;
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {
             __threadfence();
-            write_next_order(a, (int)gridDim.y, lane, s_bucket);
+            write_next_order(a, a.total_tracks, lane, s_bucket);
             if (lane == 0) *a.done_ticket = 0;
         }
     };
@@ -1394,7 +1396,7 @@ int velocity_prepare_device(const Geom& g, int n_units, int* max_active_clusters
     vt_smem_layout(g, n_units, cluster, va, bytes);
     for (int fast = 0; fast < 2; ++fast) {
         if (cudaFuncSetAttribute(vt_kernel(fast != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return -1;
-        if (cluster > 8) cudaFuncSetAttribute(vt_kernel(fast != 0), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(vt_kernel(fast != 0), cudaFuncAttributeNonPortableClusterSizeAllowed, 1);  // (4x the base cluster may be 16)
     }
     if (max_active_clusters) {
         cudaLaunchConfig_t cfg;
@@ -1459,26 +1461,60 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     // configuration (CV_16SC2 / sub-sampled flow grids, stride > 1) takes the register path of the same kernel
     static const int env_ring = [] { const char* e = getenv("ROFTB_RING"); return e ? atoi(e) : 1; }();
     const bool fast = env_ring != 0 && !g.flow_s16 && g.grid == 1 && g.scale_mode == 0 && g.stride == 1 && (g.HW % 16) == 0;
-    int bytes = 0;
-    vt_smem_layout(g, n_units, cluster, va, bytes);
-
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(cluster, T);
-    cfg.blockDim = dim3(kVtThreads);
-    cfg.dynamicSmemBytes = bytes;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cluster;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e;
-    e = cudaLaunchKernelEx(&cfg, vt_kernel(fast), va);
-    ++g_launch_count;
-    if (e != cudaSuccess) return -1;
+    // Tracks are ordered largest first and their sizes differ by more than two orders of magnitude (an object can fill
+    // the frame or a corner of it); a track's latency is inversely proportional to the CTAs that share it, and the launch
+    // cannot end before its biggest track does.  ROFTB_VT_SPLIT (default 0 = off) gives the biggest tracks - by RANK,
+    // which the host knows; the sizes never leave the device - a 2x / 4x larger cluster in concurrent launches of the
+    // same kernel.  Measured on B200 (256 tracks): the biggest track's latency falls from 745 to 280-370 us, but kernels
+    // with different cluster shapes pack worse on the GPCs and the step gets 12-15 % slower, so it stays off.
+    struct Part { int first, count, cluster; cudaStream_t stream; };
+    Part parts[3];
+    int n_parts = 0;
+    static const int env_split = [] { const char* e = getenv("ROFTB_VT_SPLIT"); return e ? atoi(e) : 0; }();
+    const bool split = env_split != 0 && a.order && a.side_stream[0] && a.side_stream[1] && T >= 64 && cluster * 2 <= kVtMaxCluster;
+    if (split && env_split == 1 && cluster * 4 <= kVtMaxCluster) {  // three ways: 1/16 at 4x, 1/8 at 2x, the rest
+        const int n_big = T / 16, n_mid = T / 8;
+        parts[n_parts++] = Part{0, n_big, cluster * 4, a.side_stream[0]};
+        parts[n_parts++] = Part{n_big, n_mid, cluster * 2, a.side_stream[1]};
+        parts[n_parts++] = Part{n_big + n_mid, T - n_big - n_mid, cluster, s};
+    } else if (split) {  // two ways: the biggest 1/env_split of the tracks at 2x
+        const int n_big = T / max(env_split, 2);
+        parts[n_parts++] = Part{0, n_big, cluster * 2, a.side_stream[0]};
+        parts[n_parts++] = Part{n_big, T - n_big, cluster, s};
+    } else {
+        parts[n_parts++] = Part{0, T, cluster, s};
+    }
+    if (n_parts > 1) {
+        cudaEventRecord(a.side_fork, s);
+        for (int i = 0; i + 1 < n_parts; ++i) cudaStreamWaitEvent(a.side_stream[i], a.side_fork, 0);
+    }
+    va.total_tracks = T;
+    for (int pi = 0; pi < n_parts; ++pi) {
+        const Part& pt = parts[pi];
+        int bytes = 0;
+        vt_smem_layout(g, n_units, pt.cluster, va, bytes);
+        va.first = pt.first;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(pt.cluster, pt.count);
+        cfg.blockDim = dim3(kVtThreads);
+        cfg.dynamicSmemBytes = bytes;
+        cfg.stream = pt.stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = pt.cluster;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, vt_kernel(fast), va);
+        ++g_launch_count;
+        if (e != cudaSuccess) return -1;
+        if (pi + 1 < n_parts) {
+            cudaEventRecord(a.side_join[pi], pt.stream);
+            cudaStreamWaitEvent(s, a.side_join[pi], 0);
+        }
+    }
     EpiArgs ea;
     ea.n_tracks = T;
     ea.ctl = a.ctl;
