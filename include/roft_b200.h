@@ -42,7 +42,8 @@ extern "C" {
 #define ROFTB_MEAS_POSE 2
 #define ROFTB_MEAS_POSE_VELOCITY 3
 
-#define ROFTB_MAX_DELAY 8 /* max frames between mask / pose iterations (D) */
+#define ROFTB_MAX_DELAY 8 /* max frames between mask / pose iterations (D) in the filter loop */
+#define ROFTB_MAX_CHAIN 30 /* longest flow chain of roftb_mask_sync (the stamped source's queue, ...Stamped.hpp:99) */
 
 typedef struct roftb_ctx roftb_ctx;
 
@@ -159,7 +160,9 @@ int roftb_get_worklist(roftb_ctx* ctx, int32_t* units, int32_t* pixels);
 /* ImageSegmentationOFAidedSource<T>::map + cv::remap (ImageSegmentationOFAidedSource.hpp:
  * 211-226,235-281): warp `mask` through `n_flows` flow frames (oldest first).  zero_origin=1
  * reproduces the "no new mask" branch (mask_(0,0)=0 first, :224).  n_masks masks, each with
- * its own flow chain: flows is [n_flows][n_masks][H/grid][W/grid][2]. out_raw/out_thr: [n_masks][H][W]. */
+ * its own flow chain: flows is [n_flows][n_masks][H/grid][W/grid][2], n_flows <= ROFTB_MAX_CHAIN.
+ * out_raw/out_thr: [n_masks][H][W].  The same call serves the time-stamped source
+ * (ImageSegmentationOFAidedSourceStamped.hpp:153-318), whose host side only SELECTS the flows differently. */
 int roftb_mask_sync(roftb_ctx* ctx, int32_t n_masks, const uint8_t* mask, const void* flows, int32_t n_flows,
                     int32_t zero_origin, uint8_t* out_raw, uint8_t* out_thr);
 /* ImageOpticalFlowMeasurement<T>::freeze (hpp:231-283) fused with the Laplacian weights and

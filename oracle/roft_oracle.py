@@ -400,6 +400,73 @@ class OFAidedSegmentationSource:
         return self.segmentation_available, self.mask
 
 
+class OpticalFlowQueue:
+    """OpticalFlowQueueHandler (src/OpticalFlowQueueHandler.cpp:18-57): the last ``window_size`` flow frames with the
+    time stamp of the RGB frame they arrived with."""
+
+    def __init__(self, window_size: int = 30):
+        self.window_size = window_size
+        self.buffer: Deque[Tuple[np.ndarray, float]] = deque()
+
+    def add_flow(self, frame: np.ndarray, time_stamp: float):  # :18-26
+        self.buffer.append((frame.copy(), float(time_stamp)))
+        if len(self.buffer) > self.window_size:
+            self.buffer.popleft()
+
+    def get_buffer_region(self, initial_time_stamp: float) -> List[np.ndarray]:  # :29-51
+        for index, (_, ts) in enumerate(self.buffer):
+            if abs(ts - initial_time_stamp) < 1e-3:
+                # the flow always refers to the PREVIOUS image: the region starts one entry later
+                return [f for f, _ in list(self.buffer)[index + 1:]]
+        return []
+
+    def clear(self):
+        self.buffer.clear()
+
+
+class StampedOFAidedSegmentationSource:
+    """ImageSegmentationOFAidedSourceStamped<T>::step_frame, ...Stamped.hpp:153-268: a new mask carries the time stamp
+    of the frame it was computed on and is warped through the queued flows that FOLLOW that frame."""
+
+    def __init__(self, cfg: RoftConfig):
+        self.cfg = cfg
+        self.segmentation_available = False
+        self.is_first_frame = True
+        self.queue = OpticalFlowQueue(30)  # flow_queue_max_size_ (:99)
+        self.mask: Optional[np.ndarray] = None
+
+    def step_frame(self, new_mask: Optional[np.ndarray], mask_time_stamp: float, flow: Optional[np.ndarray],
+                   rgb_time_stamp: float) -> bool:
+        valid_segmentation = new_mask is not None
+        mask = new_mask
+        if (not self.segmentation_available) and valid_segmentation:  # :212-221
+            self.segmentation_available = True
+            self.mask = mask.copy()
+            valid_segmentation = False
+        if valid_segmentation and find_non_zero(mask).shape[0] == 0:  # :223-230
+            valid_segmentation = False
+        valid_flow = (flow is not None) and (not self.is_first_frame)  # :233-236
+        if valid_flow:
+            self.queue.add_flow(flow, rgb_time_stamp)  # :237-241
+        if valid_segmentation:  # :243-258
+            self.mask = mask.copy()
+            region = self.queue.get_buffer_region(mask_time_stamp)
+            if len(region) > 0:
+                self.mask = remap_exact(self.mask, mask_warp_map(self.mask, region, self.cfg))
+            elif flow is not None:
+                self.mask[0, 0] = 0
+                self.mask = remap_exact(self.mask, mask_warp_map(self.mask, [flow], self.cfg))
+        elif valid_flow and self.mask is not None:  # :260-265
+            self.mask = self.mask.copy()
+            self.mask[0, 0] = 0
+            self.mask = remap_exact(self.mask, mask_warp_map(self.mask, [flow], self.cfg))
+        self.is_first_frame = False
+        return True
+
+    def segmentation(self) -> Tuple[bool, Optional[np.ndarray]]:
+        return self.segmentation_available, self.mask
+
+
 # --------------------------------------------------------------------------------------
 # a9  masked depth extraction
 # --------------------------------------------------------------------------------------

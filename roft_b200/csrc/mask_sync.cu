@@ -81,7 +81,7 @@ __global__ void k_warp_plan(int n_tracks, const WarpCtl* __restrict__ ctl, MaskS
     p.src_new = 0;
     p.zero_origin = 0;
     p.n_flows = 0;
-    for (int i = 0; i < kMaxFlows; ++i) p.flow_slot[i] = 0;
+    for (int i = 0; i < kMaxChain; ++i) p.flow_slot[i] = 0;
     p.uniform_val = fb.uniform_val;
     p.dflt = 0;
     p.fused = 0;

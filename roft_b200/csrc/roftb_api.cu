@@ -1081,7 +1081,7 @@ extern "C" {
 
 int roftb_mask_sync(roftb_ctx* ctx, int32_t n_masks, const uint8_t* mask, const void* flows, int32_t n_flows,
                     int32_t zero_origin, uint8_t* out_raw, uint8_t* out_thr) {
-    if (!ctx || !mask || n_masks <= 0 || n_flows < 0 || n_flows > kMaxFlows || (n_flows > 0 && !flows))
+    if (!ctx || !mask || n_masks <= 0 || n_flows < 0 || n_flows > kMaxChain || (n_flows > 0 && !flows))
         return ctx ? fail(ctx, "roftb_mask_sync: bad argument") : -2;
     CK(cudaSetDevice(ctx->dev));
     cudaStream_t s = ctx->stream;

@@ -11,8 +11,10 @@
 
 namespace roftb {
 
-constexpr int kMaxFlows = ROFTB_MAX_DELAY;   // longest flow chain a mask is warped through
-constexpr int kFrameRing = 16;               // device-side table of recent frames (> kMaxFlows)
+constexpr int kMaxFlows = ROFTB_MAX_DELAY;   // longest flow chain the FILTER LOOP warps a mask through
+constexpr int kMaxChain = ROFTB_MAX_CHAIN;   // longest chain of the stand-alone operator (the stamped source's queue holds 30)
+constexpr int kFrameRing = 16;               // frames the filter loop keeps addressable (> kMaxFlows)
+constexpr int kFrameTable = 32;              // entries of the plane-pointer table passed to the kernels (> kMaxChain, >= kFrameRing)
 constexpr int kThreads = 256;                // streaming kernels: 8 warps
 constexpr int kWarpTilePx = 512;             // extract kernels: one warp covers 4 sub-tiles of 128 px
 constexpr int kUnitPx = 128;                 // worklist granularity: 128 consecutive px = one quad per lane of a warp
@@ -51,8 +53,8 @@ struct Geom {
 
 // table of the recent frames' device planes (passed to kernels by value)
 struct FrameTable {
-    const void* flow[kFrameRing];
-    const float* depth[kFrameRing];
+    const void* flow[kFrameTable];
+    const float* depth[kFrameTable];
     long long flow_stride;   // scalar elements between tracks
     long long depth_stride;  // elements between tracks
 };
@@ -77,7 +79,7 @@ struct WarpPlan {          // device-resolved by k_warp_plan
     int32_t src_new;       // scatter source: 1 = newly delivered mask, 0 = state mask
     int32_t zero_origin;   // mask_(0,0) = 0 before findNonZero (hpp:224)
     int32_t n_flows;
-    int32_t flow_slot[kMaxFlows];
+    int32_t flow_slot[kMaxChain];
     int32_t uniform_val;   // >0: every non-zero source pixel has this value (byte-store fast path)
     int32_t dflt;          // value sampled by unmapped destinations = src(0,0) (Q2)
     int32_t fused;         // 1: the scatter of this track is done by the velocity pass (single current flow, state source)

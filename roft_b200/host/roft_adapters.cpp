@@ -117,6 +117,98 @@ std::pair<bool, MaskImage> ImageSegmentationOFAidedSource<T>::segmentation(const
 template class ImageSegmentationOFAidedSource<cv::Vec2f>;
 template class ImageSegmentationOFAidedSource<cv::Vec2s>;
 
+// ---- OpticalFlowQueueHandler / ImageSegmentationOFAidedSourceStamped -----------------------------------------
+void OpticalFlowQueueHandler::add_flow(const FlowFrame& frame, const double& time_stamp) {
+    buffer_.push_back(Entry{frame, time_stamp});
+    if (buffer_.size() > window_size_) buffer_.pop_front();  // enforce the maximum size
+}
+
+std::vector<const FlowFrame*> OpticalFlowQueueHandler::get_buffer_region(const double& initial_time_stamp) {
+    std::vector<const FlowFrame*> output_region;
+    std::size_t index;
+    bool found = false;
+    for (index = 0; index < buffer_.size(); index++)
+        if (std::fabs(buffer_[index].timestamp - initial_time_stamp) < 1e-3) {
+            found = true;
+            break;
+        }
+    if (!found) return output_region;
+    index++;  // the optical flow always refers to the previous RGB image, thus the next frame is needed
+    for (; index < buffer_.size(); index++) output_region.push_back(&buffer_[index].frame);
+    return output_region;
+}
+
+template <class T>
+ImageSegmentationOFAidedSourceStamped<T>::ImageSegmentationOFAidedSourceStamped(std::shared_ptr<StampedSegmentation> segmentation_source,
+                                                                                std::shared_ptr<ImageOpticalFlowSource> flow_source,
+                                                                                const CameraParameters&, const bool&, std::shared_ptr<B200Context> ctx)
+    : segmentation_(std::move(segmentation_source)), flow_(std::move(flow_source)), ctx_(std::move(ctx)) {
+    segm_frames_between_iterations_ = segmentation_->get_frames_between_iterations();
+}
+
+template <class T>
+bool ImageSegmentationOFAidedSourceStamped<T>::reset() {
+    segmentation_available_ = false;
+    is_first_frame_ = true;
+    flow_handler_.clear();
+    return segmentation_->reset();
+}
+
+template <class T>
+void ImageSegmentationOFAidedSourceStamped<T>::warp(const std::vector<const FlowFrame*>& flows, bool zero_origin) {
+    std::size_t start = 0;  // map(): only the last `segm_frames_between_iterations_` flows are chained (hpp:276-282)
+    if (segm_frames_between_iterations_ > 0 && flows.size() > std::size_t(segm_frames_between_iterations_))
+        start = flows.size() - std::size_t(segm_frames_between_iterations_);
+    const std::size_t n = flows.size() - start;
+    if (n > ROFTB_MAX_CHAIN) throw std::runtime_error("ImageSegmentationOFAidedSourceStamped::map: flow chain longer than ROFTB_MAX_CHAIN");
+    std::vector<std::uint8_t> packed;
+    for (std::size_t j = start; j < flows.size(); ++j) packed.insert(packed.end(), flows[j]->data.begin(), flows[j]->data.end());
+    MaskImage out = mask_;
+    check(roftb_mask_sync(ctx_->get(), 1, mask_.data.data(), n ? packed.data() : nullptr, int(n), zero_origin ? 1 : 0, out.data.data(), nullptr),
+          ctx_->get(), "ImageSegmentationOFAidedSourceStamped::map");
+    mask_ = std::move(out);
+}
+
+template <class T>
+bool ImageSegmentationOFAidedSourceStamped<T>::step_frame() {
+    if (segmentation_->is_stepping_required()) segmentation_->step_frame();
+    bool valid_segmentation = false;
+    MaskImage mask;
+    std::tie(valid_segmentation, mask) = segmentation_->segmentation(false);
+    const double mask_time_stamp = segmentation_->get_time_stamp();
+    if (!segmentation_available_ && valid_segmentation) {  // hpp:212-221: initialisation, not treated as a new mask
+        segmentation_available_ = true;
+        mask_ = mask;
+        valid_segmentation = false;
+    }
+    if (valid_segmentation) {  // hpp:223-230: an uninformative mask is skipped
+        bool any = false;
+        for (std::uint8_t b : mask.data) any |= b != 0;
+        if (!any) valid_segmentation = false;
+    }
+    bool valid_flow = false;
+    const FlowFrame* flow = nullptr;
+    std::tie(valid_flow, flow) = flow_->flow(false);
+    valid_flow &= !is_first_frame_;
+    if (valid_flow) flow_handler_.add_flow(*flow, rgb_image_time_stamp_);  // hpp:237-241
+    if (valid_segmentation) {  // hpp:243-258
+        mask_ = mask;
+        const std::vector<const FlowFrame*> buffer = flow_handler_.get_buffer_region(mask_time_stamp);
+        if (!buffer.empty()) {
+            warp(buffer, false);
+        } else if (flow) {
+            warp({flow}, true);  // no queued flow follows the mask's frame: propagate with the current flow (mask_(0,0) = 0 first)
+        }
+    } else if (valid_flow) {  // hpp:260-265
+        warp({flow}, true);
+    }
+    is_first_frame_ = false;
+    return true;
+}
+
+template class ImageSegmentationOFAidedSourceStamped<cv::Vec2f>;
+template class ImageSegmentationOFAidedSourceStamped<cv::Vec2s>;
+
 // ---- ImageSegmentationMeasurement --------------------------------------------------------------------------
 bool ImageSegmentationMeasurement::freeze(const bfl::Data&) {
     if (segmentation_source_->is_stepping_required()) segmentation_source_->step_frame();
@@ -459,3 +551,93 @@ void UKFCorrection::correctStep(const bfl::GaussianMixture& pred_state, bfl::Gau
 }
 
 }  // namespace ROFT
+
+// ---- test hook: the stamped source driven from arrays (tests/test_host.py) ----------------------------------------------
+namespace {
+using namespace ROFT;
+struct ArrayFlowSource : ImageOpticalFlowSource {
+    std::vector<FlowFrame> frames;
+    std::vector<uint8_t> valid;
+    int head = -1, type = ROFTB_FLOW_F32;
+    std::size_t grid = 1;
+    float scale = 1.f;
+    bool step_frame() override { ++head; return true; }
+    bool is_stepping_required() const override { return true; }
+    std::tuple<bool, const FlowFrame*> flow(const bool&) override {
+        const bool ok = head >= 0 && head < int(frames.size()) && valid[head];
+        return std::make_tuple(ok, ok ? &frames[head] : nullptr);
+    }
+    std::size_t get_grid_size() const override { return grid; }
+    float get_scaling_factor() const override { return scale; }
+    int get_matrix_type() const override { return type; }
+};
+struct ArrayStampedSegmentation : StampedSegmentation {
+    std::vector<MaskImage> masks;
+    std::vector<uint8_t> valid;
+    std::vector<double> stamps;
+    int head = -1, between = -1;
+    bool step_frame() override { ++head; return true; }
+    bool is_stepping_required() const override { return true; }
+    int get_frames_between_iterations() const override { return between; }
+    std::pair<bool, MaskImage> segmentation(const bool&) override {
+        const bool ok = head >= 0 && head < int(masks.size()) && valid[head];
+        return std::make_pair(ok, ok ? masks[head] : MaskImage());
+    }
+    double get_time_stamp() override { return head >= 0 && head < int(stamps.size()) ? stamps[head] : -1.0; }
+};
+}  // namespace
+
+extern "C" int rofth_stamped_sync_run(int width, int height, int flow_type, int flow_grid, float flow_scale, int n_frames,
+                                      const uint8_t* masks, const uint8_t* mask_valid, const double* mask_stamp, const uint8_t* flows,
+                                      const uint8_t* flow_valid, const double* rgb_stamp, int frames_between, uint8_t* out_masks,
+                                      uint8_t* out_available) {
+    try {
+        CameraParameters cam;
+        cam.width = std::size_t(width); cam.height = std::size_t(height);
+        cam.fx = cam.fy = 600.0; cam.cx = width / 2.0; cam.cy = height / 2.0;
+        const double cov_flow[2] = {1, 1}, pm[6] = {1, 1, 1, 1, 1, 1}, pz[12] = {0.1, 0.1, 0.1, 1e-4, 1e-4, 1e-4, 1e-3, 1e-3, 1e-3, 1e-4, 1e-4, 1e-4};
+        auto ctx = std::make_shared<B200Context>(cam, flow_type, std::size_t(flow_grid), flow_scale, 1.0, 2.0, true, cov_flow, pm, pz, 1.0, 2.0, 0.0,
+                                                 frames_between > 0 && frames_between <= ROFTB_MAX_DELAY ? frames_between : 0);
+        const std::size_t HW = std::size_t(width) * height;
+        const std::size_t fbytes = std::size_t(width / flow_grid) * (height / flow_grid) * (flow_type == ROFTB_FLOW_S16 ? 4 : 8);
+        auto fs = std::make_shared<ArrayFlowSource>();
+        fs->type = flow_type; fs->grid = std::size_t(flow_grid); fs->scale = flow_scale;
+        auto ss = std::make_shared<ArrayStampedSegmentation>();
+        ss->between = frames_between;
+        for (int k = 0; k < n_frames; ++k) {
+            FlowFrame f;
+            f.type = flow_type; f.cols = std::size_t(width / flow_grid); f.rows = std::size_t(height / flow_grid);
+            f.data.assign(flows + k * fbytes, flows + (k + 1) * fbytes);
+            fs->frames.push_back(std::move(f));
+            fs->valid.push_back(flow_valid[k]);
+            MaskImage m;
+            m.cols = std::size_t(width); m.rows = std::size_t(height);
+            m.data.assign(masks + k * HW, masks + (k + 1) * HW);
+            ss->masks.push_back(std::move(m));
+            ss->valid.push_back(mask_valid[k]);
+            ss->stamps.push_back(mask_stamp[k]);
+        }
+        ImageSegmentationOFAidedSourceStamped<cv::Vec2f> f32(ss, fs, cam, false, ctx);
+        ImageSegmentationOFAidedSourceStamped<cv::Vec2s> s16(ss, fs, cam, false, ctx);
+        for (int k = 0; k < n_frames; ++k) {
+            fs->step_frame();  // the filter steps the flow source before the segmentation (ROFTFilter.cpp:283-286)
+            std::pair<bool, MaskImage> r;
+            if (flow_type == ROFTB_FLOW_S16) {
+                s16.set_rgb_image_time_stamp(rgb_stamp[k]);
+                s16.step_frame();
+                r = s16.segmentation(false);
+            } else {
+                f32.set_rgb_image_time_stamp(rgb_stamp[k]);
+                f32.step_frame();
+                r = f32.segmentation(false);
+            }
+            out_available[k] = r.first ? 1 : 0;
+            if (r.first) std::memcpy(out_masks + k * HW, r.second.data.data(), HW);
+            else std::memset(out_masks + k * HW, 0, HW);
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        std::cerr << "rofth_stamped_sync_run: " << e.what() << std::endl;
+        return -1;
+    }
+}

@@ -4,6 +4,8 @@
 // compares every frame with the fused batched loop (roftb_filter_step).
 //
 //   ROFT::ImageSegmentationOFAidedSource<T>   include/ROFT/ImageSegmentationOFAidedSource.hpp:37-53,128-281  -> roftb_mask_sync
+//   ROFT::ImageSegmentationOFAidedSourceStamped<T>  include/ROFT/ImageSegmentationOFAidedSourceStamped.hpp:153-318   -> roftb_mask_sync
+//   ROFT::OpticalFlowQueueHandler             src/OpticalFlowQueueHandler.cpp:18-57 (time-stamped flow queue, host)
 //   ROFT::ImageSegmentationMeasurement        src/ImageSegmentationMeasurement.cpp:30-81 (threshold :61-65)
 //   ROFT::ImageOpticalFlowMeasurement<T>      include/ROFT/ImageOpticalFlowMeasurement.hpp:47-71,168-375     -> roftb_flow_measurement_export
 //   ROFT::SKFCorrection                       include/ROFT/SKFCorrection.h:26-33, src/SKFCorrection.cpp:37-153 -> roftb_flow_velocity
@@ -91,6 +93,54 @@ private:
     std::shared_ptr<B200Context> ctx_;
     std::vector<FlowFrame> flow_buffer_;
     MaskImage mask_;
+    bool segmentation_available_ = false, is_first_frame_ = true;
+    int segm_frames_between_iterations_;
+};
+
+// time-stamped queue of the most recent flow frames (OpticalFlowQueueHandler.cpp:18-57)
+class OpticalFlowQueueHandler {
+public:
+    explicit OpticalFlowQueueHandler(const std::size_t& window_size) : window_size_(window_size) {}
+    void add_flow(const FlowFrame& frame, const double& time_stamp);                       // :18-26
+    std::vector<const FlowFrame*> get_buffer_region(const double& initial_time_stamp);     // :29-51: the frames AFTER the stamped one
+    void clear() { buffer_.clear(); }
+    std::size_t size() const { return buffer_.size(); }
+
+private:
+    struct Entry { FlowFrame frame; double timestamp; };
+    std::size_t window_size_;
+    std::deque<Entry> buffer_;
+};
+
+// a segmentation source that stamps its masks (RobotsIO::Utils::Segmentation::get_time_stamp, UPSTREAM-RECALL)
+class StampedSegmentation : public Segmentation {
+public:
+    virtual double get_time_stamp() = 0;
+};
+
+// asynchronous (time-stamp matched) variant: a new mask is warped through the queued flows that FOLLOW the frame it was
+// computed on; host side of ImageSegmentationOFAidedSourceStamped.hpp:153-268, same kernels as the un-stamped source
+template <class T>
+class ImageSegmentationOFAidedSourceStamped : public Segmentation {
+public:
+    ImageSegmentationOFAidedSourceStamped(std::shared_ptr<StampedSegmentation> segmentation_source, std::shared_ptr<ImageOpticalFlowSource> flow_source,
+                                          const CameraParameters& camera_parameters, const bool& wait_source_initialization,
+                                          std::shared_ptr<B200Context> ctx);
+    void set_rgb_image_time_stamp(const double& timestamp) { rgb_image_time_stamp_ = timestamp; }  // set_rgb_image(image, stamp), hpp:145-150
+    bool step_frame() override;                                   // hpp:153-268
+    bool is_stepping_required() const override { return true; }
+    bool reset() override;
+    int get_frames_between_iterations() const override { return segmentation_->get_frames_between_iterations(); }
+    std::pair<bool, MaskImage> segmentation(const bool& blocking = false) override { (void)blocking; return std::make_pair(segmentation_available_, mask_); }
+
+private:
+    void warp(const std::vector<const FlowFrame*>& flows, bool zero_origin);  // map() hpp:272-318 + cv::remap
+    std::shared_ptr<StampedSegmentation> segmentation_;
+    std::shared_ptr<ImageOpticalFlowSource> flow_;
+    std::shared_ptr<B200Context> ctx_;
+    OpticalFlowQueueHandler flow_handler_{30};  // flow_queue_max_size_, hpp:99
+    MaskImage mask_;
+    double rgb_image_time_stamp_ = 0.0;
     bool segmentation_available_ = false, is_first_frame_ = true;
     int segm_frames_between_iterations_;
 };

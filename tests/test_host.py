@@ -132,3 +132,57 @@ def test_adapter_headers_carry_the_reference_names():
                  "enum class MeasurementMode { Standard, RepeatOnlyVelocity, PopBufferedMeasurement }",
                  "enum class FreezeType { OnlyStepSource, ExceptStepSource, Complete }"):
         assert virt in h, virt
+
+
+def test_flow_queue_oracle_semantics():
+    """OpticalFlowQueueHandler.cpp:18-57: bounded window, region = the frames AFTER the stamped one, empty if not found."""
+    q = o.OpticalFlowQueue(4)
+    for k in range(6):
+        q.add_flow(np.full((2, 2, 2), k, np.float32), 0.1 * k)
+    assert len(q.buffer) == 4                                   # frames 2..5 kept
+    assert [int(f[0, 0, 0]) for f in q.get_buffer_region(0.3)] == [4, 5]
+    assert q.get_buffer_region(0.5) == []                       # the newest frame: nothing follows it
+    assert q.get_buffer_region(0.1) == []                       # fell out of the window
+    assert [int(f[0, 0, 0]) for f in q.get_buffer_region(0.2 + 5e-4)] == [3, 4, 5]   # 1 ms matching tolerance
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["f32", "s16"])
+def test_stamped_mask_sync_matches_oracle(hostlib, fmt):
+    """f2: ImageSegmentationOFAidedSourceStamped (time-stamp matched masks + flow queue, ...Stamped.hpp:153-318) - the
+    adapter over roftb_mask_sync against the numpy/cv2 restatement: masks arrive with irregular latency (1-11 frames,
+    i.e. chains longer than ROFTB_MAX_DELAY), one stamp matches nothing, one mask is empty."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = small_cfg(W=160, H=96, flow_grid=1 if fmt == "f32" else 4, flow_scale=1.0 if fmt == "f32" else 32.0, segm_delay=0)
+    F = 26
+    seq = sequence(cfg, 1, F, flow_format=fmt, target_coverage=0.3)
+    H, W = cfg.height, cfg.width
+    stamps = 100.0 + np.arange(F) / 30.0
+    # frame at which a mask computed on frame `src` is delivered
+    deliveries = {0: 0, 3: 2, 9: 8, 20: 9, 22: 21, 24: 5}
+    masks = np.zeros((F, H, W), np.uint8); mvalid = np.zeros(F, np.uint8); mstamp = np.full(F, -1.0)
+    for at, src in deliveries.items():
+        masks[at] = seq.mask[src, 0].numpy(); mvalid[at] = 1; mstamp[at] = stamps[src]
+    masks[22] = 0                      # an empty (uninformative) mask: skipped
+    mstamp[24] = 55.5                  # a stamp that matches no queued frame: falls back to the current flow
+    flows = np.ascontiguousarray(seq.flow[:, 0].numpy())
+    fvalid = np.ones(F, np.uint8); fvalid[0] = 0
+    out = np.zeros((F, H, W), np.uint8); avail = np.zeros(F, np.uint8)
+    fn = hostlib.rofth_stamped_sync_run
+    fn.argtypes = [ctypes.c_int] * 4 + [ctypes.c_float, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    rc = fn(W, H, 13 if fmt == "f32" else 11, cfg.flow_grid, cfg.flow_scale, F, masks.ctypes.data, mvalid.ctypes.data, mstamp.ctypes.data,
+            flows.ctypes.data, fvalid.ctypes.data, stamps.ctypes.data, -1, out.ctypes.data, avail.ctypes.data)
+    assert rc == 0
+    src = o.StampedOFAidedSegmentationSource(cfg)
+    longest = 0
+    for k in range(F):
+        if mvalid[k]:
+            longest = max(longest, len(src.queue.get_buffer_region(mstamp[k])))
+        src.step_frame(masks[k] if mvalid[k] else None, mstamp[k], flows[k] if fvalid[k] else None, stamps[k])
+        ok, m = src.segmentation()
+        assert bool(avail[k]) == ok, k
+        if ok:
+            assert np.array_equal(out[k], m), (k, int((out[k] != m).sum()))
+    assert longest > 8                 # a chain longer than the filter loop's ROFTB_MAX_DELAY went through the operator
