@@ -186,3 +186,128 @@ def test_stamped_mask_sync_matches_oracle(hostlib, fmt):
         if ok:
             assert np.array_equal(out[k], m), (k, int((out[k] != m).sum()))
     assert longest > 8                 # a chain longer than the filter loop's ROFTB_MAX_DELAY went through the operator
+
+
+CFG_TEXT = """
+# flattened and overridden like the reference's ConfigParser
+sample_time = 0.033333333333;
+camera_dataset:
+{
+    width = 320; height = 180;      // two settings on one line
+    fx = 307.35714; fy = 307.35714; cx = 160.0; cy = 90.0;
+    path = "?";
+    heading_zeros = 0; index_offset = 0;
+}
+/* nested groups */
+initial_condition: { pose: { v = [0.0, 0.0, 0.0]; cov_q = [0.001, 0.001, 0.001]; axis_angle = [1.0, 0.0, 0.0, 0.0]; } }
+measurement_model = { velocity: { subsampling_radius = 35.0; weight_flow = true; cov_flow = [1.0, 1.0]; } use_pose = true; }
+segmentation_dataset: { set = "mrcnn"; desired_fps = 5.0; counts = [1, 2, 3]; }
+"""
+
+
+def _config_dump(hostlib, text, overrides=()):
+    buf = ctypes.create_string_buffer(1 << 16)
+    paths = (ctypes.c_char_p * max(1, len(overrides)))(*[p.encode() for p, _ in overrides])
+    vals = (ctypes.c_char_p * max(1, len(overrides)))(*[v.encode() for _, v in overrides])
+    rc = hostlib.rofth_config_dump(text.encode(), paths, vals, len(overrides), buf, len(buf))
+    out = buf.value.decode()
+    if rc != 0:
+        return rc, out
+    d = {}
+    for line in out.strip().split("\n"):
+        k, t, v = line.split("\t")
+        d[k] = (t, v)
+    return 0, d
+
+
+def test_config_parser_grammar_and_overrides(hostlib):
+    """f3: the libconfig subset + `--a::b::c value` overrides of the reference's front-end (ConfigParser.cpp:8-169)."""
+    rc, d = _config_dump(hostlib, CFG_TEXT)
+    assert rc == 0
+    assert d["sample_time"] == ("float", "0.033333333333")
+    assert d["camera_dataset.width"] == ("int", "320") and d["camera_dataset.path"] == ("string", "?")
+    assert d["initial_condition.pose.axis_angle"] == ("array", "1.0,0.0,0.0,0.0")
+    assert d["measurement_model.velocity.weight_flow"] == ("bool", "true") and d["measurement_model.use_pose"] == ("bool", "true")
+    assert d["segmentation_dataset.counts"] == ("array", "1,2,3")
+    rc, d = _config_dump(hostlib, CFG_TEXT, [("measurement_model::velocity::subsampling_radius", "1.0"),
+                                             ("measurement_model::velocity::weight_flow", "false"),
+                                             ("measurement_model::velocity::cov_flow", "2.0, 0.5"),
+                                             ("segmentation_dataset::set", "gt"), ("camera_dataset::width", "640")])
+    assert rc == 0
+    assert d["measurement_model.velocity.subsampling_radius"][1] == "1.0" and d["measurement_model.velocity.weight_flow"][1] == "false"
+    assert d["measurement_model.velocity.cov_flow"][1] == "2.0,0.5" and d["segmentation_dataset.set"][1] == "gt"
+    assert d["camera_dataset.width"][1] == "640"
+    # errors: unknown option, wrong type, wrong array length, syntax error with file:line
+    assert _config_dump(hostlib, CFG_TEXT, [("camera_dataset::nope", "1")])[0] == -1
+    assert _config_dump(hostlib, CFG_TEXT, [("measurement_model::velocity::weight_flow", "maybe")])[0] == -1
+    assert _config_dump(hostlib, CFG_TEXT, [("measurement_model::velocity::cov_flow", "1.0")])[0] == -1
+    rc, msg = _config_dump(hostlib, "a = 1;\nb: { c = ; }\n")
+    assert rc == -1 and "<string>:2" in msg
+
+
+def test_config_parser_reads_the_reference_files(hostlib):
+    """The reference's own configuration files parse, with the values SURVEY.md quotes (skipped where the read-only
+    reference tree is not mounted, e.g. on the GPU box)."""
+    path = "/root/reference/config/config_fast_ycb.cfg"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not available")
+    rc, d = _config_dump(hostlib, open(path).read())
+    assert rc == 0, d
+    assert d["camera_dataset.width"][1] == "1280" and d["camera_dataset.fx"][1] == "1229.4285612615463"
+    assert d["measurement_model.velocity.subsampling_radius"][1] == "35.0" and d["measurement_model.velocity.weight_flow"][1] == "true"
+    assert d["segmentation_dataset.desired_fps"][1] == "5.0" and d["pose_dataset.delay"][1] == "true"
+    assert d["unscented_transform.alpha"][1] == "1.0" and d["outlier_rejection.gain"][1] == "0.01"
+    rc, d2 = _config_dump(hostlib, open("/root/reference/config/config_ho3d.cfg").read())
+    assert rc == 0 and d2["camera_dataset.width"][1] == "640"
+
+
+@pytest.mark.gpu
+def test_tracker_executable_config_front_end(hostlib, tmp_path):
+    """`roft_b200_tracker --from file.cfg --group::key value ...` (main.cpp:41-424) gives the same log as the flag front-end."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    cfg = small_cfg(subsampling_radius=4.0, segm_delay=3, pose_delay=3, sample_time=1.0 / 30.0)
+    F = 8
+    seq = sequence(cfg, 1, F, target_coverage=0.3)
+    root = str(tmp_path / "seq0")
+    dataset_io.write_sequence(root, seq, 0, fx=cfg.fx, fy=cfg.fy, cx=cfg.cx, cy=cfg.cy)
+    aa = dataset_io.quat_to_axis_angle(seq.pose[0, 0].numpy()[3:])
+    x0 = seq.pose[0, 0, :3].numpy()
+    text = f"""
+sample_time = 0.033333333333;
+camera_dataset: {{ width = {cfg.width}; height = {cfg.height}; fx = {cfg.fx!r}; fy = {cfg.fy!r}; cx = {cfg.cx!r}; cy = {cfg.cy!r};
+                  path = "?"; heading_zeros = 0; index_offset = 0; }}
+initial_condition: {{
+  pose: {{ v = [0.0, 0.0, 0.0]; w = [0.0, 0.0, 0.0]; x = [{x0[0]!r}, {x0[1]!r}, {x0[2]!r}]; axis_angle = [{aa[0]!r}, {aa[1]!r}, {aa[2]!r}, {aa[3]!r}];
+          cov_v = [0.001, 0.001, 0.001]; cov_w = [0.001, 0.001, 0.001]; cov_x = [0.001, 0.001, 0.001]; cov_q = [0.001, 0.001, 0.001]; }}
+  velocity: {{ v = [0.0, 0.0, 0.0]; w = [0.0, 0.0, 0.0]; cov_v = [0.001, 0.001, 0.001]; cov_w = [0.001, 0.001, 0.001]; }} }}
+kinematic_model: {{ pose: {{ sigma_linear = [1.0, 1.0, 1.0]; sigma_angular = [1.0, 1.0, 1.0]; }}
+                   velocity: {{ sigma_linear = [0.1, 0.1, 0.1]; sigma_angular = [0.1, 0.1, 0.1]; }} }}
+log: {{ enable = true; enable_segmentation = false; path = "?"; }}
+measurement_model: {{ pose: {{ cov_v = [0.1, 0.1, 0.1]; cov_w = [0.0001, 0.0001, 0.0001]; cov_x = [0.001, 0.001, 0.001]; cov_q = [0.0001, 0.0001, 0.0001]; }}
+                     velocity: {{ cov_flow = [1.0, 1.0]; depth_maximum = 2.0; subsampling_radius = 35.0; weight_flow = true; }}
+                     use_pose = true; use_pose_resync = true; use_velocity = true; }}
+model: {{ name = "003_cracker_box"; }}
+optical_flow_dataset: {{ path = "?"; set = "nvof"; heading_zeros = 0; index_offset = 0; }}
+outlier_rejection: {{ enable = false; gain = 0.01; }}
+pose_dataset: {{ path = "?"; skip_rows = 0; skip_cols = 0; fps_reduction = true; delay = true; original_fps = 30.0; desired_fps = 5.0; }}
+segmentation_dataset: {{ path = "?"; format = "pgm"; set = "gt"; heading_zeros = 0; index_offset = 0; fps_reduction = true; delay = true;
+                        original_fps = 30.0; desired_fps = 5.0; flow_aided = true; }}
+unscented_transform: {{ alpha = 1.0; beta = 2.0; kappa = 0.0; }}
+"""
+    cfg_path = tmp_path / "tracker.cfg"
+    cfg_path.write_text(text)
+    log_a, log_b = tmp_path / "log_a", tmp_path / "log_b"
+    log_a.mkdir(); log_b.mkdir()
+    exe = os.path.join(HOST, "roft_b200_tracker")
+    a = subprocess.run([exe, "--from", str(cfg_path), "--camera_dataset::path", root, "--optical_flow_dataset::path", root,
+                        "--segmentation_dataset::path", root, "--pose_dataset::path", root + "/gt/poses.txt", "--log::path", str(log_a),
+                        "--measurement_model::velocity::subsampling_radius", "4.0", "--segmentation_dataset::desired_fps", "10.0",
+                        "--pose_dataset::desired_fps", "10.0"], capture_output=True, text=True)
+    assert a.returncode == 0, a.stdout + a.stderr
+    b = subprocess.run([exe, "--sequence", root, "--log", str(log_b), "--stride", "4", "--desired-fps", "10"], capture_output=True, text=True)
+    assert b.returncode == 0, b.stdout + b.stderr
+    pa = np.loadtxt(log_a / "track0_pose_estimate.txt"); pb = np.loadtxt(log_b / "track0_pose_estimate.txt")
+    va = np.loadtxt(log_a / "track0_velocity_estimate.txt"); vb = np.loadtxt(log_b / "track0_velocity_estimate.txt")
+    assert pa.shape == (F, 13) and np.allclose(pa, pb, rtol=1e-9, atol=1e-12) and np.allclose(va, vb, rtol=1e-9, atol=1e-12)
