@@ -272,8 +272,8 @@ def test_tracker_executable_config_front_end(hostlib, tmp_path):
     seq = sequence(cfg, 1, F, target_coverage=0.3)
     root = str(tmp_path / "seq0")
     dataset_io.write_sequence(root, seq, 0, fx=cfg.fx, fy=cfg.fy, cx=cfg.cx, cy=cfg.cy)
-    aa = dataset_io.quat_to_axis_angle(seq.pose[0, 0].numpy()[3:])
-    x0 = seq.pose[0, 0, :3].numpy()
+    aa = [float(v) for v in dataset_io.quat_to_axis_angle(seq.pose[0, 0].numpy()[3:])]
+    x0 = [float(v) for v in seq.pose[0, 0, :3].numpy()]
     text = f"""
 sample_time = 0.033333333333;
 camera_dataset: {{ width = {cfg.width}; height = {cfg.height}; fx = {cfg.fx!r}; fy = {cfg.fy!r}; cx = {cfg.cx!r}; cy = {cfg.cy!r};
