@@ -308,6 +308,6 @@ unscented_transform: {{ alpha = 1.0; beta = 2.0; kappa = 0.0; }}
     assert a.returncode == 0, a.stdout + a.stderr
     b = subprocess.run([exe, "--sequence", root, "--log", str(log_b), "--stride", "4", "--desired-fps", "10"], capture_output=True, text=True)
     assert b.returncode == 0, b.stdout + b.stderr
-    pa = np.loadtxt(log_a / "track0_pose_estimate.txt"); pb = np.loadtxt(log_b / "track0_pose_estimate.txt")
-    va = np.loadtxt(log_a / "track0_velocity_estimate.txt"); vb = np.loadtxt(log_b / "track0_velocity_estimate.txt")
+    pa = np.loadtxt(log_a / "pose_estimate.txt"); pb = np.loadtxt(log_b / "pose_estimate.txt")
+    va = np.loadtxt(log_a / "velocity_estimate.txt"); vb = np.loadtxt(log_b / "velocity_estimate.txt")
     assert pa.shape == (F, 13) and np.allclose(pa, pb, rtol=1e-9, atol=1e-12) and np.allclose(va, vb, rtol=1e-9, atol=1e-12)
