@@ -149,10 +149,11 @@ __global__ void __launch_bounds__(kThreads) k_warp_init(const WarpPlan* __restri
                                                        long long new_stride, const uint8_t* __restrict__ state_src,
                                                        uint8_t* __restrict__ state_dst, int32_t* __restrict__ winner,
                                                        const uint8_t* __restrict__ occ_src, uint8_t* __restrict__ occ_dst,
-                                                       int HW, int n_units) {
+                                                       int HW, int n_units, unsigned long long* span) {
     const int t = blockIdx.y;
     const WarpPlan p = plan[t];
     if (p.fused) return;  // the velocity kernel clears (lazily) and propagates this track's mask
+    span_stamp(span, false);
     const int n16 = HW >> 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint4* dst = reinterpret_cast<uint4*>(state_dst + (long long)t * HW);
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(kThreads) k_warp_init(const WarpPlan* __restri
             if (of && (lane & 7) == 0 && u < n_units) of[u] = any ? 1 : 0;
         }
     }
+    span_stamp(span, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -220,13 +222,14 @@ __global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft
                                                           uint8_t* __restrict__ state_dst, int32_t* __restrict__ winner,
                                                           const int32_t* __restrict__ s_list, const int32_t* __restrict__ s_n,
                                                           const int32_t* __restrict__ n_list, const int32_t* __restrict__ n_n,
-                                                          int n_warp_tiles, uint8_t* __restrict__ occ_dst) {
+                                                          int n_warp_tiles, uint8_t* __restrict__ occ_dst, unsigned long long* span) {
     const int t = blockIdx.y;
     __shared__ WarpPlan sp;
     __shared__ int32_t s_px[kThreads / 32][kScUnits * kUnitPx];
     if (threadIdx.x == 0) sp = plan[t];
     __syncthreads();
     if (sp.mode != kWarpScatter || sp.fused) return;
+    span_stamp(span, false);
     const uint8_t* src = sp.src_new ? track_plane(new_mask, new_stride, t) : state_src + (long long)t * g.HW;
     uint8_t* dst = state_dst + (long long)t * g.HW;
     int32_t* win = winner + (long long)t * g.HW;
@@ -340,16 +343,18 @@ __global__ void __launch_bounds__(kThreads) k_warp_scatter(Geom g, FrameTable ft
         }
         __syncwarp();  // the batch buffer is reused
     }
+    span_stamp(span, true);
 }
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_warp_gather(const WarpPlan* __restrict__ plan, const uint8_t* __restrict__ new_mask,
                                                          long long new_stride, const uint8_t* __restrict__ state_src,
                                                          uint8_t* __restrict__ state_dst, const int32_t* __restrict__ winner,
-                                                         uint8_t* __restrict__ occ_dst, int HW, int n_units) {
+                                                         uint8_t* __restrict__ occ_dst, int HW, int n_units, unsigned long long* span) {
     const int t = blockIdx.y;
     const WarpPlan p = plan[t];
     if (p.mode != kWarpScatter || p.uniform_val != 0) return;
+    span_stamp(span, false);
     const uint8_t* src = p.src_new ? track_plane(new_mask, new_stride, t) : state_src + (long long)t * HW;
     const int4* win = reinterpret_cast<const int4*>(winner + (long long)t * HW);
     uint32_t* dst = reinterpret_cast<uint32_t*>(state_dst + (long long)t * HW);
@@ -374,6 +379,7 @@ __global__ void __launch_bounds__(kThreads) k_warp_gather(const WarpPlan* __rest
         const bool any = __any_sync(0xffffffffu, out != 0u);
         if (of && lane == 0) of[u] = any ? 1 : 0;
     }
+    span_stamp(span, true);
 }
 
 __global__ void __launch_bounds__(kThreads) k_threshold(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n16) {
@@ -412,7 +418,7 @@ int launch_mask_init(const MaskSyncArgs& a, cudaStream_t s) {
     const int T = a.n_tracks;
     const int HW = a.g.HW;
     ROFTB_LAUNCH(k_warp_init, dim3(plane_blocks(HW >> 4, T), T), kThreads, 0, s, a.plan, a.new_mask, a.new_stride, a.state_src,
-                 a.state_dst, a.winner, a.occ_src, a.occ_dst, HW, a.n_warp_tiles);
+                 a.state_dst, a.winner, a.occ_src, a.occ_dst, HW, a.n_warp_tiles, a.span_clock);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -431,12 +437,12 @@ int launch_mask_scatter_gather(const MaskSyncArgs& a, cudaStream_t s) {
     int bs = max(1, min((a.n_warp_tiles + 7) / 8, (148 * 16 + T - 1) / T));
     if (!a.g.flow_s16 && a.g.grid == 1 && a.g.scale_mode == 0)
         ROFTB_LAUNCH(k_warp_scatter<true>, dim3(bs, T), kThreads, 0, s, a.g, a.ft, a.plan, a.new_mask, a.new_stride, a.state_src,
-                     a.state_dst, a.winner, a.s_list, a.s_n, a.n_list, a.n_n, a.n_warp_tiles, a.occ_dst);
+                     a.state_dst, a.winner, a.s_list, a.s_n, a.n_list, a.n_n, a.n_warp_tiles, a.occ_dst, a.span_clock ? a.span_clock + 2 : nullptr);
     else
         ROFTB_LAUNCH(k_warp_scatter<false>, dim3(bs, T), kThreads, 0, s, a.g, a.ft, a.plan, a.new_mask, a.new_stride, a.state_src,
-                     a.state_dst, a.winner, a.s_list, a.s_n, a.n_list, a.n_n, a.n_warp_tiles, a.occ_dst);
+                     a.state_dst, a.winner, a.s_list, a.s_n, a.n_list, a.n_n, a.n_warp_tiles, a.occ_dst, a.span_clock ? a.span_clock + 2 : nullptr);
     ROFTB_LAUNCH(k_warp_gather, dim3(bq, T), kThreads, 0, s, a.plan, a.new_mask, a.new_stride, a.state_src, a.state_dst,
-                 a.winner, a.occ_dst, HW, a.n_warp_tiles);
+                 a.winner, a.occ_dst, HW, a.n_warp_tiles, a.span_clock ? a.span_clock + 4 : nullptr);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -56,6 +56,7 @@ struct roftb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr, prep_stream = nullptr,
                  aux_stream = nullptr;
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+    unsigned long long* span_clock = nullptr;        // diagnostics: [8 steps][init, scatter, gather, velocity, ukf][2]
     cudaStream_t vel_side[2] = {nullptr, nullptr};   // larger-cluster launches of the velocity kernel (biggest tracks)
     cudaEvent_t vel_fork = nullptr, vel_join[2] = {nullptr, nullptr};
     cudaEvent_t prep_event[2] = {nullptr, nullptr}, prep2_event[2] = {nullptr, nullptr}, vel_done_event = nullptr;
@@ -78,6 +79,7 @@ struct roftb_ctx {
     unsigned long long* phase_clock = nullptr;  // [T][8] phase stamps of the velocity kernel (profiling)
     int32_t* vel_order = nullptr;   // [2][T] scheduling order of the velocity kernel (by step parity), largest worklist first
     uint32_t* vel_ticket = nullptr;
+    int32_t* order_units = nullptr;   // flagged units per track of the freshly synchronised state (k_order_from_flags)
     int32_t* wt_list = nullptr;     // state-mask worklist (only for masks scattered by the stand-alone kernel)
     int32_t* wt_n = nullptr;
     int32_t* nl_count = nullptr;    // newly delivered mask worklist
@@ -280,7 +282,10 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));  // numerically lower = higher priority
     const char* env_prio = getenv("ROFTB_STREAM_PRIORITIES");
     const bool flat = !(env_prio && env_prio[0] == '1');
-    const int prio_main = flat ? prio_hi : std::min(prio_lo, prio_hi + 1);
+    const bool side_first = env_prio && env_prio[0] == '2';  // only the larger-cluster launches above everything else
+    const int prio_main = (flat && !side_first) ? prio_hi : std::min(prio_lo, prio_hi + 1);
+    const int prio_side = side_first ? prio_hi : prio_main;
+    if (side_first) prio_hi = prio_main;
     const int prio_ukf = prio_hi;
     CKC(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_main));
     CKC(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_main));
@@ -290,7 +295,7 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(cudaStreamCreateWithPriority(&ctx->mask_stream, cudaStreamNonBlocking, prio_hi));
     CKC(cudaStreamCreateWithPriority(&ctx->prep_stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 2; ++i) {
-        CKC(cudaStreamCreateWithPriority(&ctx->vel_side[i], cudaStreamNonBlocking, prio_main));
+        CKC(cudaStreamCreateWithPriority(&ctx->vel_side[i], cudaStreamNonBlocking, prio_side));
         CKC(cudaEventCreateWithFlags(&ctx->vel_join[i], cudaEventDisableTiming));
     }
     CKC(cudaEventCreateWithFlags(&ctx->vel_fork, cudaEventDisableTiming));
@@ -346,8 +351,11 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(dalloc(&ctx->wl_units, (size_t)T));
     CKC(dalloc(&ctx->wl_pixels, (size_t)T));
     CKC(dalloc(&ctx->phase_clock, (size_t)T * 8));
+    CKC(dalloc(&ctx->span_clock, (size_t)8 * 10));
+    CKC(cudaMemset(ctx->span_clock, 0xFF, 8 * 10 * sizeof(unsigned long long)));
     CKC(dalloc(&ctx->vel_order, (size_t)2 * T));
-    CKC(dalloc(&ctx->vel_ticket, (size_t)1));
+    CKC(dalloc(&ctx->vel_ticket, (size_t)2));  // [0] velocity kernel, [1] k_order_from_flags
+    CKC(dalloc(&ctx->order_units, (size_t)T));
     CKC(dalloc(&ctx->wt_count2, (size_t)T * ctx->n_warp_tiles));
     CKC(dalloc(&ctx->wt_list, (size_t)2 * T * ctx->n_units));   // x2: worklists / plans are double-buffered by step parity
     CKC(dalloc(&ctx->wt_n, (size_t)4 * T));
@@ -412,7 +420,7 @@ void roftb_destroy(roftb_ctx* ctx) {
     void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->mask_state[2], ctx->mask_occ[0], ctx->mask_occ[1], ctx->mask_occ[2],
                      ctx->winner, ctx->scratch.nu, ctx->scratch.dp, ctx->scratch.r, ctx->scratch.hist, ctx->scratch.chunk_cnt,
                      ctx->scratch.part, ctx->scratch.track_sel, ctx->scratch.sel_part, ctx->scratch.slot_bitmap, ctx->scratch.track_slot, ctx->scratch.chunk_aux,
-                     ctx->wl_units, ctx->wl_pixels, ctx->phase_clock, ctx->vel_order, ctx->vel_ticket,
+                     ctx->wl_units, ctx->wl_pixels, ctx->phase_clock, ctx->span_clock, ctx->vel_order, ctx->vel_ticket, ctx->order_units,
                      ctx->wt_count2, ctx->wt_list, ctx->wt_n, ctx->nl_count, ctx->nl_list, ctx->nl_n, ctx->stat, ctx->plan, ctx->fbuf, ctx->v_mean,
                      ctx->v_cov, ctx->p_mean, ctx->p_cov, ctx->pb_mean, ctx->pb_cov, ctx->vel_hist, ctx->q_diag,
                      ctx->d_count, ctx->d_lambda, ctx->d_eta, ctx->d_wctl, ctx->d_vctl, ctx->d_ops, ctx->d_nops,
@@ -551,6 +559,47 @@ int roftb_profile(roftb_ctx* ctx, int32_t enable, double* ms_per_step, int64_t* 
                 fprintf(stderr, "[roftb] units per track min %d mean %.0f max %d; track latency mean %.1f us max %.1f us (track %d, %d units)\n",
                         umin, nt ? (double)usum / nt : 0.0, umax, nt ? tsum / nt * 1e-3 : 0.0, tmax * 1e-3, t_of_max, wu[t_of_max]);
             }
+            if (atoi(getenv("ROFTB_PHASE_DEBUG")) >= 2 && nt) {  // clusters in flight over the launch, start/end of the biggest tracks
+                std::vector<int32_t> wu(ctx->T);
+                cudaMemcpy(wu.data(), ctx->wl_units, wu.size() * 4, cudaMemcpyDeviceToHost);
+                const double span = (double)(last - first);
+                fprintf(stderr, "[roftb] clusters in flight at 5%% steps of the span:");
+                for (int q = 0; q < 20; ++q) {
+                    const unsigned long long at = first + (unsigned long long)(span * (q + 0.5) / 20.0);
+                    int n_in = 0;
+                    for (int t = 0; t < ctx->T; ++t) {
+                        const unsigned long long* c = &clk[(size_t)t * 8];
+                        if (c[0] && c[0] <= at && c[7] > at) ++n_in;
+                    }
+                    fprintf(stderr, " %d", n_in);
+                }
+                fprintf(stderr, "\n");
+                std::vector<int> idx(ctx->T);
+                for (int t = 0; t < ctx->T; ++t) idx[t] = t;
+                std::sort(idx.begin(), idx.end(), [&](int x, int y) { return wu[x] > wu[y]; });
+                for (int i = 0; i < std::min(ctx->T, 6); ++i) {
+                    const unsigned long long* c = &clk[(size_t)idx[i] * 8];
+                    fprintf(stderr, "[roftb]   track %d (%d units): start +%.1f us, end +%.1f us\n", idx[i], wu[idx[i]],
+                            (double)(c[0] - first) * 1e-3, (double)(c[7] - first) * 1e-3);
+                }
+            }
+            if (atoi(getenv("ROFTB_PHASE_DEBUG")) >= 2) {  // first start / last end of the kernels of the last 8 steps
+                cudaDeviceSynchronize();
+                unsigned long long sc[80];
+                cudaMemcpy(sc, ctx->span_clock, sizeof(sc), cudaMemcpyDeviceToHost);
+                unsigned long long t0 = ~0ull;
+                for (int i = 0; i < 80; i += 2) t0 = std::min(t0, sc[i]);
+                static const char* kn[5] = {"init", "scatter", "gather", "velocity", "ukf"};
+                for (int q = 0; q < 8; ++q) {
+                    const long long fi = ctx->frame_idx - 8 + q;
+                    if (fi < 0) continue;
+                    const unsigned long long* c = sc + (size_t)(fi % 8) * 10;
+                    fprintf(stderr, "[roftb] step %lld:", fi);
+                    for (int j = 0; j < 5; ++j)
+                        if (c[2 * j] != ~0ull) fprintf(stderr, " %s %.0f-%.0f", kn[j], (double)(c[2 * j] - t0) * 1e-3, (double)(~c[2 * j + 1] - t0) * 1e-3);
+                    fprintf(stderr, "\n");
+                }
+            }
             fprintf(stderr, "[roftb] velocity kernel: cluster %d, slots %d, tracks %d, kernel span %.1f us; per-track mean ns:"
                             " prologue %.0f | passA %.0f | pair %.0f | level1 %.0f | level2 %.0f | passB %.0f | epilogue %.0f\n",
                     velocity_cluster_size(), ctx->scratch.n_slots, nt, nt ? (double)(last - first) * 1e-3 : 0.0,
@@ -620,7 +669,7 @@ int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mea
         std::vector<int32_t> ord((size_t)2 * T);
         for (int t = 0; t < T; ++t) ord[t] = ord[(size_t)T + t] = t;
         CK(cudaMemcpy(ctx->vel_order, ord.data(), ord.size() * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemset(ctx->vel_ticket, 0, 4));
+        CK(cudaMemset(ctx->vel_ticket, 0, 8));
     }
     CK(cudaMemset(ctx->d_count, 0, sizeof(int32_t) * T));
     ctx->mask_cur = 0;
@@ -902,6 +951,12 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
     ma.segm_delay = cfg.segm_delay;
     ma.s_list = wt_list; ma.s_n = wt_n; ma.n_list = nl_list; ma.n_n = nl_n; ma.n_warp_tiles = ctx->n_units;
     ma.fuse = 1;
+    unsigned long long* span = nullptr;
+    if (pe) {
+        span = ctx->span_clock + (size_t)(ctx->frame_idx % 8) * 10;
+        CK(cudaMemsetAsync(span, 0xFF, 10 * sizeof(unsigned long long), ctx->prep_stream));
+    }
+    ma.span_clock = span;
     {
         cudaStream_t ps = ctx->prep_stream;
         // worklist of a newly delivered mask; the same read gathers the statistics the plan needs
@@ -948,6 +1003,7 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
         a.out_count = ctx->d_count; a.out_lambda = ctx->d_lambda; a.out_eta = ctx->d_eta;
         a.wl_units = ctx->wl_units; a.wl_pixels = ctx->wl_pixels;
         a.phase_clock = pe ? ctx->phase_clock : nullptr;
+        a.span_clock = span ? span + 6 : nullptr;
         a.order = ctx->vel_order + (size_t)par * T; a.order_next = ctx->vel_order + (size_t)(par ^ 1) * T;
         a.done_ticket = ctx->vel_ticket;
         a.side_stream[0] = ctx->vel_side[0]; a.side_stream[1] = ctx->vel_side[1];
@@ -960,6 +1016,14 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
         CK(cudaEventRecord(ctx->vel_done_event, s));
         ctx->vel_done_event_used = true;
         CK(cudaEventRecord(ctx->vel_event[cslot], s));
+        if (any_new_mask) {
+            // the launch order the velocity kernel left for the next step describes the masks BEFORE this delivery:
+            // redo it from the flags of the new state once both writers of that state are done
+            cudaStream_t ms = ctx->mask_stream;
+            CK(cudaStreamWaitEvent(ms, ctx->vel_done_event, 0));
+            if (launch_order_from_flags(occ_next, ctx->n_units, T, ctx->order_units, ctx->vel_ticket + 1, a.order_next, ms)) return fail(ctx, "launch_order_from_flags failed");
+            CK(cudaEventRecord(ctx->mask_event, ms));
+        }
     }
     {
         cudaStream_t us = ctx->ukf_stream;
@@ -970,6 +1034,7 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
         a.ops = d_ops; a.n_ops = d_nops; a.max_ops = kMaxUkfOps;
         a.mean = ctx->p_mean; a.cov = ctx->p_cov; a.buf_mean = ctx->pb_mean; a.buf_cov = ctx->pb_cov;
         a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
+        a.span_clock = span ? span + 8 : nullptr;
         if (pe) CK(cudaEventRecord(pe[8], us));
         if (launch_ukf(a, us)) return fail(ctx, "launch_ukf failed");
         if (pe) {

@@ -157,6 +157,7 @@ struct MaskSyncArgs {
     int fuse;              // allow k_warp_plan to hand single-flow propagation to the velocity pass
     // occupancy flags [T][n_units] of the two state planes (may be null in operator mode)
     const uint8_t* occ_src; uint8_t* occ_dst;
+    unsigned long long* span_clock;   // diagnostics (may be null): [first start, last end] of init / scatter / gather
 };
 // the mask synchronisation in two halves: (stats, plan, init) must precede a fused velocity pass; (scatter of the
 // non-fused tracks, gather) may run concurrently with the velocity passes
@@ -194,6 +195,7 @@ struct VelocityArgs {
     // optional: two more streams (+ fork / join events) so that the biggest tracks run in larger clusters beside the rest
     cudaStream_t side_stream[2]; cudaEvent_t side_fork; cudaEvent_t side_join[2];
     unsigned long long* phase_clock;                          // device [T][8] globaltimer stamps at the phase boundaries (may be null)
+    unsigned long long* span_clock;                           // diagnostics (may be null): [first start, last end] of the launch
     // fused mask propagation (see WarpPlan::fused): destination plane and its occupancy flags
     int fuse_scatter; const WarpPlan* plan; uint8_t* state_dst; uint8_t* occ_dst;
     int update_state;                  // 0: only compute lambda/eta/count (operator mode)
@@ -208,6 +210,8 @@ int velocity_cluster_size();
 int launch_unit_flags(const uint8_t* plane, long long stride, int HW, int n_items, uint8_t* flags, cudaStream_t s);
 int launch_flag_list(const uint8_t* flags, int n_units, int n_items, int32_t* wt_list, int32_t* wt_n, const WarpPlan* plan,
                      cudaStream_t s);
+int launch_order_from_flags(const uint8_t* flags, int n_units, int n_tracks, int32_t* units_tmp, uint32_t* ticket, int32_t* order,
+                            cudaStream_t s);
 // worklist of the non-empty 128-px units of a byte plane (+ rank base of the bytes > thr); active: optional per-item
 // flags, item i is processed iff active[i * active_stride] != 0
 // stat (optional): non-zero count / min / max of every processed plane, accumulated in the same read
@@ -225,6 +229,7 @@ struct UkfArgs {
     double* mean; double* cov;                              // [T][13], [T][144]
     double* buf_mean; double* buf_cov;                      // buffered belief (may be null)
     const double* vel_hist; int hist_ring;                  // [T][ring][6] (may be null)
+    unsigned long long* span_clock;                         // diagnostics (may be null): [first start, last end]
 };
 int launch_ukf(const UkfArgs& a, cudaStream_t s);
 
@@ -323,6 +328,13 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return r;
 }
 
+// diagnostics: first start / last end of a kernel's blocks on the global timer (both words preset to all ones)
+__device__ __forceinline__ void span_stamp(unsigned long long* span, bool end) {
+    if (!span || threadIdx.x != 0) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(span + (end ? 1 : 0), end ? ~t : t);  // (the end is kept complemented: one preset, all ones, for both)
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -463,19 +463,25 @@ __device__ void ukf_correct_warp(UkfSmem& s, const UkfParams& p, int mtype, cons
     __syncwarp();
 }
 
-// One track (one warp) per block: 27 KB of shared memory and 32 threads - small enough to be resident BESIDE the two
-// CTAs per SM of the velocity kernel (which leaves a quarter of the registers and a third of the shared memory free),
-// so the latency-bound pose filter runs in the issue slots the streaming kernel leaves idle instead of after it.
+// One track (one warp) per block: 27 KB of shared memory and 32 threads, to be resident BESIDE the two CTAs per SM of
+// the velocity kernel so that the latency-bound pose filter runs in the issue slots the streaming kernel leaves idle
+// instead of after it.  What decides that is the register file of an SM SUB-PARTITION (16384 registers): two velocity
+// CTAs put four warps of R registers x 32 lanes there, and a pose warp of U x 32 fits beside them only if
+// 4 * 32 R + 32 U <= 16384.  Left to itself ptxas gives this kernel 164 registers; next to it the second velocity CTA
+// of every SM it touches cannot start (measured: 33 instead of 71 clusters in flight while a pose kernel runs, and a
+// re-sync replay of ~1 ms halves the occupancy of a whole step).  Capped at 128 (no spills) it pairs with R = 96.
 constexpr int kUkfWarps = 1;
 struct UkfWarpSmem { UkfSmem s; double meas[16]; };
 
-__global__ void __launch_bounds__(32 * kUkfWarps) k_ukf_batch(UkfArgs a) {
+template <int REGS>
+__global__ void __maxnreg__(REGS) k_ukf_batch(UkfArgs a) {
     extern __shared__ __align__(16) unsigned char ukf_smem_raw[];
     const int t = blockIdx.x * kUkfWarps + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= a.n_tracks) return;
     const int nops = a.n_ops[t];
     if (nops <= 0) return;
+    span_stamp(a.span_clock, false);
     UkfWarpSmem& wsm = reinterpret_cast<UkfWarpSmem*>(ukf_smem_raw)[threadIdx.x >> 5];
     UkfSmem& s = wsm.s;
     double* meas = wsm.meas;
@@ -517,6 +523,7 @@ __global__ void __launch_bounds__(32 * kUkfWarps) k_ukf_batch(UkfArgs a) {
     }
     if (lane < 13) gm[lane] = s.mean[lane];
     for (int i = lane; i < 144; i += 32) gc[i] = s.P[i / 12][i % 12];
+    span_stamp(a.span_clock, true);
 }
 
 }  // namespace
@@ -524,8 +531,16 @@ __global__ void __launch_bounds__(32 * kUkfWarps) k_ukf_batch(UkfArgs a) {
 int launch_ukf(const UkfArgs& a, cudaStream_t s) {
     const int smem = (int)sizeof(UkfWarpSmem) * kUkfWarps;  // (below the 48 KB that need no opt-in)
     static_assert(sizeof(UkfWarpSmem) * kUkfWarps <= 48 * 1024, "k_ukf_batch would need the shared-memory opt-in per device");
-    ROFTB_LAUNCH(k_ukf_batch, (a.n_tracks + kUkfWarps - 1) / kUkfWarps, 32 * kUkfWarps, smem, s, a);
+    static const int regs = [] { const char* e = getenv("ROFTB_UKF_REGS"); return e ? atoi(e) : 128; }();
+    const int grid = (a.n_tracks + kUkfWarps - 1) / kUkfWarps;
+    if (regs >= 168)
+        ROFTB_LAUNCH(k_ukf_batch<168>, grid, 32 * kUkfWarps, smem, s, a);
+    else if (regs >= 128)
+        ROFTB_LAUNCH(k_ukf_batch<128>, grid, 32 * kUkfWarps, smem, s, a);
+    else
+        ROFTB_LAUNCH(k_ukf_batch<96>, grid, 32 * kUkfWarps, smem, s, a);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
+
 
 }  // namespace roftb

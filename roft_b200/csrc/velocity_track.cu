@@ -205,6 +205,7 @@ struct VtArgs {
     int first;                                            // this launch covers order[first .. first + gridDim.y)
     int total_tracks;                                     // tracks of the step over all launches (ticket target)
     unsigned long long* phase_clock;                      // optional [T][8]
+    unsigned long long* span_clock;                       // optional [2]
     int l2_hint;
     int dbg;                                              // knock-out experiments (timing only, WRONG results): 1 no mask stores, 2 no record stores, 4 no flag stores
     int stage_mode;                                       // pass A staging: 0 = bulk copies + mbarrier, 1 = per-lane cp.async groups
@@ -293,6 +294,7 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
     const unsigned uW = (unsigned)W;
     unsigned long long* clk = (a.phase_clock && rank == 0 && tid == 0) ? a.phase_clock + (long long)t * 8 : nullptr;
     if (clk) clk[0] = global_timer();
+    if (rank == 0) span_stamp(a.span_clock, false);
 
     float* s_xh = reinterpret_cast<float*>(smem + a.smem_tab);
     float* s_yh = s_xh + W;
@@ -1022,14 +1024,16 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
     }
 
     // ================================ pass B =======================================================
-    // Each warp streams the records of its own chunk (two per lane per 128-bit load) and accumulates the 40 sums with
-    // the UN-normalised weights l' = max(exp(-|n - m| / b), 2e-6 b); the true maximum of the likelihoods
+    // The N records are split evenly over the cluster's warps by RANK (the chunks of pass A hold unequal numbers of
+    // valid pixels); a warp walks the one to three chunk segments its rank range covers.  The 40 sums use the
+    // UN-normalised weights l' = max(exp(-|n - m| / b), 2e-6 b); the true maximum of the likelihoods
     // (SKFCorrection.cpp:114) follows from the smallest |n - m| seen and is divided out in the epilogue.
     {
-        const int cntg = s_cnt[gchunk];
-        const long long rec0 = (long long)gchunk * chunk_stride;
-        const float4* nu4 = reinterpret_cast<const float4*>(nu_t + rec0);
-        const uint4* dp4 = reinterpret_cast<const uint4*>(dp_t + rec0);
+        const int per_b = (N + n_chunks - 1) / n_chunks;
+        const int lo0 = min(N, gchunk * per_b), hi0 = min(N, lo0 + per_b);
+        int c0 = 0;  // chunk holding rank lo0
+        for (int i = lane; i < n_chunks; i += 32) c0 += (s_base[i + 1] <= lo0) ? 1 : 0;
+        c0 = min(warp_sum(c0), n_chunks - 1);
         float dmin = 3.0e38f;
         const bool fp64 = a.accum_fp64 == 1 || (a.accum_fp64 == 2 && N < kAutoFp64Candidates);
         double* out = &s_part[warp][0];
@@ -1068,33 +1072,43 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
                 for (int kk = 0; kk < 5; ++kk) acc2[15 + kk] = __ffma2_rn(w[kk], zz, acc2[15 + kk]);
             };
             // software pipeline: the four records of the NEXT trip are in flight while this trip's are accumulated
-            auto fetch = [&](int k, float4& A, uint4& DA, float4& B, uint4& DB) {
-                A = make_float4(0.f, 0.f, 0.f, 0.f);
-                B = A;
-                DA = make_uint4(0u, 0u, 0u, 0u);
-                DB = DA;
-                if (k < cntg) {
-                    A = __ldcg(nu4 + (k >> 1));
-                    DA = __ldcg(dp4 + (k >> 1));
-                }
-                if (k + 64 < cntg) {
-                    B = __ldcg(nu4 + ((k + 64) >> 1));
-                    DB = __ldcg(dp4 + ((k + 64) >> 1));
+            auto fetch = [&](const float2* nup, const uint2* dpp, int k, int n, float2 (&A)[4], uint2 (&D)[4]) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    A[u] = make_float2(0.f, 0.f);
+                    D[u] = make_uint2(0u, 0u);
+                    if (k + 32 * u < n) {
+                        A[u] = __ldcg(nup + k + 32 * u);
+                        D[u] = __ldcg(dpp + k + 32 * u);
+                    }
                 }
             };
-            float4 A, B;
-            uint4 DA, DB;
-            fetch(2 * lane, A, DA, B, DB);
+            int lo = lo0, c = c0;
 #pragma unroll 1
-            for (int k = 2 * lane; k < cntg; k += 128) {
-                float4 An, Bn;
-                uint4 DAn, DBn;
-                fetch(k + 128, An, DAn, Bn, DBn);
-                accum(A.x, A.y, DA.x, DA.y, true);
-                accum(A.z, A.w, DA.z, DA.w, k + 1 < cntg);
-                accum(B.x, B.y, DB.x, DB.y, k + 64 < cntg);
-                accum(B.z, B.w, DB.z, DB.w, k + 65 < cntg);
-                A = An; B = Bn; DA = DAn; DB = DBn;
+            while (lo < hi0) {
+                const int ce = min(hi0, s_base[c + 1]);
+                const int n = ce - lo;
+                const long long off = (long long)c * chunk_stride + (lo - s_base[c]);
+                const float2* nup = nu_t + off;
+                const uint2* dpp = dp_t + off;
+                float2 A[4];
+                uint2 D[4];
+                fetch(nup, dpp, lane, n, A, D);
+#pragma unroll 1
+                for (int k = lane; k < n; k += 128) {
+                    float2 An[4];
+                    uint2 Dn[4];
+                    fetch(nup, dpp, k + 128, n, An, Dn);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) accum(A[u].x, A[u].y, D[u].x, D[u].y, k + 32 * u < n);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        A[u] = An[u];
+                        D[u] = Dn[u];
+                    }
+                }
+                lo = ce;
+                ++c;
             }
 #pragma unroll
             for (int o = 0; o < 15; ++o) {
@@ -1121,10 +1135,12 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
                 double acc[15];
 #pragma unroll
                 for (int i = 0; i < 15; ++i) acc[i] = 0.0;
+                int cc = c0;
 #pragma unroll 1
-                for (int k = lane; k < cntg; k += 32) {
-                    const float2 nn = __ldcg(nu_t + rec0 + k);
-                    const uint2 dpk = __ldcg(dp_t + rec0 + k);
+                for (int k = lo0 + lane; k < hi0; k += 32) {
+                    const long long ri = rec_index(k, cc, s_base, chunk_stride);
+                    const float2 nn = __ldcg(nu_t + ri);
+                    const uint2 dpk = __ldcg(dp_t + ri);
                     const double xh = ((double)(dpk.y & 0xffffu) - a.cx) * ifx, yh = ((double)(dpk.y >> 16) - a.cy) * ify;
                     const float df = __uint_as_float(dpk.x);
                     // 1/d from the FP32 approximation (rel. error < 2^-22) by two Newton steps
@@ -1173,7 +1189,7 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dmin = fminf(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
         if (lane == 0) {
-            out[40] = (double)cntg;
+            out[40] = (double)(hi0 - lo0);
             out[41] = (double)dmin;
         }
         __syncthreads();
@@ -1206,6 +1222,7 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
     }
     __syncwarp();
     if (clk) clk[7] = global_timer();
+    if (lane == 0) span_stamp(a.span_clock, true);
     check_out();
 }
 
@@ -1374,8 +1391,8 @@ int velocity_cluster_size() {
 static int velocity_regs() {
     static const int v = [] {
         const char* e = getenv("ROFTB_VT_REGS");
-        const int r = e ? atoi(e) : 96;
-        return r <= 80 ? 80 : r >= 128 ? 128 : 96;
+        const int r = e ? atoi(e) : 128;
+        return r <= 80 ? 80 : r >= 128 ? 128 : r >= 112 ? 112 : r >= 104 ? 104 : 96;
     }();
     return v;
 }
@@ -1385,6 +1402,8 @@ static VtKernel vt_kernel(bool fast) {
     switch (velocity_regs()) {
         case 80: return fast ? k_velocity_track<true, 80> : k_velocity_track<false, 80>;
         case 128: return fast ? k_velocity_track<true, 128> : k_velocity_track<false, 128>;
+        case 112: return fast ? k_velocity_track<true, 112> : k_velocity_track<false, 112>;
+        case 104: return fast ? k_velocity_track<true, 104> : k_velocity_track<false, 104>;
         default: return fast ? k_velocity_track<true, 96> : k_velocity_track<false, 96>;
     }
 }
@@ -1451,6 +1470,7 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     va.order = a.order; va.order_next = a.order_next;
     va.done_ticket = (a.order_next && a.wl_units) ? a.done_ticket : nullptr;
     va.phase_clock = a.phase_clock;
+    va.span_clock = a.span_clock;
     static const int env_hint = [] { const char* e = getenv("ROFTB_L2HINT"); return e ? atoi(e) : 1; }();
     va.l2_hint = env_hint;
     static const int env_stage = [] { const char* e = getenv("ROFTB_STAGE"); return e ? atoi(e) : 1; }();
@@ -1510,11 +1530,9 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
         const cudaError_t e = cudaLaunchKernelEx(&cfg, vt_kernel(fast), va);
         ++g_launch_count;
         if (e != cudaSuccess) return -1;
-        if (pi + 1 < n_parts) {
-            cudaEventRecord(a.side_join[pi], pt.stream);
-            cudaStreamWaitEvent(s, a.side_join[pi], 0);
-        }
+        if (pi + 1 < n_parts) cudaEventRecord(a.side_join[pi], pt.stream);
     }
+    for (int pi = 0; pi + 1 < n_parts; ++pi) cudaStreamWaitEvent(s, a.side_join[pi], 0);  // join AFTER the last launch
     EpiArgs ea;
     ea.n_tracks = T;
     ea.ctl = a.ctl;
