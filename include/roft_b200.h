@@ -188,6 +188,24 @@ int roftb_masked_points(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, co
  * 0<d<2, rendered!=0: err_sum [n], samples [n]. rendered is [n][H/divider][W/divider]. */
 int roftb_masked_depth_l1(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, const float* depth,
                           const float* rendered, int32_t divider, double* err_sum, int32_t* samples);
+/* Mesh of the tracked object for the render-and-compare pose test: what ROFTFilter's constructor hands to SICAD
+ * (ROFTFilter.cpp:184-199, MeshResource -> SICAD::ModelStreamContainer).  Assimp is not part of this path: the caller
+ * passes the triangles (vertices [n_vertices][3] in the model frame, metres; faces [n_faces][3]).  Host memory. */
+int roftb_set_mesh(roftb_ctx* ctx, const float* vertices, int32_t n_vertices, const int32_t* faces, int32_t n_faces);
+/* SICAD::superimpose(poses, cam_x = 0, cam_o = identity, ..., depth) (SICAD.cpp:924-1066, depth attachment of
+ * shader_model.frag:33-52) for a renderer built like ROFTFilter.cpp:194-198 (every intrinsic / divider, OpenGL-to-camera
+ * rotation pi about x): poses [n_items][7] = (x, y, z, axis x y z, angle) as SICAD::ModelPose; out_depth
+ * [n_items][H/divider][W/divider] = one tile per pose, metres, 0 where nothing is hit.  Host memory. */
+int roftb_render_depth(roftb_ctx* ctx, int32_t n_items, const double* poses7, int32_t divider, float* out_depth);
+/* ROFTFilter::pick_best_alternative (ROFTFilter.cpp:467-621) for n_items tracks: alternatives [n_items][2][13] are the
+ * means of the two corrected beliefs (v, w, x, q wxyz), segmentation / depth [n_items][H][W] the (buffered) features;
+ * renders both, takes the masked depth L1 of each (every 2nd mask pixel, 0 < d < 2, rendered != 0), likelihood = mean
+ * error / gain (DBL_MAX without samples) and selects the second alternative iff likelihood[0] > 2 likelihood[1].
+ * selected [n_items] (0 / 1), likelihoods [n_items][2] (may be NULL).  (The reference always reports success once the
+ * renderer ran; a failed render is an error code here.) */
+int roftb_pick_best_alternative(roftb_ctx* ctx, int32_t n_items, const uint8_t* segmentation, const float* depth,
+                                const double* alternatives, int32_t divider, double gain, int32_t* selected,
+                                double* likelihoods);
 /* bfl::UKFPrediction through CartesianQuaternionModel (CartesianQuaternionModel.cpp:86-141):
  * mean [n][13], cov [n][144] in/out; dt [n]. */
 int roftb_ukf_predict(roftb_ctx* ctx, int32_t n_items, double* mean, double* cov, const double* dt);

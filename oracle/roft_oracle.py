@@ -947,3 +947,117 @@ class RoftFilterOracle:
         else:
             self.p_mean, self.p_cov = pm, pc
         return self.p_mean.copy(), self.v_mean.copy()
+
+
+# ---- pose outlier rejection ------------------------------------------------------------------
+# PARITY UNPINNED: the reference renders with OpenGL (SICAD) whose rasterisation is implementation-defined in the last
+# bits and cannot run here (no GL stack).  The functions below restate the pipeline the reference drives it with; the
+# CUDA rasteriser (roft_b200/csrc/render.cu) follows the same restatement and is compared against it with a tolerance.
+
+def quaternion_to_axis_angle(q: np.ndarray) -> np.ndarray:
+    """Eigen::AngleAxisd(Eigen::Quaterniond(w, x, y, z)) (ROFTFilter.cpp:518-524; UPSTREAM-RECALL of Eigen 3.3+)."""
+    w, v = float(q[0]), np.asarray(q[1:4], np.float64)
+    n = float(np.sqrt(v @ v))
+    if n != 0.0:
+        angle = 2.0 * np.arctan2(n, abs(w))
+        if w < 0.0:
+            n = -n
+        return np.array([v[0] / n, v[1] / n, v[2] / n, angle])
+    return np.array([1.0, 0.0, 0.0, 0.0])
+
+
+def sicad_model_matrix(pose7: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """glm::rotate(I, float(angle), float(axis)) + translation (SICAD.cpp:604-607; UPSTREAM-RECALL of glm), float32."""
+    f = np.float32
+    ang = f(pose7[6])
+    ax = np.asarray(pose7[3:6], np.float64).astype(f)
+    c, s = f(np.cos(ang)), f(np.sin(ang))
+    n = f(np.sqrt(f(f(ax[0] * ax[0] + ax[1] * ax[1]) + ax[2] * ax[2])))
+    if n > 0:
+        ax = (ax / n).astype(f)
+    t = ((f(1) - c) * ax).astype(f)
+    x, y, z = ax
+    R = np.array([[c + t[0] * x, t[1] * x - s * z, t[2] * x + s * y],
+                  [t[0] * y + s * z, c + t[1] * y, t[2] * y - s * x],
+                  [t[0] * z - s * y, t[1] * z + s * x, c + t[2] * z]], f)
+    return R, np.asarray(pose7[:3], np.float64).astype(f)
+
+
+def render_depth(vertices: np.ndarray, faces: np.ndarray, pose7: np.ndarray, width: int, height: int,
+                 fx: float, fy: float, cx: float, cy: float) -> np.ndarray:
+    """SICAD::superimpose depth output for one pose (SICAD.cpp:924-1066, shader_model.frag:33-52).
+
+    Projection matrix of SICAD.cpp:1634-1637 + viewport + cv::flip reduce to u = fx X/Z + cx, v = fy Y/Z + cy with pixel
+    centres at +0.5; window depth (z_ndc + 1) / 2 for near 0.001 / far 1000 in float32; vertices snapped to 1/256 px;
+    inclusive integer edge functions; z interpolated with the integer barycentrics in float64, rounded to float32;
+    nearest fragment wins; linearize_depth() in float32; 0 where nothing is hit.  No clipping: triangles with a
+    vertex outside (near, far) are dropped.
+    """
+    f = np.float32
+    near, far = f(0.001), f(1000.0)
+    R, t = sicad_model_matrix(pose7)
+    V = np.asarray(vertices, f)
+    P = np.empty_like(V)
+    for r in range(3):
+        P[:, r] = ((R[r, 0] * V[:, 0] + R[r, 1] * V[:, 1]).astype(f) + R[r, 2] * V[:, 2]).astype(f) + t[r]
+    X, Y, Z = P[:, 0], P[:, 1], P[:, 2]
+    ok = (Z > near) & (Z < far)
+    iz = (f(1) / np.where(ok, Z, f(1))).astype(f)
+    u = ((f(fx) * X).astype(f) * iz).astype(f) + f(cx)
+    v = ((f(fy) * Y).astype(f) * iz).astype(f) + f(cy)
+    A = f((far + near) / (far - near))
+    B = f(f(f(2) * far * near) / (far - near))
+    zn = (A - (B * iz).astype(f)).astype(f)
+    zw = (f(0.5) * zn).astype(f) + f(0.5)
+    lim = f(1.0e6 * 256)
+    xs = np.rint(np.clip((u * f(256)).astype(f), -lim, lim)).astype(np.int64)
+    ys = np.rint(np.clip((v * f(256)).astype(f), -lim, lim)).astype(np.int64)
+    zbuf = np.full((height, width), np.inf, f)
+    for tri in np.asarray(faces, np.int64):
+        i0, i1, i2 = tri
+        if not (ok[i0] and ok[i1] and ok[i2]):
+            continue
+        area = (xs[i1] - xs[i0]) * (ys[i2] - ys[i0]) - (ys[i1] - ys[i0]) * (xs[i2] - xs[i0])
+        if area == 0:
+            continue
+        if area < 0:
+            i1, i2, area = i2, i1, -area
+        x0, x1, x2, y0, y1, y2 = xs[i0], xs[i1], xs[i2], ys[i0], ys[i1], ys[i2]
+        xmin = max(0, (min(x0, x1, x2) - 128 + 255) >> 8)
+        xmax = min(width - 1, (max(x0, x1, x2) - 128) >> 8)
+        ymin = max(0, (min(y0, y1, y2) - 128 + 255) >> 8)
+        ymax = min(height - 1, (max(y0, y1, y2) - 128) >> 8)
+        if xmin > xmax or ymin > ymax:
+            continue
+        px = np.arange(xmin, xmax + 1, dtype=np.int64)[None, :] * 256 + 128
+        py = np.arange(ymin, ymax + 1, dtype=np.int64)[:, None] * 256 + 128
+        w0 = (x2 - x1) * (py - y1) - (y2 - y1) * (px - x1)
+        w1 = (x0 - x2) * (py - y2) - (y0 - y2) * (px - x2)
+        w2 = area - w0 - w1
+        inside = (w0 >= 0) & (w1 >= 0) & (w2 >= 0)
+        zd = (w0.astype(np.float64) * float(zw[i0]) + w1.astype(np.float64) * float(zw[i1]) +
+              w2.astype(np.float64) * float(zw[i2])) * (1.0 / float(area))
+        zf = zd.astype(f)
+        inside &= (zf >= 0) & (zf <= 1)
+        sub = zbuf[ymin:ymax + 1, xmin:xmax + 1]
+        np.minimum(sub, np.where(inside, zf, np.inf).astype(f), out=sub)
+    hit = np.isfinite(zbuf)
+    z = (np.where(hit, zbuf, f(0)) * f(2)).astype(f) - f(1)
+    lin = (f(f(2) * near * far) / ((far + near) - (z * (far - near)).astype(f)).astype(f)).astype(f)
+    return np.where(hit, lin, f(0)).astype(f)
+
+
+def pick_best_alternative(cfg: "RoftConfig", vertices: np.ndarray, faces: np.ndarray, alternatives: Sequence[np.ndarray],
+                          segmentation: np.ndarray, depth: np.ndarray, divider: int, gain: float):
+    """ROFTFilter::pick_best_alternative, ROFTFilter.cpp:467-621: (selected, likelihoods)."""
+    w, h = cfg.width // divider, cfg.height // divider
+    lik = []
+    for alt in alternatives:
+        aa = quaternion_to_axis_angle(np.asarray(alt[9:13]))
+        pose7 = np.concatenate([np.asarray(alt[6:9], np.float64), aa])
+        rend = render_depth(vertices, faces, pose7, w, h, cfg.fx / divider, cfg.fy / divider, cfg.cx / divider, cfg.cy / divider)
+        err, n = masked_depth_l1(segmentation, depth, rend, divider)
+        lik.append(np.finfo(np.float64).max if n == 0 else (err / n) / gain)
+    with np.errstate(over="ignore"):  # 2 * DBL_MAX = inf, as in C
+        selected = 1 if lik[0] > np.float64(2.0) * np.float64(lik[1]) else 0
+    return selected, np.array(lik)

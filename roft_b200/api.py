@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "roftb_kernel_launches", "roftb_stream", "roftb_profile", "roftb_filter_init", "roftb_filter_step", "roftb_get_state",
     "roftb_get_mask", "roftb_get_velocity_info", "roftb_get_worklist", "roftb_mask_sync", "roftb_flow_velocity", "roftb_velocity_kf",
     "roftb_flow_measurement_export", "roftb_masked_points", "roftb_masked_depth_l1", "roftb_ukf_predict",
-    "roftb_ukf_correct",
+    "roftb_ukf_correct", "roftb_set_mesh", "roftb_render_depth", "roftb_pick_best_alternative",
 ]
 
 
@@ -100,6 +100,10 @@ def load_library() -> C.CDLL:
                                                   C.c_void_p, C.c_void_p, C.c_void_p]
     lib.roftb_masked_points.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]
     lib.roftb_masked_depth_l1.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.roftb_set_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    lib.roftb_render_depth.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.roftb_pick_best_alternative.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double,
+                                                C.c_void_p, C.c_void_p]
     lib.roftb_ukf_predict.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.roftb_ukf_correct.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
@@ -332,6 +336,25 @@ class Tracker:
         self._check(self._lib.roftb_masked_depth_l1(self._h, N, _ptr(mask), _ptr(depth), _ptr(rendered), int(divider),
                                                     _ptr(err), _ptr(cnt)), "roftb_masked_depth_l1")
         return err, cnt
+
+    def set_mesh(self, vertices, faces):
+        v = _np(vertices, np.float32); f = _np(faces, np.int32)
+        self._check(self._lib.roftb_set_mesh(self._h, _ptr(v), int(v.shape[0]), _ptr(f), int(f.shape[0])), "roftb_set_mesh")
+
+    def render_depth(self, poses7, divider: int):
+        p = _np(poses7, np.float64)
+        N = p.shape[0]
+        out = np.empty((N, self.cfg.height // divider, self.cfg.width // divider), np.float32)
+        self._check(self._lib.roftb_render_depth(self._h, N, _ptr(p), int(divider), _ptr(out)), "roftb_render_depth")
+        return out
+
+    def pick_best_alternative(self, segmentation, depth, alternatives, divider: int, gain: float):
+        m = _np(segmentation, np.uint8); d = _np(depth, np.float32); a = _np(alternatives, np.float64)
+        N = m.shape[0]
+        sel = np.empty(N, np.int32); lik = np.empty((N, 2))
+        self._check(self._lib.roftb_pick_best_alternative(self._h, N, _ptr(m), _ptr(d), _ptr(a), int(divider), C.c_double(gain),
+                                                          _ptr(sel), _ptr(lik)), "roftb_pick_best_alternative")
+        return sel, lik
 
     def ukf_predict(self, mean, cov, dt=None):
         mean = _np(mean, np.float64).copy(); cov = _np(cov, np.float64).copy()

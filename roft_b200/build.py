@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "roft_b200", "csrc")
 LIB = os.path.join(ROOT, "roft_b200", "libroft_b200.so")
-SOURCES = ["roftb_api.cu", "mask_sync.cu", "worklist.cu", "velocity_track.cu", "ukf_batch.cu", "extract.cu"]
+SOURCES = ["roftb_api.cu", "mask_sync.cu", "worklist.cu", "velocity_track.cu", "ukf_batch.cu", "extract.cu", "render.cu"]
 
 
 def needs_build() -> bool:

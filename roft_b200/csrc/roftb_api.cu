@@ -56,6 +56,9 @@ struct roftb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr, prep_stream = nullptr,
                  aux_stream = nullptr;
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+    float* mesh_vertices = nullptr;                  // outlier-rejection mesh (roftb_set_mesh): device [n][3]
+    int32_t* mesh_faces = nullptr;
+    int mesh_nv = 0, mesh_nf = 0;
     unsigned long long* span_clock = nullptr;        // diagnostics: [8 steps][init, scatter, gather, velocity, ukf][2]
     cudaStream_t vel_side[2] = {nullptr, nullptr};   // larger-cluster launches of the velocity kernel (biggest tracks)
     cudaEvent_t vel_fork = nullptr, vel_join[2] = {nullptr, nullptr};
@@ -420,7 +423,7 @@ void roftb_destroy(roftb_ctx* ctx) {
     void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->mask_state[2], ctx->mask_occ[0], ctx->mask_occ[1], ctx->mask_occ[2],
                      ctx->winner, ctx->scratch.nu, ctx->scratch.dp, ctx->scratch.r, ctx->scratch.hist, ctx->scratch.chunk_cnt,
                      ctx->scratch.part, ctx->scratch.track_sel, ctx->scratch.sel_part, ctx->scratch.slot_bitmap, ctx->scratch.track_slot, ctx->scratch.chunk_aux,
-                     ctx->wl_units, ctx->wl_pixels, ctx->phase_clock, ctx->span_clock, ctx->vel_order, ctx->vel_ticket, ctx->order_units,
+                     ctx->wl_units, ctx->wl_pixels, ctx->phase_clock, ctx->span_clock, ctx->mesh_vertices, ctx->mesh_faces, ctx->vel_order, ctx->vel_ticket, ctx->order_units,
                      ctx->wt_count2, ctx->wt_list, ctx->wt_n, ctx->nl_count, ctx->nl_list, ctx->nl_n, ctx->stat, ctx->plan, ctx->fbuf, ctx->v_mean,
                      ctx->v_cov, ctx->p_mean, ctx->p_cov, ctx->pb_mean, ctx->pb_cov, ctx->vel_hist, ctx->q_diag,
                      ctx->d_count, ctx->d_lambda, ctx->d_eta, ctx->d_wctl, ctx->d_vctl, ctx->d_ops, ctx->d_nops,
@@ -1393,6 +1396,135 @@ int roftb_masked_depth_l1(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, 
     if (launch_masked_depth_l1(a, d_r, (long long)rsz, divider, d_e, d_n, s)) return fail(ctx, "masked_depth_l1 launch failed");
     CK(cudaMemcpyAsync(err_sum, d_e, (size_t)n_items * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(samples, d_n, (size_t)n_items * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- pose outlier rejection ------------------------------------------------------------------
+namespace {
+
+// Model matrix of SICAD::superimpose (SICAD.cpp:604-607) for a pose (x, y, z, axis, angle): glm::rotate(I, angle, axis)
+// in float (UPSTREAM-RECALL of glm: normalised axis, Rodrigues with c = cos(angle), s = sin(angle)), translation in the
+// last column.  out: rotation row-major (9), translation (3).
+void model_matrix(const double* pose7, float* out) {
+    const float ang = static_cast<float>(pose7[6]);
+    float ax = static_cast<float>(pose7[3]), ay = static_cast<float>(pose7[4]), az = static_cast<float>(pose7[5]);
+    const float c = std::cos(ang), s = std::sin(ang);
+    const float n = std::sqrt(ax * ax + ay * ay + az * az);
+    if (n > 0.f) { ax /= n; ay /= n; az /= n; }
+    const float tx = (1.f - c) * ax, ty = (1.f - c) * ay, tz = (1.f - c) * az;
+    out[0] = c + tx * ax;      out[1] = ty * ax - s * az;  out[2] = tz * ax + s * ay;
+    out[3] = tx * ay + s * az; out[4] = c + ty * ay;       out[5] = tz * ay - s * ax;
+    out[6] = tx * az - s * ay; out[7] = ty * az + s * ax;  out[8] = c + tz * az;
+    out[9] = static_cast<float>(pose7[0]); out[10] = static_cast<float>(pose7[1]); out[11] = static_cast<float>(pose7[2]);
+}
+
+// Eigen::AngleAxisd(Eigen::Quaterniond(w, x, y, z)) as used at ROFTFilter.cpp:518-524 (UPSTREAM-RECALL of Eigen 3.3+:
+// angle = 2 atan2(|v|, |w|), axis = v / (+-|v|) with the sign of w; identity -> angle 0, axis (1, 0, 0))
+void state_to_pose7(const double* state13, double* pose7) {
+    pose7[0] = state13[6]; pose7[1] = state13[7]; pose7[2] = state13[8];
+    const double w = state13[9], x = state13[10], y = state13[11], z = state13[12];
+    double n = std::sqrt(x * x + y * y + z * z);
+    if (n != 0.0) {
+        pose7[6] = 2.0 * std::atan2(n, std::fabs(w));
+        if (w < 0.0) n = -n;
+        pose7[3] = x / n; pose7[4] = y / n; pose7[5] = z / n;
+    } else {
+        pose7[6] = 0.0; pose7[3] = 1.0; pose7[4] = 0.0; pose7[5] = 0.0;
+    }
+}
+
+int render_tiles(roftb_ctx* ctx, TmpBuf& tb, int n_items, const double* poses7, int divider, float** d_out, cudaStream_t s) {
+    const int w = ctx->g.W / divider, h = ctx->g.H / divider;
+    std::vector<float> model((size_t)n_items * 12);
+    for (int i = 0; i < n_items; ++i) model_matrix(poses7 + (size_t)i * 7, &model[(size_t)i * 12]);
+    RenderArgs ra;
+    ra.n_items = n_items;
+    ra.vertices = ctx->mesh_vertices; ra.n_vertices = ctx->mesh_nv;
+    ra.faces = ctx->mesh_faces; ra.n_faces = ctx->mesh_nf;
+    ra.model = tb.upload(model.data(), model.size(), s);
+    // SICAD is constructed with every intrinsic divided by divider_ (ROFTFilter.cpp:194-197)
+    ra.fx = (float)(ctx->cfg.fx / divider); ra.fy = (float)(ctx->cfg.fy / divider);
+    ra.cx = (float)(ctx->cfg.cx / divider); ra.cy = (float)(ctx->cfg.cy / divider);
+    ra.w = w; ra.h = h;
+    void* vs = tb.alloc<char>(render_vertex_scratch_bytes(n_items, ctx->mesh_nv));
+    uint32_t* zb = tb.alloc<uint32_t>((size_t)n_items * w * h);
+    float* out = tb.alloc<float>((size_t)n_items * w * h);
+    if (!ra.model || !vs || !zb || !out) return -1;
+    cudaStreamSynchronize(s);  // `model` is a local vector
+    if (launch_render_depth(ra, vs, zb, out, s)) return -1;
+    *d_out = out;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int roftb_set_mesh(roftb_ctx* ctx, const float* vertices, int32_t n_vertices, const int32_t* faces, int32_t n_faces) {
+    if (!ctx || !vertices || !faces || n_vertices <= 0 || n_faces <= 0) return ctx ? fail(ctx, "roftb_set_mesh: bad argument") : -2;
+    for (int64_t i = 0; i < (int64_t)n_faces * 3; ++i)
+        if (faces[i] < 0 || faces[i] >= n_vertices) return fail(ctx, "roftb_set_mesh: face index out of range");
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->mesh_vertices) cudaFree(ctx->mesh_vertices);
+    if (ctx->mesh_faces) cudaFree(ctx->mesh_faces);
+    ctx->mesh_vertices = nullptr; ctx->mesh_faces = nullptr; ctx->mesh_nv = ctx->mesh_nf = 0;
+    CK(cudaMalloc(&ctx->mesh_vertices, (size_t)n_vertices * 3 * sizeof(float)));
+    CK(cudaMalloc(&ctx->mesh_faces, (size_t)n_faces * 3 * sizeof(int32_t)));
+    CK(cudaMemcpy(ctx->mesh_vertices, vertices, (size_t)n_vertices * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->mesh_faces, faces, (size_t)n_faces * 3 * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ctx->mesh_nv = n_vertices; ctx->mesh_nf = n_faces;
+    return 0;
+}
+
+int roftb_render_depth(roftb_ctx* ctx, int32_t n_items, const double* poses7, int32_t divider, float* out_depth) {
+    if (!ctx || n_items <= 0 || !poses7 || divider <= 0 || !out_depth) return ctx ? fail(ctx, "roftb_render_depth: bad argument") : -2;
+    if (!ctx->mesh_nv) return fail(ctx, "roftb_render_depth: no mesh (roftb_set_mesh)");
+    if (ctx->g.W % divider || ctx->g.H % divider) return fail(ctx, "roftb_render_depth: divider must divide the frame size");
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    TmpBuf tb;
+    float* d_out = nullptr;
+    if (render_tiles(ctx, tb, n_items, poses7, divider, &d_out, s)) return fail(ctx, "roftb_render_depth: launch failed / out of device memory");
+    const size_t tile = (size_t)(ctx->g.W / divider) * (ctx->g.H / divider);
+    CK(cudaMemcpyAsync(out_depth, d_out, (size_t)n_items * tile * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int roftb_pick_best_alternative(roftb_ctx* ctx, int32_t n_items, const uint8_t* segmentation, const float* depth,
+                                const double* alternatives, int32_t divider, double gain, int32_t* selected, double* likelihoods) {
+    if (!ctx || n_items <= 0 || !segmentation || !depth || !alternatives || divider <= 0 || !selected || !(gain != 0.0))
+        return ctx ? fail(ctx, "roftb_pick_best_alternative: bad argument") : -2;
+    if (!ctx->mesh_nv) return fail(ctx, "roftb_pick_best_alternative: no mesh (roftb_set_mesh)");
+    if (ctx->g.W % divider || ctx->g.H % divider) return fail(ctx, "roftb_pick_best_alternative: divider must divide the frame size");
+    CK(cudaSetDevice(ctx->dev));
+    cudaStream_t s = ctx->stream;
+    TmpBuf tb;
+    // tiles laid out [alternative][item]: one masked-L1 launch per alternative over the same masks and depths
+    std::vector<double> poses((size_t)2 * n_items * 7);
+    for (int k = 0; k < 2; ++k)
+        for (int i = 0; i < n_items; ++i) state_to_pose7(alternatives + ((size_t)i * 2 + k) * 13, &poses[((size_t)k * n_items + i) * 7]);
+    float* d_r = nullptr;
+    if (render_tiles(ctx, tb, 2 * n_items, poses.data(), divider, &d_r, s)) return fail(ctx, "roftb_pick_best_alternative: render failed");
+    SelectArgs a;
+    fill_select(ctx, a, tb, n_items, segmentation, depth, nullptr, s);
+    const size_t rsz = (size_t)(ctx->g.W / divider) * (ctx->g.H / divider);
+    double* d_e = tb.alloc<double>((size_t)2 * n_items, true);
+    int32_t* d_n = tb.alloc<int32_t>((size_t)2 * n_items, true);
+    int32_t* d_sel = tb.alloc<int32_t>(n_items);
+    double* d_l = tb.alloc<double>((size_t)2 * n_items);
+    if (!a.mask || !a.depth || !a.wt_count || !d_e || !d_n || !d_sel || !d_l) return fail(ctx, "roftb_pick_best_alternative: out of device memory");
+    for (int k = 0; k < 2; ++k)
+        if (launch_masked_depth_l1(a, d_r + (size_t)k * n_items * rsz, (long long)rsz, divider, d_e + (size_t)k * n_items,
+                                   d_n + (size_t)k * n_items, s))
+            return fail(ctx, "roftb_pick_best_alternative: L1 launch failed");
+    if (launch_pick_best(n_items, d_e, d_n, gain, d_sel, d_l, s)) return fail(ctx, "roftb_pick_best_alternative: launch failed");
+    CK(cudaMemcpyAsync(selected, d_sel, (size_t)n_items * 4, cudaMemcpyDeviceToHost, s));
+    if (likelihoods) CK(cudaMemcpyAsync(likelihoods, d_l, (size_t)2 * n_items * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return 0;
 }

@@ -233,6 +233,20 @@ struct UkfArgs {
 };
 int launch_ukf(const UkfArgs& a, cudaStream_t s);
 
+// depth rasteriser (render.cu): n_items poses of ONE mesh -> n_items tiles of w x h pixels
+struct RenderArgs {
+    int n_items;
+    const float* vertices; int n_vertices;   // device [n_vertices][3], model frame, metres
+    const int32_t* faces; int n_faces;       // device [n_faces][3]
+    const float* model;                      // device [n_items][12]: rotation row-major (9), translation (3)
+    float fx, fy, cx, cy;                    // intrinsics of the tile (camera intrinsics / divider)
+    int w, h;
+};
+size_t render_vertex_scratch_bytes(int n_items, int n_vertices);
+int launch_render_depth(const RenderArgs& a, void* vertex_scratch, uint32_t* zbuf, float* out, cudaStream_t s);
+int launch_pick_best(int n, const double* err, const int32_t* samples, double gain, int32_t* selected, double* likelihoods,
+                     cudaStream_t s);
+
 struct SelectArgs {        // ordered compaction helpers (export / points / L1)
     Geom g;
     int n_items;

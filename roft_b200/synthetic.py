@@ -36,6 +36,18 @@ class SyntheticSequence:
     flow_grid: int
     flow_scale: float
     dt: float
+    half: Optional[torch.Tensor] = None   # [T, 3] float64 half extents of each track's cuboid
+
+
+def cuboid_mesh(half):
+    """Triangle mesh (vertices [8,3] float32, faces [12,3] int32) of the axis-aligned cuboid with the given half extents -
+    the object every synthetic track shows, for the render-and-compare pose test (roftb_set_mesh)."""
+    import numpy as np
+    h = np.asarray(half, np.float64)
+    v = np.array([[sx * h[0], sy * h[1], sz * h[2]] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float32)
+    f = np.array([[0, 1, 3], [0, 3, 2], [4, 6, 7], [4, 7, 5], [0, 4, 5], [0, 5, 1], [2, 3, 7], [2, 7, 6], [0, 2, 6], [0, 6, 4],
+                  [1, 5, 7], [1, 7, 3]], np.int32)
+    return v, f
 
 
 def _quat_to_rot(q: torch.Tensor) -> torch.Tensor:
@@ -156,6 +168,7 @@ def make_sequence(n_tracks: int, n_frames: int, width: int = 1280, height: int =
     def rand(c0, c1, shape):
         return torch.stack([torch.rand(shape, generator=gens[t], device=dev, dtype=torch.float32) for t in range(c0, c1)])
 
+    half_used = half.clone()
     for c0 in range(0, T, track_chunk):
         c1 = min(T, c0 + track_chunk)
         hc = half[c0:c1].to(dev)
@@ -167,6 +180,7 @@ def make_sequence(n_tracks: int, n_frames: int, width: int = 1280, height: int =
                 hc = hc * torch.sqrt(target_coverage / cov).clamp(0.25, 4.0).unsqueeze(-1)
                 zmin = gt_pose[0, c0:c1, 2].to(dev) - 0.12
                 hc = torch.minimum(hc, zmin.clamp_min(0.05).unsqueeze(-1).expand_as(hc) * torch.tensor([4.0, 4.0, 1.0], device=dev, dtype=torch.float64))
+        half_used[c0:c1] = hc.to("cpu", torch.float64)
         prev = None
         for f in range(F):
             xf = gt_pose[f, c0:c1, :3].to(dev)
@@ -218,4 +232,4 @@ def make_sequence(n_tracks: int, n_frames: int, width: int = 1280, height: int =
             depth[f, c0:c1] = dn
             prev = (d, hit, xf, Rf)
     return SyntheticSequence(depth=depth, flow=flow, mask=mask, pose=pose, pose_valid=pose_valid,
-                             gt_pose=gt_pose, gt_twist=gt_twist, flow_grid=grid, flow_scale=scale, dt=dt)
+                             gt_pose=gt_pose, gt_twist=gt_twist, flow_grid=grid, flow_scale=scale, dt=dt, half=half_used)

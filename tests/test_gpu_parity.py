@@ -484,3 +484,76 @@ def test_worklist_diagnostics(api):
             pad = (-flat.size) % 128
             u = np.pad(flat, (0, pad)).reshape(-1, 128).any(axis=1).sum()
             assert units[t] == int(u), (k, t)
+
+
+# ---- f1: render-and-compare pose outlier rejection -------------------------------------------------------------------
+def _render_close(got, exp):
+    """Depth tiles agree: same silhouette up to a handful of edge pixels (the model matrix goes through the C library's
+    cosf / sinf on one side and numpy's on the other: positions can differ by one 1/256-px step), depth within 1e-4."""
+    both = (got > 0) & (exp > 0)
+    mism = int(((got > 0) != (exp > 0)).sum())
+    assert mism <= max(2, 0.002 * int((exp > 0).sum())), (mism, int((exp > 0).sum()))
+    assert both.sum() > 0 and np.abs(got[both] - exp[both]).max() <= 1e-4 * exp[both].max()
+
+
+@pytest.mark.gpu
+def test_depth_rasteriser_matches_oracle(lib_built):
+    """roftb_render_depth (SICAD::superimpose depth, SICAD.cpp:924-1066) against the numpy restatement: cuboid and a
+    2048-triangle sphere, poses incl. partially out of frame and behind the camera, dividers 1 / 2 / 4."""
+    from roft_b200 import api
+    from roft_b200.synthetic import cuboid_mesh
+    from test_oracle import _octasphere
+    cfg = small_cfg()
+    trk = api.Tracker(to_roftb_config(cfg, 1))
+    rng = np.random.default_rng(5)
+    for verts, faces in (cuboid_mesh([0.08, 0.105, 0.03]), _octasphere(0.07, 4)):
+        trk.set_mesh(verts, faces)
+        poses = []
+        for k in range(6):
+            ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+            poses.append(np.concatenate([[rng.uniform(-0.05, 0.05), rng.uniform(-0.03, 0.03), rng.uniform(0.4, 0.9)], ax, [rng.uniform(0, 3.1)]]))
+        poses.append(np.array([0.12, 0.05, 0.5, 0, 0, 1, 0.3]))      # partly outside the frame
+        poses.append(np.array([0.0, 0.0, -0.5, 1, 0, 0, 0.0]))       # behind the camera: nothing
+        poses.append(np.array([0.0, 0.0, 0.6, 0, 0, 0, 0.0]))        # zero axis (identity rotation)
+        poses = np.array(poses)
+        for div in (1, 2, 4):
+            got = trk.render_depth(poses, div)
+            assert got.shape == (len(poses), cfg.height // div, cfg.width // div)
+            for i, p in enumerate(poses):
+                exp = o.render_depth(verts, faces, p, cfg.width // div, cfg.height // div, cfg.fx / div, cfg.fy / div, cfg.cx / div, cfg.cy / div)
+                if not exp.any():
+                    assert not got[i].any()
+                else:
+                    _render_close(got[i], exp)
+
+
+@pytest.mark.gpu
+def test_pick_best_alternative_matches_oracle(lib_built):
+    """roftb_pick_best_alternative (ROFTFilter.cpp:467-621): same selection and likelihoods as the oracle for a
+    consistent / displaced pair in both orders, a near-tie, and an empty mask (DBL_MAX, first alternative kept)."""
+    from roft_b200 import api
+    from roft_b200.synthetic import cuboid_mesh
+    cfg = small_cfg()
+    T = 3
+    seq = sequence(cfg, T, 3, corrupt=False)
+    verts, faces = cuboid_mesh(seq.half[0].numpy())
+    trk = api.Tracker(to_roftb_config(cfg, T))
+    trk.set_mesh(verts, faces)
+    k = 2
+    masks = seq.mask[k].numpy().copy(); depths = seq.depth[k].numpy()
+    alts = np.zeros((T, 2, 13))
+    for t in range(T):
+        alts[t, :, 6:] = seq.gt_pose[k, t].numpy()
+    alts[0, 1, 8] += 0.12          # track 0: second alternative displaced -> first wins
+    alts[1, 0, 6] += 0.05          # track 1: first displaced -> second wins
+    alts[2, 1, 8] += 0.002         # track 2: near tie -> first stays
+    for div, gain in ((2, 0.01), (4, 1.0)):
+        sel, lik = trk.pick_best_alternative(masks, depths, alts, div, gain)
+        for t in range(T):
+            es, el = o.pick_best_alternative(cfg, verts, faces, [alts[t, 0], alts[t, 1]], masks[t], depths[t], div, gain)
+            assert sel[t] == es, (t, sel[t], es, lik[t], el)
+            assert np.allclose(lik[t], el, rtol=2e-3), (t, lik[t], el)
+        assert list(sel) == [0, 1, 0]
+    masks[0] = 0
+    sel, lik = trk.pick_best_alternative(masks, depths, alts, 2, 0.01)
+    assert sel[0] == 0 and lik[0, 0] == np.finfo(np.float64).max and lik[0, 1] == np.finfo(np.float64).max

@@ -310,3 +310,73 @@ def test_masked_points_and_l1_small():
         if dd > 0 and dd < 2.0 and r != 0:
             e2 += float(abs(np.float32(dd) - np.float32(r))); n2 += 1
     assert n == n2 and abs(err - e2) < 1e-9
+
+
+# ---- f1: render-and-compare pose outlier rejection -------------------------------------------------------------------
+def _octasphere(radius, level=3):
+    """Subdivided octahedron: a closed mesh with many small triangles."""
+    v = [np.array(p, np.float64) for p in ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1))]
+    f = [(0, 2, 4), (2, 1, 4), (1, 3, 4), (3, 0, 4), (2, 0, 5), (1, 2, 5), (3, 1, 5), (0, 3, 5)]
+    for _ in range(level):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            k = (min(a, b), max(a, b))
+            if k not in cache:
+                m = v[a] + v[b]
+                v.append(m / np.linalg.norm(m))
+                cache[k] = len(v) - 1
+            return cache[k]
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    return (np.array(v) * radius).astype(np.float32), np.array(f, np.int32)
+
+
+def test_oracle_rasteriser_against_closed_forms():
+    """SICAD depth restatement: a sphere renders the analytic ray/sphere depth at the pixel centres (u + 0.5, v + 0.5), the
+    silhouette is the analytic disc up to the faceting, and the quaternion -> axis-angle conversion is Eigen's."""
+    W, H, fx, fy, cx, cy = 160, 120, 200.0, 210.0, 80.0, 60.0
+    r, c = 0.08, np.array([0.03, -0.02, 0.6])
+    verts, faces = _octasphere(r, 4)
+    q = np.array([0.9, 0.1, -0.3, 0.2]); q /= np.linalg.norm(q)
+    aa = o.quaternion_to_axis_angle(q)
+    assert abs(np.linalg.norm(aa[:3]) - 1) < 1e-12 and abs(np.cos(aa[3] / 2) - q[0]) < 1e-12
+    assert np.allclose(o.quaternion_to_axis_angle(-q), aa, atol=1e-12)   # q and -q: same axis, same angle
+    assert np.array_equal(o.quaternion_to_axis_angle(np.array([1.0, 0, 0, 0])), [1.0, 0, 0, 0])
+    d = o.render_depth(verts, faces, np.concatenate([c, aa]), W, H, fx, fy, cx, cy)
+    uu, vv = np.meshgrid(np.arange(W) + 0.5, np.arange(H) + 0.5)
+    ray = np.stack([(uu - cx) / fx, (vv - cy) / fy, np.ones_like(uu)], -1)
+    a = (ray * ray).sum(-1); b = -2 * (ray @ c); cc = c @ c - r * r
+    disc = b * b - 4 * a * cc
+    z = np.where(disc > 0, (-b - np.sqrt(np.maximum(disc, 0))) / (2 * a), 0.0)
+    hit = d > 0
+    assert abs(int(hit.sum()) - int((disc > 0).sum())) < 0.03 * (disc > 0).sum()     # faceted silhouette
+    inner = hit & (disc > 0.5 * disc.max())
+    assert inner.sum() > 500 and np.abs(d[inner] - z[inner]).max() < 5e-4               # chord error of the facets
+    # a fronto-parallel square: exact coverage and constant depth
+    sq = np.array([[-0.1, -0.05, 0], [0.1, -0.05, 0], [0.1, 0.05, 0], [-0.1, 0.05, 0]], np.float32)
+    d2 = o.render_depth(sq, np.array([[0, 1, 2], [0, 2, 3]], np.int32), np.array([0, 0, 0.5, 1, 0, 0, 0.0]), W, H, fx, fy, cx, cy)
+    u0, u1 = cx - 0.1 * fx / 0.5, cx + 0.1 * fx / 0.5
+    v0, v1 = cy - 0.05 * fy / 0.5, cy + 0.05 * fy / 0.5
+    exp = ((uu >= u0) & (uu <= u1) & (vv >= v0) & (vv <= v1))
+    assert np.array_equal(d2 > 0, exp) and np.abs(d2[exp] - 0.5).max() < 5e-5
+    # a triangle behind the camera is dropped, not wrapped around
+    assert not o.render_depth(sq, np.array([[0, 1, 2]], np.int32), np.array([0, 0, -0.5, 1, 0, 0, 0.0]), W, H, fx, fy, cx, cy).any()
+
+
+def test_oracle_pick_best_alternative_prefers_the_consistent_pose():
+    from roft_b200.synthetic import cuboid_mesh
+    cfg = small_cfg()
+    seq = sequence(cfg, 1, 2, corrupt=False)
+    verts, faces = cuboid_mesh(seq.half[0].numpy())
+    good = np.zeros(13); good[6:] = seq.gt_pose[1, 0].numpy()
+    bad = good.copy(); bad[8] += 0.15
+    sel, lik = o.pick_best_alternative(cfg, verts, faces, [good, bad], seq.mask[1, 0].numpy(), seq.depth[1, 0].numpy(), 2, 0.01)
+    assert sel == 0 and lik[0] < 0.5 * lik[1]
+    sel, lik = o.pick_best_alternative(cfg, verts, faces, [bad, good], seq.mask[1, 0].numpy(), seq.depth[1, 0].numpy(), 2, 0.01)
+    assert sel == 1
+    # no samples (empty mask): DBL_MAX for both, the first alternative stays (ROFTFilter.cpp:569-583)
+    sel, lik = o.pick_best_alternative(cfg, verts, faces, [good, bad], np.zeros_like(seq.mask[1, 0].numpy()), seq.depth[1, 0].numpy(), 2, 0.01)
+    assert sel == 0 and lik[0] == np.finfo(np.float64).max
