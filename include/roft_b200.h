@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ROFTB_VERSION 2
+#define ROFTB_VERSION 3
 
 /* flow formats: the two cv::Mat types ROFT accepts (ImageOpticalFlowSource.h:44-45) */
 #define ROFTB_FLOW_F32 13 /* CV_32FC2: float2 per element, grid 1, scale 1            */
@@ -78,6 +78,14 @@ typedef struct roftb_config {
                                         1: FP64; 0: FP32 terms, FP64 reduction (agreement with the FP64 reference then
                                         scales as cond(Lambda)*6e-8/sqrt(N)); 2 (default): FP64 for tracks with fewer
                                         than 32768 candidate pixels, FP32 terms above */
+    /* Render-and-compare pose outlier rejection inside the filter loop (outlier_rejection.enable / gain, cfg:108-112;
+       ROFTFilter.cpp:346-359, 649-676).  Needs roftb_set_mesh before the first step.  The likelihood gain does not
+       influence the choice (likelihood[0] > 2 likelihood[1]); the reference moreover receives it through a `const bool`
+       constructor parameter (ROFTFilter.cpp:54), i.e. as 1.0 - pass what the caller's ROFTFilter would hold.
+       divider: 0 = the reference's rule (2 for 640-wide frames, else 4: ROFTFilter.cpp:191-193). */
+    int32_t outlier_rejection;
+    int32_t outlier_rejection_divider;
+    double outlier_rejection_gain;
 } roftb_config;
 
 /* One camera frame for all tracks = what the reference's sources deliver at one

@@ -97,6 +97,11 @@ class RoftConfig:
     # segmentation_dataset / pose_dataset (cfg:110-137): frames between iterations D
     segm_delay: int = 6
     pose_delay: int = 6
+    # outlier_rejection (cfg:108-112).  The gain reaches ROFTFilter through a `const bool` parameter (ROFTFilter.cpp:54), so the
+    # reference divides by 1.0; the choice does not depend on it.  divider: 0 = 2 for 640-wide frames else 4 (:191-193)
+    outlier_rejection: bool = False
+    outlier_rejection_gain: float = 1.0
+    outlier_rejection_divider: int = 0
 
 
 # --------------------------------------------------------------------------------------
@@ -864,12 +869,16 @@ class FrameInput:
 class RoftFilterOracle:
     """Single-track restatement of ROFTFilter (ROFTFilter.cpp:216-367) over the functions above.
 
-    The render-and-compare pose outlier rejection (ROFTFilter.cpp:467-621, GL) is out of scope
-    (SURVEY.md 8f); everything else in filtering_step is followed in order.
+    With cfg.outlier_rejection the render-and-compare pose test (ROFTFilter.cpp:467-621, 649-676) runs over the
+    restated rasteriser below (`mesh` = (vertices, faces) of the tracked object); everything in filtering_step is
+    followed in order.
     """
 
-    def __init__(self, cfg: RoftConfig, x0: Optional[np.ndarray] = None, sqrt_method: str = "jacobi"):
+    def __init__(self, cfg: RoftConfig, x0: Optional[np.ndarray] = None, sqrt_method: str = "jacobi", mesh=None):
         self.cfg = cfg
+        self.mesh = mesh
+        self.or_features = None          # (segmentation, depth) of buffer_outlier_rejection_features
+        self.or_selected: List[int] = []  # diagnostics: choices made so far
         self.sqrt_method = sqrt_method
         self.v_mean = np.zeros(6)
         self.v_cov = np.diag(cfg.v_cov0).astype(np.float64)
@@ -931,6 +940,10 @@ class RoftFilterOracle:
         # 7-9. pose UKF (ROFTFilter.cpp:305-367)
         velocity = self.v_mean.copy()  # velocity_->set_twist(...) then freeze(true) always succeeds
         T = dt
+        # ROFTFilter.cpp:313-321: the first step of a re-synchronising filter buffers the features of the test
+        current_features = (self.seg if self.seg is not None else np.zeros((cfg.height, cfg.width), np.uint8), fr.depth)
+        if cfg.outlier_rejection and cfg.use_pose_resync and self.or_features is None:
+            self.or_features = current_features
         pm, pc = ukf_predict(self.p_mean, self.p_cov, cfg, T, self.sqrt_method)
         pmodel = self.pose_model
         if pmodel.freeze(pmodel.STANDARD, velocity, fr.pose):
@@ -940,13 +953,32 @@ class RoftFilterOracle:
                 cm, cc = buffered_copy
                 while pmodel.freeze(pmodel.POP_BUFFERED):
                     pm, pc = ukf_predict(cm, cc, cfg, T, self.sqrt_method)
-                    cm, cc = ukf_correct(pm, pc, pmodel.measurement, pmodel.mtype, cfg, self.sqrt_method)
+                    if cfg.outlier_rejection and pmodel.mtype == MEAS_POSE_VELOCITY:
+                        cm, cc = self._correct_outlier_rejection(pm, pc, self.or_features)
+                    else:
+                        cm, cc = ukf_correct(pm, pc, pmodel.measurement, pmodel.mtype, cfg, self.sqrt_method)
                 self.p_mean, self.p_cov = cm, cc
+                if cfg.outlier_rejection:
+                    self.or_features = current_features  # :352-353
+            elif cfg.outlier_rejection and pmodel.mtype == MEAS_POSE_VELOCITY:
+                self.p_mean, self.p_cov = self._correct_outlier_rejection(pm, pc, current_features)  # :357-358
             else:
                 self.p_mean, self.p_cov = ukf_correct(pm, pc, pmodel.measurement, pmodel.mtype, cfg, self.sqrt_method)
         else:
             self.p_mean, self.p_cov = pm, pc
         return self.p_mean.copy(), self.v_mean.copy()
+
+    def _correct_outlier_rejection(self, pm, pc, features):
+        """ROFTFilter::correct_outlier_rejection, ROFTFilter.cpp:649-676."""
+        cfg, pmodel = self.cfg, self.pose_model
+        a_m, a_c = ukf_correct(pm, pc, pmodel.measurement, pmodel.mtype, cfg, self.sqrt_method)
+        pmodel.freeze(pmodel.REPEAT_ONLY_VELOCITY)
+        b_m, b_c = ukf_correct(pm, pc, pmodel.measurement, pmodel.mtype, cfg, self.sqrt_method)
+        seg, depth = features
+        divider = cfg.outlier_rejection_divider or (2 if cfg.width == 640 else 4)
+        sel, _ = pick_best_alternative(cfg, self.mesh[0], self.mesh[1], [a_m, b_m], seg, depth, divider, cfg.outlier_rejection_gain)
+        self.or_selected.append(sel)
+        return (b_m, b_c) if sel == 1 else (a_m, a_c)
 
 
 # ---- pose outlier rejection (SURVEY.md 8 row f1) ------------------------------------------------------------------

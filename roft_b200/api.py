@@ -46,6 +46,7 @@ class RoftbConfig(C.Structure):
         ("use_pose", C.c_int32), ("use_pose_resync", C.c_int32), ("use_velocity", C.c_int32), ("flow_aided", C.c_int32),
         ("segm_delay", C.c_int32), ("pose_delay", C.c_int32),
         ("device", C.c_int32), ("accum_fp64", C.c_int32),
+        ("outlier_rejection", C.c_int32), ("outlier_rejection_divider", C.c_int32), ("outlier_rejection_gain", C.c_double),
     ]
 
 

@@ -131,6 +131,84 @@ __global__ void k_pick_best(int n, const double* __restrict__ err, const int32_t
     selected[t] = l[0] > 2.0 * l[1] ? 1 : 0;
 }
 
+
+// In-loop variant of the host-side pose conversion (roftb_api.cu: state_to_pose7 + model_matrix): the two candidate means
+// of every track with a pending render-and-compare test -> model matrices laid out [alternative][track]; tracks without
+// one are placed behind the camera (nothing is rendered, no samples, first alternative kept).
+__global__ void k_or_models(int n_tracks, const int32_t* __restrict__ resume, const double* __restrict__ cand_mean,
+                            float* __restrict__ model) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n_tracks) return;
+    const int k = i / n_tracks, t = i - k * n_tracks;
+    float* out = model + (long long)i * 12;
+    if (resume[t] <= 0) {
+        for (int j = 0; j < 12; ++j) out[j] = 0.f;
+        out[0] = out[4] = out[8] = 1.f;
+        out[11] = -1.f;
+        return;
+    }
+    const double* m = cand_mean + ((long long)t * 2 + k) * 13;
+    // Eigen::AngleAxisd(Quaterniond) (ROFTFilter.cpp:518-524)
+    const double w = m[9], x = m[10], y = m[11], z = m[12];
+    double n = sqrt(x * x + y * y + z * z), angle = 0.0, axd[3] = {1.0, 0.0, 0.0};
+    if (n != 0.0) {
+        angle = 2.0 * atan2(n, fabs(w));
+        if (w < 0.0) n = -n;
+        axd[0] = x / n; axd[1] = y / n; axd[2] = z / n;
+    }
+    // glm::rotate(I, float(angle), float(axis)) (SICAD.cpp:604-607)
+    const float ang = (float)angle;
+    float ax = (float)axd[0], ay = (float)axd[1], az = (float)axd[2];
+    const float c = cosf(ang), s = sinf(ang);
+    const float nn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az)));
+    if (nn > 0.f) { ax = __fdiv_rn(ax, nn); ay = __fdiv_rn(ay, nn); az = __fdiv_rn(az, nn); }
+    const float omc = __fadd_rn(1.f, -c);
+    const float tx = __fmul_rn(omc, ax), ty = __fmul_rn(omc, ay), tz = __fmul_rn(omc, az);
+    out[0] = __fadd_rn(c, __fmul_rn(tx, ax));
+    out[1] = __fadd_rn(__fmul_rn(ty, ax), -__fmul_rn(s, az));
+    out[2] = __fadd_rn(__fmul_rn(tz, ax), __fmul_rn(s, ay));
+    out[3] = __fadd_rn(__fmul_rn(tx, ay), __fmul_rn(s, az));
+    out[4] = __fadd_rn(c, __fmul_rn(ty, ay));
+    out[5] = __fadd_rn(__fmul_rn(tz, ay), -__fmul_rn(s, ax));
+    out[6] = __fadd_rn(__fmul_rn(tx, az), -__fmul_rn(s, ay));
+    out[7] = __fadd_rn(__fmul_rn(ty, az), __fmul_rn(s, ax));
+    out[8] = __fadd_rn(c, __fmul_rn(tz, az));
+    out[9] = (float)m[6]; out[10] = (float)m[7]; out[11] = (float)m[8];
+}
+
+// correction = best_alternative (ROFTFilter.cpp:670-673): candidate 1 replaces the belief where it was selected
+__global__ void k_or_select(int n_tracks, const int32_t* __restrict__ resume, const int32_t* __restrict__ selected,
+                            const double* __restrict__ cand_mean, const double* __restrict__ cand_cov, double* __restrict__ mean,
+                            double* __restrict__ cov) {
+    const int t = blockIdx.x;
+    if (resume[t] <= 0 || selected[t] != 1) return;
+    for (int i = threadIdx.x; i < 13; i += blockDim.x) mean[(long long)t * 13 + i] = cand_mean[(long long)t * 26 + 13 + i];
+    for (int i = threadIdx.x; i < 144; i += blockDim.x) cov[(long long)t * 144 + i] = cand_cov[(long long)t * 288 + 144 + i];
+}
+
+
+// Buffered features of the render-and-compare test (ROFTFilter::buffer_outlier_rejection_features, ROFTFilter.cpp:624-646):
+// the mask state and the depth of the tracks whose first op carries `bits` in UkfOp::pad are copied plane by plane.
+// Two hops: k_or_copy(stage <- live planes) as soon as the step's mask state is final, k_or_copy(snapshot <- stage) on the
+// pose stream before (bit 2) or after (bit 1) the step's test, which may still be reading the previous snapshot.
+__global__ void __launch_bounds__(kThreads) k_or_copy(const UkfOp* __restrict__ ops, int max_ops, int bits,
+                                                      const uint8_t* __restrict__ mask_src, const float* __restrict__ depth_src,
+                                                      long long depth_stride, uint8_t* __restrict__ mask_dst,
+                                                      float* __restrict__ depth_dst, int HW) {
+    const int t = blockIdx.y;
+    if ((ops[(long long)t * max_ops].pad & bits) == 0) return;
+    const uint4* ms = reinterpret_cast<const uint4*>(mask_src + (long long)t * HW);
+    uint4* md = reinterpret_cast<uint4*>(mask_dst + (long long)t * HW);
+    const uint4* ds = reinterpret_cast<const uint4*>(depth_src + (long long)t * depth_stride);
+    uint4* dd = reinterpret_cast<uint4*>(depth_dst + (long long)t * HW);
+    const int n16 = HW >> 4, n4 = HW >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        if (i < n16) md[i] = ms[i];
+        dd[i] = ds[i];
+    }
+    // (frame sizes are multiples of 16 pixels per track plane: check_geom)
+}
+
 }  // namespace
 
 int launch_render_depth(const RenderArgs& a, void* vertex_scratch, uint32_t* zbuf, float* out, cudaStream_t s) {
@@ -153,6 +231,25 @@ size_t render_vertex_scratch_bytes(int n_items, int n_vertices) { return (size_t
 int launch_pick_best(int n, const double* err, const int32_t* samples, double gain, int32_t* selected, double* likelihoods,
                      cudaStream_t s) {
     ROFTB_LAUNCH(k_pick_best, (n + 127) / 128, 128, 0, s, n, err, samples, gain, selected, likelihoods);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_or_models(int n_tracks, const int32_t* resume, const double* cand_mean, float* model, cudaStream_t s) {
+    ROFTB_LAUNCH(k_or_models, (2 * n_tracks + 127) / 128, 128, 0, s, n_tracks, resume, cand_mean, model);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_or_select(int n_tracks, const int32_t* resume, const int32_t* selected, const double* cand_mean, const double* cand_cov,
+                     double* mean, double* cov, cudaStream_t s) {
+    ROFTB_LAUNCH(k_or_select, n_tracks, 64, 0, s, n_tracks, resume, selected, cand_mean, cand_cov, mean, cov);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_or_copy(int n_tracks, const UkfOp* ops, int max_ops, int bits, const uint8_t* mask_src, const float* depth_src,
+                   long long depth_stride, uint8_t* mask_dst, float* depth_dst, int HW, cudaStream_t s) {
+    const int bx = max(1, min((HW / 4 + kThreads - 1) / kThreads, max(1, 148 * 8 / n_tracks)));
+    ROFTB_LAUNCH(k_or_copy, dim3(bx, n_tracks), kThreads, 0, s, ops, max_ops, bits, mask_src, depth_src, depth_stride, mask_dst,
+                 depth_dst, HW);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -41,6 +41,7 @@ struct TrackHost {
     bool segmeas_available = false;   // ImageSegmentationMeasurement::segmentation_available_
     bool fm_first_frame = true;       // ImageOpticalFlowMeasurement::is_first_frame_
     int prev_slot = -1;               // frame slot of previous_depth_
+    bool or_features_initialized = false;  // ROFTFilter::outlier_rejection_features_initialized_
     PoseMeasHost pm;
 };
 
@@ -56,6 +57,29 @@ struct roftb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr, ukf_stream = nullptr, mask_stream = nullptr, prep_stream = nullptr,
                  aux_stream = nullptr;
     cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+    // render-and-compare pose outlier rejection inside the filter loop (cfg.outlier_rejection)
+    struct OutlierRejection {
+        int divider = 4;
+        int32_t* resume = nullptr;          // [T] op index the UKF continues from after the test (-1: nothing pending)
+        double* cand_mean = nullptr;        // [T][2][13]
+        double* cand_cov = nullptr;         // [T][2][144]
+        float* model = nullptr;             // [2][T][12]
+        void* vertex_scratch = nullptr;     // (allocated with the mesh)
+        uint32_t* zbuf = nullptr;           // [2][T][h][w]
+        float* rendered = nullptr;          // [2][T][h][w]
+        double* err = nullptr; int32_t* samples = nullptr;   // [2][T]
+        int32_t* selected = nullptr;        // [T]
+        int32_t* wt_count = nullptr;        // [T][n_units] rank scratch of the masked L1
+        // features buffered at the previous re-synchronisation (ROFTFilter.cpp:624-646): raw mask state + depth per track.
+        // A refresh goes through a staging copy: stage <- live planes as soon as the step's mask state is final (own
+        // stream; the planes are recycled two steps later), snapshot <- stage on the pose stream, before or after the
+        // step's test, which may still be reading the previous snapshot
+        uint8_t* snap_mask = nullptr; float* snap_depth = nullptr;
+        uint8_t* stage_mask = nullptr; float* stage_depth = nullptr;
+        cudaEvent_t stage_done[3] = {nullptr, nullptr, nullptr}, unstage_done = nullptr, ops_ready = nullptr;
+        bool stage_done_used[3] = {false, false, false}, unstage_done_used = false;
+        cudaStream_t stream = nullptr;      // snapshot copies
+    } orj;
     float* mesh_vertices = nullptr;                  // outlier-rejection mesh (roftb_set_mesh): device [n][3]
     int32_t* mesh_faces = nullptr;
     int mesh_nv = 0, mesh_nf = 0;
@@ -219,6 +243,9 @@ void roftb_config_default(roftb_config* c) {
     c->segm_delay = 6; c->pose_delay = 6;
     c->device = 0;
     c->accum_fp64 = 2;
+    c->outlier_rejection = 0;          // (cfg:110 enables it; here it needs roftb_set_mesh first)
+    c->outlier_rejection_divider = 0;
+    c->outlier_rejection_gain = 1.0;   // 0.01 in the cfg, `true` in ROFTFilter (see roft_b200.h)
 }
 
 const char* roftb_last_error(const roftb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -375,6 +402,34 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(dalloc(&ctx->pb_mean, (size_t)T * 13));
     CKC(dalloc(&ctx->pb_cov, (size_t)T * 144));
     CKC(dalloc(&ctx->vel_hist, (size_t)T * kHistRing * 6));
+    if (cfg->outlier_rejection) {
+        auto& oj = ctx->orj;
+        oj.divider = cfg->outlier_rejection_divider > 0 ? cfg->outlier_rejection_divider : (cfg->width == 640 ? 2 : 4);
+        if (cfg->width % oj.divider || cfg->height % oj.divider) {
+            g_create_error = "outlier_rejection_divider must divide the frame size";
+            roftb_destroy(ctx);
+            return -1;
+        }
+        const size_t tile = (size_t)(cfg->width / oj.divider) * (cfg->height / oj.divider);
+        CKC(dalloc(&oj.resume, (size_t)T));
+        CKC(dalloc(&oj.cand_mean, (size_t)T * 26));
+        CKC(dalloc(&oj.cand_cov, (size_t)T * 288));
+        CKC(dalloc(&oj.model, (size_t)T * 24));
+        CKC(dalloc(&oj.zbuf, (size_t)2 * T * tile));
+        CKC(dalloc(&oj.rendered, (size_t)2 * T * tile));
+        CKC(dalloc(&oj.err, (size_t)2 * T));
+        CKC(dalloc(&oj.samples, (size_t)2 * T));
+        CKC(dalloc(&oj.selected, (size_t)T));
+        CKC(dalloc(&oj.wt_count, (size_t)T * ctx->n_units));
+        CKC(dalloc(&oj.snap_mask, (size_t)T * ctx->HW));
+        CKC(dalloc(&oj.snap_depth, (size_t)T * ctx->HW));
+        CKC(dalloc(&oj.stage_mask, (size_t)T * ctx->HW));
+        CKC(dalloc(&oj.stage_depth, (size_t)T * ctx->HW));
+        for (int i = 0; i < 3; ++i) CKC(cudaEventCreateWithFlags(&oj.stage_done[i], cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&oj.unstage_done, cudaEventDisableTiming));
+        CKC(cudaEventCreateWithFlags(&oj.ops_ready, cudaEventDisableTiming));
+        CKC(cudaStreamCreateWithFlags(&oj.stream, cudaStreamNonBlocking));
+    }
     CKC(dalloc(&ctx->q_diag, (size_t)6));
     CKC(dalloc(&ctx->d_count, (size_t)T));
     CKC(dalloc(&ctx->d_lambda, (size_t)T * 36));
@@ -420,6 +475,18 @@ void roftb_destroy(roftb_ctx* ctx) {
         if (ctx->vel_join[i]) cudaEventDestroy(ctx->vel_join[i]);
     }
     if (ctx->vel_fork) cudaEventDestroy(ctx->vel_fork);
+    {
+        auto& oj = ctx->orj;
+        if (oj.stream) { cudaStreamSynchronize(oj.stream); cudaStreamDestroy(oj.stream); }
+        void* op[] = {oj.resume, oj.cand_mean, oj.cand_cov, oj.model, oj.vertex_scratch, oj.zbuf, oj.rendered, oj.err, oj.samples,
+                      oj.selected, oj.wt_count, oj.snap_mask, oj.snap_depth, oj.stage_mask, oj.stage_depth};
+        for (void* p : op)
+            if (p) cudaFree(p);
+        for (int i = 0; i < 3; ++i)
+            if (oj.stage_done[i]) cudaEventDestroy(oj.stage_done[i]);
+        if (oj.unstage_done) cudaEventDestroy(oj.unstage_done);
+        if (oj.ops_ready) cudaEventDestroy(oj.ops_ready);
+    }
     void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->mask_state[2], ctx->mask_occ[0], ctx->mask_occ[1], ctx->mask_occ[2],
                      ctx->winner, ctx->scratch.nu, ctx->scratch.dp, ctx->scratch.r, ctx->scratch.hist, ctx->scratch.chunk_cnt,
                      ctx->scratch.part, ctx->scratch.track_sel, ctx->scratch.sel_part, ctx->scratch.slot_bitmap, ctx->scratch.track_slot, ctx->scratch.chunk_aux,
@@ -639,6 +706,9 @@ int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mea
     CK(cudaStreamSynchronize(ctx->ukf_stream));
     ctx->mask_event_used = false;
     ctx->vel_done_event_used = false;
+    if (ctx->orj.stream) CK(cudaStreamSynchronize(ctx->orj.stream));
+    for (int i = 0; i < 3; ++i) ctx->orj.stage_done_used[i] = false;
+    ctx->orj.unstage_done_used = false;
     // ROFTFilter::initialization_step (ROFTFilter.cpp:216-237)
     std::vector<double> pm((size_t)T * 13, 0.0), pc((size_t)T * 144, 0.0), vm((size_t)T * 6, 0.0), vc((size_t)T * 36, 0.0);
     for (int t = 0; t < T; ++t) {
@@ -782,7 +852,8 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
     VelCtl* vc = ctx->h_vctl + (size_t)cslot * T;
     UkfOp* ops = ctx->h_ops + (size_t)cslot * T * kMaxUkfOps;
     int32_t* nops = ctx->h_nops + (size_t)cslot * T;
-    bool any_new_mask = false, any_vel = false;
+    bool any_new_mask = false, any_vel = false, any_or = false, any_stage_before = false, any_stage_after = false;
+    if (cfg.outlier_rejection && !ctx->mesh_nv) return fail(ctx, "outlier_rejection is enabled but no mesh was set (roftb_set_mesh)");
     for (int t = 0; t < T; ++t) {
         TrackHost& h = ctx->th[t];
         const bool flow_in = d_flow && (!f->flow_valid || f->flow_valid[t]);
@@ -841,6 +912,11 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
             o[n].meas_type = mtype;
             o[n].vel_slot = vel_slot;
             for (int i = 0; i < 7; ++i) o[n].meas[6 + i] = pm.last_pose[i];
+            // a 13-sized measurement goes through correct_outlier_rejection (ROFTFilter.cpp:346-347, 357-358)
+            if (cfg.outlier_rejection && mtype == ROFTB_MEAS_POSE_VELOCITY) {
+                o[n].kind = kOpCorrectBoth;
+                any_or = true;
+            }
             ++n;
         };
         // Standard freeze (.cpp:176-347)
@@ -904,6 +980,27 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
             add_correct(pm.mtype, pm.mtype == ROFTB_MEAS_POSE ? -1 : pm.last_vel_slot);
         }
         nops[t] = n;
+        // buffered features of the render-and-compare test -> UkfOp::pad of the track's first op: bit 2 = refresh before
+        // this step's test (ROFTFilter.cpp:313-321: first step; :357-358: no re-sync, the test uses the current features),
+        // bit 1 = refresh after it (:352-353: end of a re-synchronisation)
+        if (cfg.outlier_rejection) {
+            int bits = 0;
+            const bool resync_now = o[0].kind == kOpSwapBuffered;
+            bool tests = false;
+            for (int i = 0; i < n; ++i) tests |= o[i].kind == kOpCorrectBoth;
+            if (cfg.use_pose_resync) {
+                if (!h.or_features_initialized) {
+                    bits |= 2;
+                    h.or_features_initialized = true;
+                }
+                if (resync_now) bits |= 1;
+            } else if (tests) {
+                bits |= 2;
+            }
+            o[0].pad = bits;
+            any_stage_before |= (bits & 2) != 0;
+            any_stage_after |= (bits & 1) != 0;
+        }
     }
 
     cudaStream_t s = ctx->stream;
@@ -915,6 +1012,15 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
     int32_t* d_nops = ctx->d_nops + (size_t)cslot * T;
     CK(cudaMemcpyAsync(d_ops, ops, sizeof(UkfOp) * T * kMaxUkfOps, cudaMemcpyHostToDevice, ctx->ukf_stream));
     CK(cudaMemcpyAsync(d_nops, nops, sizeof(int32_t) * T, cudaMemcpyHostToDevice, ctx->ukf_stream));
+    if (cfg.outlier_rejection) {
+        CK(cudaEventRecord(ctx->orj.ops_ready, ctx->ukf_stream));
+        // a mask plane staged two steps ago is recycled by this step: the staging copy must be through
+        const int old = (int)((ctx->frame_idx + 1) % 3);  // == (frame_idx - 2) mod 3
+        if (ctx->frame_idx >= 2 && ctx->orj.stage_done_used[old]) {
+            for (cudaStream_t st : {s, ctx->prep_stream, ctx->mask_stream}) CK(cudaStreamWaitEvent(st, ctx->orj.stage_done[old], 0));
+            ctx->orj.stage_done_used[old] = false;
+        }
+    }
     CK(cudaEventRecord(ctx->ctl_event[cslot], s));
     // the pose UKF trails on its own stream; keep it within kUkfLag steps of the streaming kernels (velocity-history
     // ring): a pose re-sync replays pose_delay + 1 predict/correct pairs in one step, which the slack spreads out
@@ -1028,6 +1134,22 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
             CK(cudaEventRecord(ctx->mask_event, ms));
         }
     }
+    const bool any_stage = any_stage_before || any_stage_after;
+    if (any_stage) {
+        // stage <- (mask state after this step, depth of this step) of the flagged tracks, once both writers of the state
+        // (velocity kernel, new-mask scatter) are done; the previous staging must have been consumed
+        auto& oj = ctx->orj;
+        cudaStream_t cs = oj.stream;
+        CK(cudaStreamWaitEvent(cs, oj.ops_ready, 0));
+        CK(cudaStreamWaitEvent(cs, ctx->vel_done_event, 0));
+        CK(cudaStreamWaitEvent(cs, ctx->mask_event, 0));
+        if (oj.unstage_done_used) CK(cudaStreamWaitEvent(cs, oj.unstage_done, 0));
+        if (launch_or_copy(T, d_ops, kMaxUkfOps, 3, seg_next, d_depth, depth_stride, oj.stage_mask, oj.stage_depth, (int)ctx->HW, cs))
+            return fail(ctx, "launch_or_copy failed");
+        const int cur = (int)(ctx->frame_idx % 3);
+        CK(cudaEventRecord(oj.stage_done[cur], cs));
+        oj.stage_done_used[cur] = true;
+    }
     {
         cudaStream_t us = ctx->ukf_stream;
         CK(cudaStreamWaitEvent(us, ctx->vel_event[cslot], 0));
@@ -1038,8 +1160,60 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
         a.mean = ctx->p_mean; a.cov = ctx->p_cov; a.buf_mean = ctx->pb_mean; a.buf_cov = ctx->pb_cov;
         a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
         a.span_clock = span ? span + 8 : nullptr;
+        auto& oj = ctx->orj;
+        if (cfg.outlier_rejection) {
+            a.resume = oj.resume; a.cand_mean = oj.cand_mean; a.cand_cov = oj.cand_cov;
+            CK(cudaMemsetAsync(oj.resume, 0, sizeof(int32_t) * T, us));
+        }
         if (pe) CK(cudaEventRecord(pe[8], us));
-        if (launch_ukf(a, us)) return fail(ctx, "launch_ukf failed");
+        if (launch_ukf(a, us)) return fail(ctx, "launch_ukf failed");  // everything, or up to the first render-and-compare test
+        const int stage_slot = (int)(ctx->frame_idx % 3);
+        if (any_stage_before) {
+            CK(cudaStreamWaitEvent(us, oj.stage_done[stage_slot], 0));
+            if (launch_or_copy(T, d_ops, kMaxUkfOps, 2, oj.stage_mask, oj.stage_depth, (long long)ctx->HW, oj.snap_mask, oj.snap_depth,
+                               (int)ctx->HW, us))
+                return fail(ctx, "launch_or_copy failed");
+        }
+        if (any_or) {
+            // ROFTFilter::pick_best_alternative (ROFTFilter.cpp:467-621) on the buffered features, all on this stream
+            const int dv = oj.divider;
+            const size_t tile = (size_t)(ctx->g.W / dv) * (ctx->g.H / dv);
+            if (launch_or_models(T, oj.resume, oj.cand_mean, oj.model, us)) return fail(ctx, "launch_or_models failed");
+            RenderArgs ra;
+            ra.n_items = 2 * T;
+            ra.vertices = ctx->mesh_vertices; ra.n_vertices = ctx->mesh_nv;
+            ra.faces = ctx->mesh_faces; ra.n_faces = ctx->mesh_nf;
+            ra.model = oj.model;
+            ra.fx = (float)(cfg.fx / dv); ra.fy = (float)(cfg.fy / dv); ra.cx = (float)(cfg.cx / dv); ra.cy = (float)(cfg.cy / dv);
+            ra.w = ctx->g.W / dv; ra.h = ctx->g.H / dv;
+            if (launch_render_depth(ra, oj.vertex_scratch, oj.zbuf, oj.rendered, us)) return fail(ctx, "launch_render_depth failed");
+            CK(cudaMemsetAsync(oj.err, 0, sizeof(double) * 2 * T, us));
+            CK(cudaMemsetAsync(oj.samples, 0, sizeof(int32_t) * 2 * T, us));
+            SelectArgs sa;
+            memset(&sa, 0, sizeof(sa));
+            sa.g = ctx->g; sa.n_items = T;
+            sa.mask = oj.snap_mask; sa.mask_stride = (long long)ctx->HW; sa.thr = 1;  // the state holds raw values: threshold(> 1) on load
+            sa.depth = oj.snap_depth; sa.depth_stride = (long long)ctx->HW;
+            sa.wt_count = oj.wt_count;
+            for (int k = 0; k < 2; ++k)
+                if (launch_masked_depth_l1(sa, oj.rendered + (size_t)k * T * tile, (long long)tile, dv, oj.err + (size_t)k * T,
+                                           oj.samples + (size_t)k * T, us))
+                    return fail(ctx, "launch_masked_depth_l1 failed");
+            if (launch_pick_best(T, oj.err, oj.samples, cfg.outlier_rejection_gain, oj.selected, nullptr, us)) return fail(ctx, "launch_pick_best failed");
+            if (launch_or_select(T, oj.resume, oj.selected, oj.cand_mean, oj.cand_cov, ctx->p_mean, ctx->p_cov, us))
+                return fail(ctx, "launch_or_select failed");
+            if (launch_ukf(a, us)) return fail(ctx, "launch_ukf failed");  // the rest of the op lists
+        }
+        if (any_stage_after) {
+            CK(cudaStreamWaitEvent(us, oj.stage_done[stage_slot], 0));
+            if (launch_or_copy(T, d_ops, kMaxUkfOps, 1, oj.stage_mask, oj.stage_depth, (long long)ctx->HW, oj.snap_mask, oj.snap_depth,
+                               (int)ctx->HW, us))
+                return fail(ctx, "launch_or_copy failed");
+        }
+        if (any_stage) {
+            CK(cudaEventRecord(oj.unstage_done, us));
+            oj.unstage_done_used = true;
+        }
         if (pe) {
             CK(cudaEventRecord(pe[9], us));
             ctx->prof_used[cslot] = true;
@@ -1477,6 +1651,12 @@ int roftb_set_mesh(roftb_ctx* ctx, const float* vertices, int32_t n_vertices, co
     CK(cudaMemcpy(ctx->mesh_vertices, vertices, (size_t)n_vertices * 3 * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->mesh_faces, faces, (size_t)n_faces * 3 * sizeof(int32_t), cudaMemcpyHostToDevice));
     ctx->mesh_nv = n_vertices; ctx->mesh_nf = n_faces;
+    if (ctx->cfg.outlier_rejection) {
+        CK(cudaStreamSynchronize(ctx->ukf_stream));
+        if (ctx->orj.vertex_scratch) cudaFree(ctx->orj.vertex_scratch);
+        ctx->orj.vertex_scratch = nullptr;
+        CK(cudaMalloc(&ctx->orj.vertex_scratch, render_vertex_scratch_bytes(2 * ctx->T, n_vertices)));
+    }
     return 0;
 }
 

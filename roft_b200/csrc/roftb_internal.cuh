@@ -122,7 +122,10 @@ struct VelScratch {
 };
 
 // ---- pose UKF -----------------------------------------------------------------------------
-enum UkfOpKind : int32_t { kOpPredict = 1, kOpCorrect = 2, kOpSwapBuffered = 3 };
+// kOpCorrectBoth: ROFTFilter::correct_outlier_rejection (ROFTFilter.cpp:649-676) up to the choice: the standard correction
+// and the velocity-only one (MeasurementMode::RepeatOnlyVelocity) of the same prediction are both computed and parked in
+// UkfArgs::cand_*; the launch ends there for the track (UkfArgs::resume) and continues after the render-and-compare test.
+enum UkfOpKind : int32_t { kOpPredict = 1, kOpCorrect = 2, kOpSwapBuffered = 3, kOpCorrectBoth = 4 };
 
 struct UkfOp {
     int32_t kind;
@@ -230,6 +233,8 @@ struct UkfArgs {
     double* buf_mean; double* buf_cov;                      // buffered belief (may be null)
     const double* vel_hist; int hist_ring;                  // [T][ring][6] (may be null)
     unsigned long long* span_clock;                         // diagnostics (may be null): [first start, last end]
+    // outlier rejection (all null when off): per-track op index to start from (-1: nothing left), candidates [T][2][13|144]
+    int32_t* resume; double* cand_mean; double* cand_cov;
 };
 int launch_ukf(const UkfArgs& a, cudaStream_t s);
 
@@ -246,6 +251,11 @@ size_t render_vertex_scratch_bytes(int n_items, int n_vertices);
 int launch_render_depth(const RenderArgs& a, void* vertex_scratch, uint32_t* zbuf, float* out, cudaStream_t s);
 int launch_pick_best(int n, const double* err, const int32_t* samples, double gain, int32_t* selected, double* likelihoods,
                      cudaStream_t s);
+int launch_or_copy(int n_tracks, const UkfOp* ops, int max_ops, int bits, const uint8_t* mask_src, const float* depth_src,
+                   long long depth_stride, uint8_t* mask_dst, float* depth_dst, int HW, cudaStream_t s);
+int launch_or_models(int n_tracks, const int32_t* resume, const double* cand_mean, float* model, cudaStream_t s);
+int launch_or_select(int n_tracks, const int32_t* resume, const int32_t* selected, const double* cand_mean, const double* cand_cov,
+                     double* mean, double* cov, cudaStream_t s);
 
 struct SelectArgs {        // ordered compaction helpers (export / points / L1)
     Geom g;

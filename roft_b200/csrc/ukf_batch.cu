@@ -487,10 +487,16 @@ __global__ void __maxnreg__(REGS) k_ukf_batch(UkfArgs a) {
     double* meas = wsm.meas;
     double* gm = a.mean + (long long)t * 13;
     double* gc = a.cov + (long long)t * 144;
+    const int o_first = a.resume ? a.resume[t] : 0;
+    if (o_first < 0 || o_first >= nops) {  // (second launch of a step: this track had no render-and-compare test)
+        if (a.resume && lane == 0) a.resume[t] = -1;
+        return;
+    }
     if (lane < 13) s.mean[lane] = gm[lane];
     for (int i = lane; i < 144; i += 32) s.P[i / 12][i % 12] = gc[i];
     __syncwarp();
-    for (int o = 0; o < nops; ++o) {
+    int o_next = -1;
+    for (int o = o_first; o < nops; ++o) {
         const UkfOp* op = a.ops + (long long)t * a.max_ops + o;
         const int kind = op->kind;
         if (kind == kOpPredict) {
@@ -504,6 +510,41 @@ __global__ void __maxnreg__(REGS) k_ukf_batch(UkfArgs a) {
             }
             __syncwarp();
             ukf_correct_warp(s, a.p, op->meas_type, meas, lane);
+        } else if (kind == kOpCorrectBoth && a.cand_mean) {
+            if (lane < 13) {
+                double v = op->meas[lane];
+                if (lane < 6 && op->vel_slot >= 0 && a.vel_hist)
+                    v = a.vel_hist[((long long)t * a.hist_ring + op->vel_slot) * 6 + lane];
+                meas[lane] = v;
+            }
+            __syncwarp();
+            // park the prediction in candidate slot 1, correct with (velocity, pose) -> candidate 0, then restore the
+            // prediction and correct with the velocity only (CartesianQuaternionMeasurement.cpp:154-174) -> candidate 1
+            double* cm = a.cand_mean + (long long)t * 26;
+            double* cc = a.cand_cov + (long long)t * 288;
+            if (lane < 13) cm[13 + lane] = s.mean[lane];
+            for (int i = lane; i < 144; i += 32) cc[144 + i] = s.P[i / 12][i % 12];
+            __syncwarp();
+            ukf_correct_warp(s, a.p, ROFTB_MEAS_POSE_VELOCITY, meas, lane);
+            if (lane < 13) {
+                cm[lane] = s.mean[lane];
+                s.mean[lane] = cm[13 + lane];
+            }
+            for (int i = lane; i < 144; i += 32) {
+                cc[i] = s.P[i / 12][i % 12];
+                s.P[i / 12][i % 12] = cc[144 + i];
+            }
+            __syncwarp();
+            ukf_correct_warp(s, a.p, ROFTB_MEAS_VELOCITY, meas, lane);
+            if (lane < 13) cm[13 + lane] = s.mean[lane];
+            for (int i = lane; i < 144; i += 32) cc[144 + i] = s.P[i / 12][i % 12];
+            __syncwarp();
+            // the belief continues from candidate 0 unless k_or_select overwrites it (ROFTFilter.cpp:670-673)
+            if (lane < 13) s.mean[lane] = cm[lane];
+            for (int i = lane; i < 144; i += 32) s.P[i / 12][i % 12] = cc[i];
+            __syncwarp();
+            o_next = o + 1;
+            break;
         } else if (kind == kOpSwapBuffered && a.buf_mean) {
             // ROFTFilter.cpp:334-340: buffered_belief_ <-> p_corr_belief_
             double* bm = a.buf_mean + (long long)t * 13;
@@ -523,6 +564,7 @@ __global__ void __maxnreg__(REGS) k_ukf_batch(UkfArgs a) {
     }
     if (lane < 13) gm[lane] = s.mean[lane];
     for (int i = lane; i < 144; i += 32) gc[i] = s.P[i / 12][i % 12];
+    if (a.resume && lane == 0) a.resume[t] = o_next;
     span_stamp(a.span_clock, true);
 }
 

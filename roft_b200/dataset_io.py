@@ -91,3 +91,12 @@ def write_sequence(root: str, seq, track: int, object_name: str = "003_cracker_b
                 fp.write("0 0 0 0 0 0 0\n")
     with open(os.path.join(root, "cam_K.json"), "w") as f:
         json.dump({"name": "synthetic", "width": W, "height": H, "fx": fx, "fy": fy, "cx": cx, "cy": cy}, f, indent=1)
+
+
+def write_obj(path: str, vertices, faces) -> None:
+    """Wavefront OBJ (v / f records, 1-based indices): the mesh input of the render-and-compare pose test."""
+    with open(path, "w") as f:
+        for v in np.asarray(vertices, np.float64):
+            f.write(f"v {float(v[0])!r} {float(v[1])!r} {float(v[2])!r}\n")
+        for t in np.asarray(faces, np.int64):
+            f.write(f"f {t[0] + 1} {t[1] + 1} {t[2] + 1}\n")

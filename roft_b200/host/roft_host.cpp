@@ -247,6 +247,37 @@ bool DatasetTransformDelayed::freeze(bool) {
     return true;
 }
 
+// ---- mesh input of the depth renderer -----------------------------------------------------------------------
+void read_obj_mesh(const std::string& path, std::vector<float>& vertices, std::vector<std::int32_t>& faces) {
+    std::ifstream in(path);
+    if (!in.is_open()) throw std::runtime_error("read_obj_mesh. Error: cannot open " + path);
+    vertices.clear();
+    faces.clear();
+    std::string line;
+    while (std::getline(in, line)) {
+        std::istringstream ls(line);
+        std::string tag;
+        if (!(ls >> tag)) continue;
+        if (tag == "v") {
+            float x, y, z;
+            if (!(ls >> x >> y >> z)) throw std::runtime_error("read_obj_mesh. Error: malformed vertex in " + path);
+            vertices.push_back(x); vertices.push_back(y); vertices.push_back(z);
+        } else if (tag == "f") {
+            std::vector<std::int32_t> idx;
+            std::string tok;
+            while (ls >> tok) {
+                const long v = std::strtol(tok.c_str(), nullptr, 10);  // "v", "v/vt", "v//vn", "v/vt/vn"
+                const long nv = long(vertices.size() / 3);
+                const long k = v > 0 ? v - 1 : nv + v;
+                if (v == 0 || k < 0 || k >= nv) throw std::runtime_error("read_obj_mesh. Error: face index out of range in " + path);
+                idx.push_back(std::int32_t(k));
+            }
+            for (std::size_t i = 2; i < idx.size(); ++i) { faces.push_back(idx[0]); faces.push_back(idx[i - 1]); faces.push_back(idx[i]); }
+        }
+    }
+    if (vertices.empty() || faces.empty()) throw std::runtime_error("read_obj_mesh. Error: no triangles in " + path);
+}
+
 // ---- ROFTFilter ---------------------------------------------------------------------------------------------
 ROFTFilter::ROFTFilter(std::vector<TrackSources> tracks, const std::vector<double>& initial_covariance_p,
                        const std::vector<double>& model_covariance_p, const std::vector<double>& measurement_covariance_p,
@@ -254,7 +285,8 @@ ROFTFilter::ROFTFilter(std::vector<TrackSources> tracks, const std::vector<doubl
                        const std::vector<double>& measurement_covariance_v, double ut_alpha, double ut_beta, double ut_kappa,
                        double sample_time, bool pose_meas, bool pose_resync, bool velocity_meas, bool flow_weighting,
                        bool flow_aided_segmentation, double maximum_depth, double subsampling_radius, bool enable_log,
-                       const std::string& log_path, const std::string& log_prefix, int device)
+                       const std::string& log_path, const std::string& log_prefix, int device, bool pose_outlier_rejection,
+                       bool pose_outlier_rejection_gain, const std::string& model_mesh_path)
     : tracks_(std::move(tracks)), sample_time_(sample_time), enable_log_(enable_log) {
     const std::string log_name = "ROFTFilter";
     if (tracks_.empty()) throw std::runtime_error(log_name + "::ctor. Error: no tracks.");
@@ -292,7 +324,18 @@ ROFTFilter::ROFTFilter(std::vector<TrackSources> tracks, const std::vector<doubl
     cfg_.segm_delay = tracks_[0].segmentation->get_frames_between_iterations();
     cfg_.pose_delay = tracks_[0].pose ? tracks_[0].pose->get_frames_between_iterations() : 0;
     cfg_.device = device;
+    std::vector<float> mesh_vertices;
+    std::vector<std::int32_t> mesh_faces;
+    if (pose_outlier_rejection) {
+        read_obj_mesh(model_mesh_path, mesh_vertices, mesh_faces);
+        cfg_.outlier_rejection = 1;
+        cfg_.outlier_rejection_gain = pose_outlier_rejection_gain ? 1.0 : 0.0;  // the reference's `const bool` (ROFTFilter.cpp:54)
+        if (cfg_.outlier_rejection_gain == 0.0) cfg_.outlier_rejection_gain = 1.0;  // (a zero gain divides by zero there; the choice ignores it)
+    }
     if (roftb_create(&cfg_, &ctx_) != 0) throw std::runtime_error(log_name + "::ctor. Error: " + roftb_last_error(nullptr));
+    if (pose_outlier_rejection &&
+        roftb_set_mesh(ctx_, mesh_vertices.data(), int(mesh_vertices.size() / 3), mesh_faces.data(), int(mesh_faces.size() / 3)) != 0)
+        throw std::runtime_error(log_name + "::ctor. Error: " + roftb_last_error(ctx_));
     const std::size_t T = tracks_.size(), HW = cam.width * cam.height;
     flow_bytes_per_track_ = (cam.width / cfg_.flow_grid) * (cam.height / cfg_.flow_grid) * (cfg_.flow_format == ROFTB_FLOW_S16 ? 4 : 8);
     depth_.resize(T * HW);

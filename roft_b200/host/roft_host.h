@@ -193,6 +193,10 @@ private:
 };
 
 // ---- the filter -------------------------------------------------------------------------------------------
+// Wavefront OBJ triangles (v / f records, polygons fan-triangulated, 1-based or negative indices): the mesh input of the
+// depth renderer.  Stands in for MeshResource + Assimp (SICAD's model loading); throws std::runtime_error.
+void read_obj_mesh(const std::string& path, std::vector<float>& vertices, std::vector<std::int32_t>& faces);
+
 struct TrackSources {  // what main.cpp:328-388 wires into one ROFTFilter
     std::shared_ptr<CameraMeasurement> camera;
     std::shared_ptr<Segmentation> segmentation;
@@ -210,7 +214,11 @@ public:
                const std::vector<double>& measurement_covariance_v, double ut_alpha, double ut_beta, double ut_kappa,
                double sample_time, bool pose_meas, bool pose_resync, bool velocity_meas, bool flow_weighting,
                bool flow_aided_segmentation, double maximum_depth, double subsampling_radius, bool enable_log,
-               const std::string& log_path, const std::string& log_prefix, int device = 0);
+               const std::string& log_path, const std::string& log_prefix, int device = 0,
+               // render-and-compare pose outlier rejection (ROFTFilter.cpp:52-54, 184-199): the reference takes them after
+               // pose_resync; they trail here so that existing callers compile.  model_mesh_path: Wavefront OBJ of the object
+               // (what ModelParameters / MeshResource resolve to); the gain is a `const bool` in the reference
+               bool pose_outlier_rejection = false, bool pose_outlier_rejection_gain = false, const std::string& model_mesh_path = "");
     ~ROFTFilter();
     bool initialization_step();            // ROFTFilter.cpp:216-237
     bool filtering_step();                 // ROFTFilter.cpp:255-452; false = teardown (no depth)

@@ -68,9 +68,18 @@ static int main_from_config(int argc, char** argv) {
     int of_heading_zeros, of_index_offset;
     conf("optical_flow_dataset.heading_zeros", of_heading_zeros); conf("optical_flow_dataset.index_offset", of_index_offset);
     bool outlier_rejection_enable; conf("outlier_rejection.enable", outlier_rejection_enable);
-    if (outlier_rejection_enable)
-        std::cout << "outlier_rejection.enable: the render-and-compare pose test (ROFTFilter.cpp:467-621) needs the OpenGL renderer and is "
-                     "not part of this path; running without it (as --outlier_rejection::enable false)." << std::endl;
+    double outlier_rejection_gain = 0.0;
+    if (conf.exists("outlier_rejection.gain")) conf("outlier_rejection.gain", outlier_rejection_gain);
+    // ModelParameters (main.cpp:224-235): only an external Wavefront OBJ is understood here (no Assimp, no internal DB)
+    std::string model_mesh_path;
+    if (outlier_rejection_enable) {
+        if (conf.exists("model.external_path")) conf("model.external_path", model_mesh_path);
+        if (model_mesh_path.empty() || !std::ifstream(model_mesh_path).is_open()) {
+            std::cout << "outlier_rejection.enable: no readable mesh at model.external_path (Wavefront OBJ); running without the "
+                         "render-and-compare pose test (as --outlier_rejection::enable false)." << std::endl;
+            outlier_rejection_enable = false;
+        }
+    }
     std::string pose_path; conf("pose_dataset.path", pose_path);
     int pose_skip_rows, pose_skip_cols; conf("pose_dataset.skip_rows", pose_skip_rows); conf("pose_dataset.skip_cols", pose_skip_cols);
     bool pose_fps_reduction, pose_delay; conf("pose_dataset.fps_reduction", pose_fps_reduction); conf("pose_dataset.delay", pose_delay);
@@ -128,7 +137,8 @@ static int main_from_config(int argc, char** argv) {
     ROFTFilter filter(std::move(tracks), cat({&p_cov_v_0, &p_cov_w_0, &p_cov_x_0, &p_cov_q_0}), cat({&sigma_ang_vel, &psd_lin_acc}),
                       cat({&m_cov_v, &m_cov_w, &m_cov_x, &m_cov_q}), cat({&v_cov_v_0, &v_cov_w_0}), cat({&kin_q_v, &kin_q_w}), v_meas_cov_flow,
                       ut_alpha, ut_beta, ut_kappa, sample_time, use_pose, use_pose_resync, use_velocity, flow_weighting, flow_aided,
-                      depth_maximum, subsampling_radius, enable_log, log_path, "");
+                      depth_maximum, subsampling_radius, enable_log, log_path, "", 0, outlier_rejection_enable,
+                      bool(outlier_rejection_gain), model_mesh_path);  // (the gain goes through `const bool`, ROFTFilter.cpp:54)
     filter.initialization_step();
     int k = 0;
     while (filter.filtering_step()) ++k;
@@ -147,7 +157,8 @@ int main(int argc, char** argv) {
             }
         }
     std::vector<std::string> sequences;
-    std::string object = "003_cracker_box", log_path = ".", flow_set = "nvof", mask_set = "gt", pose_set = "gt";
+    std::string object = "003_cracker_box", log_path = ".", flow_set = "nvof", mask_set = "gt", pose_set = "gt", mesh_path;
+    bool outlier_rejection = false;
     int frames = -1, device = 0;
     double stride = 35.0, fps = 30.0, desired_fps = 5.0;
     bool delay = true, weight = true, resync = true, flow_aided = true;
@@ -157,6 +168,8 @@ int main(int argc, char** argv) {
         if (a == "--sequence") sequences.push_back(next());
         else if (a == "--object") object = next();
         else if (a == "--log") log_path = next();
+        else if (a == "--mesh") mesh_path = next();
+        else if (a == "--outlier-rejection") outlier_rejection = true;
         else if (a == "--flow-set") flow_set = next();
         else if (a == "--mask-set") mask_set = next();
         else if (a == "--pose-set") pose_set = next();
@@ -172,7 +185,7 @@ int main(int argc, char** argv) {
     }
     if (sequences.empty()) {
         std::cerr << "usage: roft_b200_tracker --sequence <dir> [--sequence <dir> ...] [--object name] [--log dir] [--frames N] "
-                     "[--stride S] [--flow-set s] [--mask-set s] [--pose-set s] [--no-delay] [--no-weight] [--no-resync]" << std::endl;
+                     "[--stride S] [--flow-set s] [--mask-set s] [--pose-set s] [--no-delay] [--no-weight] [--no-resync] [--outlier-rejection --mesh file.obj]" << std::endl;
         return 2;
     }
     try {
@@ -212,7 +225,7 @@ int main(int argc, char** argv) {
         const std::vector<double> p_model{1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
         const std::vector<double> p_meas{0.1, 0.1, 0.1, 1e-4, 1e-4, 1e-4, 1e-3, 1e-3, 1e-3, 1e-4, 1e-4, 1e-4};
         ROFTFilter filter(std::move(tracks), p_cov0, p_model, p_meas, v_cov0, v_q, v_r, 1.0, 2.0, 0.0, 0.033333333333, true, resync, true,
-                          weight, flow_aided, 2.0, stride, true, log_path, "", device);
+                          weight, flow_aided, 2.0, stride, true, log_path, "", device, outlier_rejection, true, mesh_path);
         filter.initialization_step();
         int k = 0;
         while ((frames < 0 || k < frames) && filter.filtering_step()) ++k;

@@ -34,6 +34,8 @@ def to_roftb_config(cfg: o.RoftConfig, n_tracks: int, flow_format="f32"):
         ut_alpha=cfg.ut_alpha, ut_beta=cfg.ut_beta, ut_kappa=cfg.ut_kappa,
         use_pose=int(cfg.use_pose), use_pose_resync=int(cfg.use_pose_resync), use_velocity=int(cfg.use_velocity),
         flow_aided=int(cfg.flow_aided), segm_delay=cfg.segm_delay, pose_delay=cfg.pose_delay,
+        outlier_rejection=int(cfg.outlier_rejection), outlier_rejection_gain=float(cfg.outlier_rejection_gain),
+        outlier_rejection_divider=int(cfg.outlier_rejection_divider),
         accum_fp64=int(os.environ.get("ROFTB_TEST_ACCUM_FP64", "2")))
 
 

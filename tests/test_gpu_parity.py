@@ -557,3 +557,57 @@ def test_pick_best_alternative_matches_oracle(lib_built):
     masks[0] = 0
     sel, lik = trk.pick_best_alternative(masks, depths, alts, 2, 0.01)
     assert sel[0] == 0 and lik[0, 0] == np.finfo(np.float64).max and lik[0, 1] == np.finfo(np.float64).max
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resync", [True, False])
+def test_filter_loop_with_outlier_rejection_matches_oracle(api, resync):
+    """cfg.outlier_rejection: every 13-sized pose measurement goes through correct_outlier_rejection (two UKF corrections,
+    depth render of both, masked L1 on the buffered features, choice - ROFTFilter.cpp:346-359, 649-676) on the device.
+    Some delivered poses are displaced by 6-10 cm so that both outcomes occur; beliefs match the oracle frame by frame
+    and the oracle took each branch at least once."""
+    import torch
+    from roft_b200.synthetic import cuboid_mesh
+    cfg = small_cfg(subsampling_radius=2.0, use_pose_resync=resync, segm_delay=3, pose_delay=3,
+                    outlier_rejection=True, outlier_rejection_divider=2)
+    T, F = 2, 26
+    seq = sequence(cfg, T, F)
+    # gross pose outliers on some deliveries (the delayed source delivers frame k - delay at steps k % delay == 0)
+    for f_idx, t, off in ((6, 0, (0.08, 0.0, 0.0)), (12, 1, (0.0, -0.06, 0.05)), (15, 0, (0.0, 0.0, 0.10))):
+        seq.pose[f_idx, t, :3] += torch.tensor(off, dtype=seq.pose.dtype)
+    verts, faces = cuboid_mesh(seq.half[0].numpy())
+    x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
+    trk = make_tracker(api, cfg, T, "f32")
+    trk.set_mesh(verts, faces)
+    trk.init(x0)
+    oracles = [o.RoftFilterOracle(cfg, x0[t], mesh=(verts, faces)) for t in range(T)]
+    for k in range(F):
+        frs = [frame_inputs(seq, cfg, k, t) for t in range(T)]
+        has_mask = frs[0].mask is not None
+        mask = np.stack([f.mask for f in frs]) if has_mask else None
+        pose = np.stack([f.pose if f.pose is not None else np.zeros(7) for f in frs])
+        pv = np.array([f.pose is not None for f in frs], np.uint8)
+        flow = np.stack([f.flow for f in frs]) if k > 0 else None
+        trk.step(np.stack([f.depth for f in frs]), flow, mask, pose=pose, pose_valid=pv)
+        pm, vm = trk.state()
+        for t in range(T):
+            ep, ev = oracles[t].step(frs[t])
+            assert rel(vm[t], ev) < TOL or np.linalg.norm(vm[t] - ev) < 1e-9, (k, t, rel(vm[t], ev))
+            assert rel(pm[t, :9], ep[:9]) < TOL, (k, t, rel(pm[t, :9], ep[:9]), oracles[t].or_selected)
+            assert quat_close(pm[t, 9:], ep[9:]) < TOL, (k, t)
+    picks = sum((orc.or_selected for orc in oracles), [])
+    assert 0 in picks and 1 in picks, picks
+    # the same run without a host synchronisation between the steps (the pose stream trails, the buffered features go
+    # through their staging copies while later steps recycle the planes): same final beliefs
+    trk2 = make_tracker(api, cfg, T, "f32")
+    trk2.set_mesh(verts, faces)
+    trk2.init(x0)
+    for k in range(F):
+        frs = [frame_inputs(seq, cfg, k, t) for t in range(T)]
+        mask = np.stack([f.mask for f in frs]) if frs[0].mask is not None else None
+        pose = np.stack([f.pose if f.pose is not None else np.zeros(7) for f in frs])
+        pv = np.array([f.pose is not None for f in frs], np.uint8)
+        flow = np.stack([f.flow for f in frs]) if k > 0 else None
+        trk2.step(np.stack([f.depth for f in frs]), flow, mask, pose=pose, pose_valid=pv)
+    pm2, vm2 = trk2.state()
+    assert rel(pm2, pm) < 1e-9 and rel(vm2, vm) < 1e-9

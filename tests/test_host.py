@@ -311,3 +311,43 @@ unscented_transform: {{ alpha = 1.0; beta = 2.0; kappa = 0.0; }}
     pa = np.loadtxt(log_a / "pose_estimate.txt"); pb = np.loadtxt(log_b / "pose_estimate.txt")
     va = np.loadtxt(log_a / "velocity_estimate.txt"); vb = np.loadtxt(log_b / "velocity_estimate.txt")
     assert pa.shape == (F, 13) and np.allclose(pa, pb, rtol=1e-9, atol=1e-12) and np.allclose(va, vb, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_tracker_executable_with_outlier_rejection(hostlib, tmp_path):
+    """roft_b200_tracker --outlier-rejection --mesh box.obj (ROFTFilter ctor parameters pose_outlier_rejection + model,
+    ROFTFilter.cpp:52-54, 184-199): a grossly displaced pose delivery is rejected like the oracle rejects it."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from roft_b200.synthetic import cuboid_mesh
+    cfg = small_cfg(subsampling_radius=4.0, segm_delay=3, pose_delay=3, sample_time=1.0 / 30.0, outlier_rejection=True)
+    F = 14
+    seq = sequence(cfg, 1, F, target_coverage=0.3, corrupt=False)
+    seq.pose[6, 0, :3] += torch.tensor([0.0, 0.07, 0.06], dtype=seq.pose.dtype)
+    root = str(tmp_path / "seq0")
+    dataset_io.write_sequence(root, seq, 0, fx=cfg.fx, fy=cfg.fy, cx=cfg.cx, cy=cfg.cy)
+    verts, faces = cuboid_mesh(seq.half[0].numpy())
+    dataset_io.write_obj(str(tmp_path / "box.obj"), verts, faces)
+    out = subprocess.run([os.path.join(HOST, "roft_b200_tracker"), "--sequence", root, "--log", str(tmp_path), "--stride", "4",
+                          "--desired-fps", "10", "--outlier-rejection", "--mesh", str(tmp_path / "box.obj")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    pose_log = np.loadtxt(tmp_path / "pose_estimate.txt")
+    x0 = np.zeros(13)
+    aa = dataset_io.quat_to_axis_angle(seq.pose[0, 0].numpy()[3:])
+    x0[6:9] = seq.pose[0, 0, :3].numpy()
+    x0[9] = np.cos(aa[3] / 2); x0[10:] = np.sin(aa[3] / 2) * aa[:3]
+    orc = o.RoftFilterOracle(cfg, x0, mesh=(verts, faces))
+    for k in range(F):
+        fr = frame_inputs(seq, cfg, k, 0)
+        if fr.pose is not None:
+            a2 = dataset_io.quat_to_axis_angle(fr.pose[3:])
+            fr.pose = np.concatenate([fr.pose[:3], [np.cos(a2[3] / 2)], np.sin(a2[3] / 2) * a2[:3]])
+        fr.dt = None if k == 0 else (k * seq.dt - (k - 1) * seq.dt)
+        ep, _ = orc.step(fr)
+        assert rel(pose_log[k, :9], ep[:9]) < 1e-4, (k, orc.or_selected)
+    assert 1 in orc.or_selected and 0 in orc.or_selected, orc.or_selected
+    # a missing mesh is an error, not a silent fallback
+    bad = subprocess.run([os.path.join(HOST, "roft_b200_tracker"), "--sequence", root, "--log", str(tmp_path), "--outlier-rejection",
+                          "--mesh", str(tmp_path / "nope.obj")], capture_output=True, text=True)
+    assert bad.returncode != 0 and "cannot open" in (bad.stdout + bad.stderr)
