@@ -55,6 +55,9 @@ WORKLOADS = {
                  name="reference defaults: CV_16SC2 flow on a 4-px grid (NVOF 1.0), subsampling_radius 35, mask coverage ~0.25, delay 6"),
     "full": dict(coverage=1.0, delay=6, stride=1, fmt="f32",
                  name="every pixel masked (coverage 1.0), dense CV_32FC2 flow, subsampling_radius 1, delay 6"),
+    "c2":   dict(coverage=0.25, delay=6, stride=1, fmt="f32", outlier_rejection=True,
+                 name="BASELINE configs[1] per track: c4 + render-and-compare pose outlier rejection on every re-synchronisation "
+                      "(cuboid mesh, per-track scale)"),
 }
 
 
@@ -246,7 +249,7 @@ class Runner:
     """One tracker + its resident synthetic frames for a workload."""
 
     def __init__(self, api, dev, local, T, F, coverage, delay, stride, fmt, accum, first_track=0, no_resync=False,
-                 single_mask=False, width=W, height=H, intr=None):
+                 single_mask=False, width=W, height=H, intr=None, outlier_rejection=False):
         import numpy as np
         import torch
         from roft_b200.synthetic import make_sequence
@@ -259,7 +262,8 @@ class Runner:
                                  pose_delay=delay, device=local, accum_fp64={"fp32": 0, "fp64": 1, "auto": 2}[accum],
                                  flow_format=api.FLOW_F32 if fmt == "f32" else api.FLOW_S16,
                                  flow_grid=1 if fmt == "f32" else 4, flow_scale=1.0 if fmt == "f32" else 32.0,
-                                 **({"use_pose_resync": 0} if no_resync else {}), **kw)
+                                 **({"use_pose_resync": 0} if no_resync else {}),
+                                 **({"outlier_rejection": 1} if outlier_rejection else {}), **kw)
         self.cfg = cfg
         self.trk = api.Tracker(cfg)
         # frames 0..F; frame 0 only provides the initial mask/pose, frames 1..F are cycled
@@ -269,6 +273,10 @@ class Runner:
         torch.cuda.synchronize()
         self.x0 = np.zeros((T, 13)); self.x0[:, 6:] = self.seq.pose[0].numpy()
         self.pose_np = self.seq.pose.numpy(); self.pv_np = self.seq.pose_valid.numpy().astype(np.uint8)
+        if outlier_rejection:  # every synthetic track shows a cuboid: unit mesh + the track's half extents
+            from roft_b200.synthetic import cuboid_mesh
+            self.trk.set_mesh(*cuboid_mesh([1.0, 1.0, 1.0]))
+            self.trk.set_mesh_scale(self.seq.half.numpy().astype(np.float32))
         self.trk.init(self.x0)
         self.step_i = 0
 
@@ -424,7 +432,8 @@ def extra_workload(api, dev, local, name, T, peak, accum):
     import numpy as np
     import torch
     wl = WORKLOADS[name]
-    r = Runner(api, dev, local, T, 6, wl["coverage"], wl["delay"], wl["stride"], wl["fmt"], accum)
+    r = Runner(api, dev, local, T, 6, wl["coverage"], wl["delay"], wl["stride"], wl["fmt"], accum,
+               outlier_rejection=wl.get("outlier_rejection", False))
 
     def barrier():
         torch.cuda.synchronize(); r.trk.sync()
@@ -475,6 +484,7 @@ def run_own(args):
         sampler.start()
 
     r = Runner(api, dev, local, T, args.frames, args.coverage, args.delay, args.stride, args.fmt, args.accum,
+               outlier_rejection=WORKLOADS[args.workload].get("outlier_rejection", False),
                first_track=rank * T, no_resync=args.no_resync, single_mask=args.single_mask)
     trk = r.trk
 
@@ -539,7 +549,10 @@ def run_own(args):
 
     # ---- parity of sample tracks against the CPU restatement (outside the timed regions) ------------------
     parity = None
-    if not args.no_parity and rank == 0:
+    if WORKLOADS[args.workload].get("outlier_rejection"):
+        # the C++ checker has no rasteriser: this workload's parity is the GPU tests' (numpy restatement, small frames)
+        parity = {"skipped": "outlier rejection is checked by tests/test_gpu_parity.py against oracle/roft_oracle.py"}
+    elif not args.no_parity and rank == 0:
         try:
             parity = parity_sample(args, api, dev, local, r, rank)
         except Exception as e:  # a checker problem must not lose the bench line; it is reported
@@ -606,7 +619,7 @@ def run_own(args):
         extras = {}
         del r, trk
         torch.cuda.empty_cache()
-        for name in ("c5", "full", "ref"):
+        for name in ("c2", "c5", "full", "ref"):
             try:
                 extras[name] = extra_workload(api, dev, local, name, T, peak, args.accum)
             except Exception as e:

@@ -200,6 +200,10 @@ int roftb_masked_depth_l1(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, 
  * (ROFTFilter.cpp:184-199, MeshResource -> SICAD::ModelStreamContainer).  Assimp is not part of this path: the caller
  * passes the triangles (vertices [n_vertices][3] in the model frame, metres; faces [n_faces][3]).  Host memory. */
 int roftb_set_mesh(roftb_ctx* ctx, const float* vertices, int32_t n_vertices, const int32_t* faces, int32_t n_faces);
+/* Batched extension without a reference counterpart (one ROFTFilter tracks one object): per-track scale [n_tracks][3]
+ * applied to the vertices of the shared mesh inside the filter loop's render-and-compare test, so that a batch can
+ * hold objects of different sizes; NULL removes it.  Host memory. */
+int roftb_set_mesh_scale(roftb_ctx* ctx, const float* scale);
 /* SICAD::superimpose(poses, cam_x = 0, cam_o = identity, ..., depth) (SICAD.cpp:924-1066, depth attachment of
  * shader_model.frag:33-52) for a renderer built like ROFTFilter.cpp:194-198 (every intrinsic / divider, OpenGL-to-camera
  * rotation pi about x): poses [n_items][7] = (x, y, z, axis x y z, angle) as SICAD::ModelPose; out_depth

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "roftb_kernel_launches", "roftb_stream", "roftb_profile", "roftb_filter_init", "roftb_filter_step", "roftb_get_state",
     "roftb_get_mask", "roftb_get_velocity_info", "roftb_get_worklist", "roftb_mask_sync", "roftb_flow_velocity", "roftb_velocity_kf",
     "roftb_flow_measurement_export", "roftb_masked_points", "roftb_masked_depth_l1", "roftb_ukf_predict",
-    "roftb_ukf_correct", "roftb_set_mesh", "roftb_render_depth", "roftb_pick_best_alternative",
+    "roftb_ukf_correct", "roftb_set_mesh", "roftb_set_mesh_scale", "roftb_render_depth", "roftb_pick_best_alternative",
 ]
 
 
@@ -102,6 +102,7 @@ def load_library() -> C.CDLL:
     lib.roftb_masked_points.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_void_p]
     lib.roftb_masked_depth_l1.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.roftb_set_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    lib.roftb_set_mesh_scale.argtypes = [C.c_void_p, C.c_void_p]
     lib.roftb_render_depth.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     lib.roftb_pick_best_alternative.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double,
                                                 C.c_void_p, C.c_void_p]
@@ -341,6 +342,10 @@ class Tracker:
     def set_mesh(self, vertices, faces):
         v = _np(vertices, np.float32); f = _np(faces, np.int32)
         self._check(self._lib.roftb_set_mesh(self._h, _ptr(v), int(v.shape[0]), _ptr(f), int(f.shape[0])), "roftb_set_mesh")
+
+    def set_mesh_scale(self, scale):
+        sc = None if scale is None else _np(scale, np.float32)
+        self._check(self._lib.roftb_set_mesh_scale(self._h, _ptr(sc)), "roftb_set_mesh_scale")
 
     def render_depth(self, poses7, divider: int):
         p = _np(poses7, np.float64)

@@ -34,8 +34,11 @@ struct RVertex {
 __global__ void __launch_bounds__(kThreads) k_render_vertices(RenderArgs a, RVertex* __restrict__ out) {
     const int item = blockIdx.y;
     const float* m = a.model + (long long)item * 12;
+    // optional per-track scale of the shared mesh (batched tracks of differently sized objects): items are [alternative][track]
+    const float* sc = a.scale ? a.scale + 3 * (item % a.n_scale) : nullptr;
+    const float sx = sc ? sc[0] : 1.f, sy = sc ? sc[1] : 1.f, sz = sc ? sc[2] : 1.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_vertices; i += gridDim.x * blockDim.x) {
-        const float x = a.vertices[3 * i], y = a.vertices[3 * i + 1], z = a.vertices[3 * i + 2];
+        const float x = __fmul_rn(a.vertices[3 * i], sx), y = __fmul_rn(a.vertices[3 * i + 1], sy), z = __fmul_rn(a.vertices[3 * i + 2], sz);
         // p = R v + t, IEEE FP32 without contraction
         const float X = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[9]);
         const float Y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[3], x), __fmul_rn(m[4], y)), __fmul_rn(m[5], z)), m[10]);

@@ -83,6 +83,7 @@ struct roftb_ctx {
     float* mesh_vertices = nullptr;                  // outlier-rejection mesh (roftb_set_mesh): device [n][3]
     int32_t* mesh_faces = nullptr;
     int mesh_nv = 0, mesh_nf = 0;
+    float* mesh_scale = nullptr;                     // optional [T][3] (roftb_set_mesh_scale)
     unsigned long long* span_clock = nullptr;        // diagnostics: [8 steps][init, scatter, gather, velocity, ukf][2]
     cudaStream_t vel_side[2] = {nullptr, nullptr};   // larger-cluster launches of the velocity kernel (biggest tracks)
     cudaEvent_t vel_fork = nullptr, vel_join[2] = {nullptr, nullptr};
@@ -490,7 +491,7 @@ void roftb_destroy(roftb_ctx* ctx) {
     void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->mask_state[2], ctx->mask_occ[0], ctx->mask_occ[1], ctx->mask_occ[2],
                      ctx->winner, ctx->scratch.nu, ctx->scratch.dp, ctx->scratch.r, ctx->scratch.hist, ctx->scratch.chunk_cnt,
                      ctx->scratch.part, ctx->scratch.track_sel, ctx->scratch.sel_part, ctx->scratch.slot_bitmap, ctx->scratch.track_slot, ctx->scratch.chunk_aux,
-                     ctx->wl_units, ctx->wl_pixels, ctx->phase_clock, ctx->span_clock, ctx->mesh_vertices, ctx->mesh_faces, ctx->vel_order, ctx->vel_ticket, ctx->order_units,
+                     ctx->wl_units, ctx->wl_pixels, ctx->phase_clock, ctx->span_clock, ctx->mesh_vertices, ctx->mesh_faces, ctx->mesh_scale, ctx->vel_order, ctx->vel_ticket, ctx->order_units,
                      ctx->wt_count2, ctx->wt_list, ctx->wt_n, ctx->nl_count, ctx->nl_list, ctx->nl_n, ctx->stat, ctx->plan, ctx->fbuf, ctx->v_mean,
                      ctx->v_cov, ctx->p_mean, ctx->p_cov, ctx->pb_mean, ctx->pb_cov, ctx->vel_hist, ctx->q_diag,
                      ctx->d_count, ctx->d_lambda, ctx->d_eta, ctx->d_wctl, ctx->d_vctl, ctx->d_ops, ctx->d_nops,
@@ -1186,6 +1187,7 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
             ra.model = oj.model;
             ra.fx = (float)(cfg.fx / dv); ra.fy = (float)(cfg.fy / dv); ra.cx = (float)(cfg.cx / dv); ra.cy = (float)(cfg.cy / dv);
             ra.w = ctx->g.W / dv; ra.h = ctx->g.H / dv;
+            ra.scale = ctx->mesh_scale; ra.n_scale = T;
             if (launch_render_depth(ra, oj.vertex_scratch, oj.zbuf, oj.rendered, us)) return fail(ctx, "launch_render_depth failed");
             CK(cudaMemsetAsync(oj.err, 0, sizeof(double) * 2 * T, us));
             CK(cudaMemsetAsync(oj.samples, 0, sizeof(int32_t) * 2 * T, us));
@@ -1623,6 +1625,7 @@ int render_tiles(roftb_ctx* ctx, TmpBuf& tb, int n_items, const double* poses7, 
     ra.fx = (float)(ctx->cfg.fx / divider); ra.fy = (float)(ctx->cfg.fy / divider);
     ra.cx = (float)(ctx->cfg.cx / divider); ra.cy = (float)(ctx->cfg.cy / divider);
     ra.w = w; ra.h = h;
+    ra.scale = nullptr; ra.n_scale = 1;  // (the operators render the mesh as uploaded)
     void* vs = tb.alloc<char>(render_vertex_scratch_bytes(n_items, ctx->mesh_nv));
     uint32_t* zb = tb.alloc<uint32_t>((size_t)n_items * w * h);
     float* out = tb.alloc<float>((size_t)n_items * w * h);
@@ -1657,6 +1660,20 @@ int roftb_set_mesh(roftb_ctx* ctx, const float* vertices, int32_t n_vertices, co
         ctx->orj.vertex_scratch = nullptr;
         CK(cudaMalloc(&ctx->orj.vertex_scratch, render_vertex_scratch_bytes(2 * ctx->T, n_vertices)));
     }
+    return 0;
+}
+
+int roftb_set_mesh_scale(roftb_ctx* ctx, const float* scale) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaStreamSynchronize(ctx->ukf_stream));
+    if (!scale) {
+        if (ctx->mesh_scale) cudaFree(ctx->mesh_scale);
+        ctx->mesh_scale = nullptr;
+        return 0;
+    }
+    if (!ctx->mesh_scale) CK(cudaMalloc(&ctx->mesh_scale, (size_t)ctx->T * 3 * sizeof(float)));
+    CK(cudaMemcpy(ctx->mesh_scale, scale, (size_t)ctx->T * 3 * sizeof(float), cudaMemcpyHostToDevice));
     return 0;
 }
 

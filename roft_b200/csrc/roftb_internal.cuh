@@ -246,6 +246,7 @@ struct RenderArgs {
     const float* model;                      // device [n_items][12]: rotation row-major (9), translation (3)
     float fx, fy, cx, cy;                    // intrinsics of the tile (camera intrinsics / divider)
     int w, h;
+    const float* scale; int n_scale;         // optional device [n_scale][3]: vertex scale of item i = scale[i % n_scale]
 };
 size_t render_vertex_scratch_bytes(int n_items, int n_vertices);
 int launch_render_depth(const RenderArgs& a, void* vertex_scratch, uint32_t* zbuf, float* out, cudaStream_t s);

@@ -578,9 +578,13 @@ def test_filter_loop_with_outlier_rejection_matches_oracle(api, resync):
     verts, faces = cuboid_mesh(seq.half[0].numpy())
     x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
     trk = make_tracker(api, cfg, T, "f32")
-    trk.set_mesh(verts, faces)
+    if resync:
+        trk.set_mesh(verts, faces)
+    else:  # batched extension: one unit mesh, per-track scale (roftb_set_mesh_scale)
+        trk.set_mesh(*cuboid_mesh([1.0, 1.0, 1.0]))
+        trk.set_mesh_scale(np.stack([seq.half[t].numpy() for t in range(T)]))
     trk.init(x0)
-    oracles = [o.RoftFilterOracle(cfg, x0[t], mesh=(verts, faces)) for t in range(T)]
+    oracles = [o.RoftFilterOracle(cfg, x0[t], mesh=cuboid_mesh(seq.half[t].numpy())) for t in range(T)]
     for k in range(F):
         frs = [frame_inputs(seq, cfg, k, t) for t in range(T)]
         has_mask = frs[0].mask is not None
@@ -601,6 +605,9 @@ def test_filter_loop_with_outlier_rejection_matches_oracle(api, resync):
     # through their staging copies while later steps recycle the planes): same final beliefs
     trk2 = make_tracker(api, cfg, T, "f32")
     trk2.set_mesh(verts, faces)
+    if not resync:
+        trk2.set_mesh(*cuboid_mesh([1.0, 1.0, 1.0]))
+        trk2.set_mesh_scale(np.stack([seq.half[t].numpy() for t in range(T)]))
     trk2.init(x0)
     for k in range(F):
         frs = [frame_inputs(seq, cfg, k, t) for t in range(T)]
