@@ -116,10 +116,6 @@ __device__ __forceinline__ void red_shared_inc_if_eq(uint32_t smem_addr, uint32_
         "r"(x), "r"(y)
         : "memory");
 }
-__device__ __forceinline__ uint32_t nibble_of(uint32_t bytemask) {
-    // bytemask has 0xff / 0x00 per byte (vcmp result): gather bit 0 of each byte into bits 0..3
-    return ((bytemask & 0x01010101u) * 0x10204080u) >> 28;
-}
 // high bit of every non-zero byte of x
 __device__ __forceinline__ uint32_t nz4(uint32_t x) { return (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u; }
 __device__ __forceinline__ float comp(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
@@ -207,7 +203,6 @@ struct VtArgs {
     unsigned long long* phase_clock;                      // optional [T][8]
     unsigned long long* span_clock;                       // optional [2]
     int l2_hint;
-    int dbg;                                              // knock-out experiments (timing only, WRONG results): 1 no mask stores, 2 no record stores, 4 no flag stores
     int stage_mode;                                       // pass A staging: 0 = bulk copies + mbarrier, 1 = per-lane cp.async groups
     int slice_cap;                                        // list entries a CTA may own
     int smem_tab, smem_list;                              // byte offsets into dynamic shared memory
@@ -651,10 +646,10 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
                         const unsigned bx = __float_as_uint(__fadd_rz(fmaxf(tx, 0.0f), 8388608.0f));
                         const unsigned by = __float_as_uint(__fadd_rz(fmaxf(ty, 0.0f), 8388608.0f));
                         const unsigned di = by * uW + bx - sc_bias;
-                        if (ok && !(a.dbg & 1)) dst_t[di] = sc_val;
+                        if (ok) dst_t[di] = sc_val;
                         // occupancy flag of the destination unit (idempotent store, skipped while the unit repeats)
                         const int du = (int)(di >> 7);
-                        const bool nf = ok && du != last_flag && !(a.dbg & 4);
+                        const bool nf = ok && du != last_flag;
                         if (nf) odst_t[du] = 1;
                         last_flag = nf ? du : last_flag;
                     }
@@ -677,7 +672,7 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
                 int idx = woff + __popc(b0 & lt_mask) + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    if (valid[i] && !(a.dbg & 2)) {
+                    if (valid[i]) {
                         nu_c[idx] = make_float2(n1[i], n2[i]);
                         dp_c[idx] = make_uint2(__float_as_uint(dd[i]), pk0 + (uint32_t)i);
                     }
@@ -1475,8 +1470,6 @@ int launch_velocity(const VelocityArgs& a, cudaStream_t s) {
     va.l2_hint = env_hint;
     static const int env_stage = [] { const char* e = getenv("ROFTB_STAGE"); return e ? atoi(e) : 1; }();
     va.stage_mode = env_stage;
-    static const int env_dbg = [] { const char* e = getenv("ROFTB_VT_KNOCKOUT"); return e ? atoi(e) : 0; }();
-    va.dbg = env_dbg;
     // the bulk-copy ring needs dense float2 flow at full resolution and whole 16-byte groups; every other
     // configuration (CV_16SC2 / sub-sampled flow grids, stride > 1) takes the register path of the same kernel
     static const int env_ring = [] { const char* e = getenv("ROFTB_RING"); return e ? atoi(e) : 1; }();
