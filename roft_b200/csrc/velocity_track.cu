@@ -32,6 +32,8 @@
 // HBM-bound phase A of one track with the L2- / issue-bound phases of others - with a single launch per step.
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "roftb_internal.cuh"
 
 namespace roftb {
@@ -1033,6 +1035,12 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
         const bool fp64 = a.accum_fp64 == 1 || (a.accum_fp64 == 2 && N < kAutoFp64Candidates);
         double* out = &s_part[warp][0];
         if (!fp64) {
+            // SW = -1: all 40 sums in one sweep over the records.  SW = 0 / 1 (the 80-register build, three CTAs per SM):
+            // two sweeps with 20 sums each - row 0 of the S blocks and the g vectors, then rows 1-4 - so that the accumulators
+            // fit the register budget; the records are re-read from L2 and the weight is recomputed
+            auto run_sweep = [&](auto SWC) {
+            constexpr int SW = decltype(SWC)::value;
+            constexpr int PF = SW < 0 ? 4 : 2;  // records in flight per lane
             float2 acc2[20];
 #pragma unroll
             for (int i = 0; i < 20; ++i) acc2[i] = make_float2(0.f, 0.f);
@@ -1045,7 +1053,7 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
                 const float ia = rcp_approx(d);
                 const float nr = sqrt_approx(fmaf(n1, n1, n2 * n2));
                 const float dev = fabsf(nr - sp.m);
-                dmin = fminf(dmin, ok ? dev : 3.0e38f);
+                if (SW <= 0) dmin = fminf(dmin, ok ? dev : 3.0e38f);
                 float l = sp.use ? fmaxf(ex2_approx(dev * sp.k2), sp.floor_) : 1.0f;
                 l = ok ? l : 0.f;
                 const float2 e[5] = {make_float2(ia, ia), make_float2(-xh * ia, -yh * ia), make_float2(-xh * yh, -fmaf(yh, yh, 1.0f)),
@@ -1059,17 +1067,19 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
                 for (int r = 0; r < 5; ++r)
 #pragma unroll
                     for (int qq = r; qq < 5; ++qq) {
-                        acc2[o] = __ffma2_rn(w[r], e[qq], acc2[o]);
+                        if (SW < 0 || (SW == 0) == (r == 0)) acc2[o] = __ffma2_rn(w[r], e[qq], acc2[o]);
                         ++o;
                     }
-                const float2 zz = make_float2(n1, n2);
+                if (SW <= 0) {
+                    const float2 zz = make_float2(n1, n2);
 #pragma unroll
-                for (int kk = 0; kk < 5; ++kk) acc2[15 + kk] = __ffma2_rn(w[kk], zz, acc2[15 + kk]);
+                    for (int kk = 0; kk < 5; ++kk) acc2[15 + kk] = __ffma2_rn(w[kk], zz, acc2[15 + kk]);
+                }
             };
-            // software pipeline: the four records of the NEXT trip are in flight while this trip's are accumulated
-            auto fetch = [&](const float2* nup, const uint2* dpp, int k, int n, float2 (&A)[4], uint2 (&D)[4]) {
+            // software pipeline: the records of the NEXT trip are in flight while this trip's are accumulated
+            auto fetch = [&](const float2* nup, const uint2* dpp, int k, int n, float2 (&A)[PF], uint2 (&D)[PF]) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < PF; ++u) {
                     A[u] = make_float2(0.f, 0.f);
                     D[u] = make_uint2(0u, 0u);
                     if (k + 32 * u < n) {
@@ -1086,18 +1096,18 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
                 const long long off = (long long)c * chunk_stride + (lo - s_base[c]);
                 const float2* nup = nu_t + off;
                 const uint2* dpp = dp_t + off;
-                float2 A[4];
-                uint2 D[4];
+                float2 A[PF];
+                uint2 D[PF];
                 fetch(nup, dpp, lane, n, A, D);
 #pragma unroll 1
-                for (int k = lane; k < n; k += 128) {
-                    float2 An[4];
-                    uint2 Dn[4];
-                    fetch(nup, dpp, k + 128, n, An, Dn);
+                for (int k = lane; k < n; k += 32 * PF) {
+                    float2 An[PF];
+                    uint2 Dn[PF];
+                    fetch(nup, dpp, k + 32 * PF, n, An, Dn);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) accum(A[u].x, A[u].y, D[u].x, D[u].y, k + 32 * u < n);
+                    for (int u = 0; u < PF; ++u) accum(A[u].x, A[u].y, D[u].x, D[u].y, k + 32 * u < n);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
+                    for (int u = 0; u < PF; ++u) {
                         A[u] = An[u];
                         D[u] = Dn[u];
                     }
@@ -1107,19 +1117,29 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
             }
 #pragma unroll
             for (int o = 0; o < 15; ++o) {
+                if (!(SW < 0 || (SW == 0) == (o < 5))) continue;  // (o < 5 <=> row 0)
                 const float s1 = warp_sum(acc2[o].x), s2 = warp_sum(acc2[o].y);
                 if (lane == 0) {
                     out[o] = (double)s1;
                     out[15 + o] = (double)s2;
                 }
             }
+            if (SW <= 0) {
 #pragma unroll
-            for (int kk = 0; kk < 5; ++kk) {
-                const float s1 = warp_sum(acc2[15 + kk].x), s2 = warp_sum(acc2[15 + kk].y);
-                if (lane == 0) {
-                    out[30 + kk] = (double)s1;
-                    out[35 + kk] = (double)s2;
+                for (int kk = 0; kk < 5; ++kk) {
+                    const float s1 = warp_sum(acc2[15 + kk].x), s2 = warp_sum(acc2[15 + kk].y);
+                    if (lane == 0) {
+                        out[30 + kk] = (double)s1;
+                        out[35 + kk] = (double)s2;
+                    }
                 }
+            }
+            };
+            if (REGS > 80) {
+                run_sweep(std::integral_constant<int, -1>());
+            } else {
+                run_sweep(std::integral_constant<int, 0>());
+                run_sweep(std::integral_constant<int, 1>());
             }
         } else {
             // FP64 terms and sums (small, typically ill-conditioned tracks; accum_fp64): three sweeps over the chunk's
