@@ -122,12 +122,17 @@ __device__ void jacobi_warp(UkfSmem& s, int n, int lane) {
                     // |apq| > tol * sqrt(|app aqq|), squared (no square root on the critical path)
                     if (apq * apq > kTol2 * fabs(app * aqq)) {
                         rot = true;
-                        // t = sign(theta) / (|theta| + sqrt(theta^2 + 1)) with theta = (aqq - app) / (2 apq), written
-                        // with one square root and one division
+                        // rotation angle phi, |phi| <= pi/4, with tan(2 phi) = be / al for al = aqq - app, be = 2 apq - the same
+                        // angle as t = sign(theta) / (|theta| + sqrt(theta^2 + 1)), theta = al / be, c = 1 / sqrt(t^2 + 1),
+                        // s = t c - from the double-angle identities: cos(2 phi) = |al| / sqrt(al^2 + be^2),
+                        // c = sqrt((1 + cos 2phi) / 2), s = sin(2 phi) / (2 c).  Two reciprocal square roots on the critical
+                        // path of a round instead of a square root, a division and a reciprocal square root.
                         const double al = aqq - app, be = 2.0 * apq;
-                        const double tt = copysign(fabs(be), al * be) / (fabs(al) + sqrt(al * al + be * be));
-                        c = rsqrt(tt * tt + 1.0);
-                        sn = tt * c;
+                        const double rq = rsqrt(al * al + be * be);
+                        const double h = fma(0.5 * fabs(al), rq, 0.5);
+                        const double rc = rsqrt(h);
+                        c = h * rc;
+                        sn = copysign(0.5 * fabs(be) * rq * rc, al * be);
                     }
                 }
             }
@@ -164,13 +169,9 @@ __device__ void jacobi_warp(UkfSmem& s, int n, int lane) {
                 if (pj < 0) continue;
                 const double cc = s.jc[j], ss = s.js[j];
                 const double apk = s.A[pj][rk[i]], aqk = s.A[qj][rk[i]];
-                s.A[pj][rk[i]] = cc * apk - ss * aqk;
-                s.A[qj][rk[i]] = ss * apk + cc * aqk;
-            }
-            __syncwarp();
-            if (rot) {
-                s.A[p][q] = 0.0;
-                s.A[q][p] = 0.0;
+                // the rotated pair of off-diagonal entries is zero by construction: store it as such (exactly symmetric)
+                s.A[pj][rk[i]] = rk[i] == qj ? 0.0 : cc * apk - ss * aqk;
+                s.A[qj][rk[i]] = rk[i] == pj ? 0.0 : ss * apk + cc * aqk;
             }
             __syncwarp();
         }
@@ -248,7 +249,7 @@ __device__ __forceinline__ void make_sigma_point(const UkfSmem& s, int i, int n,
 }
 
 // ---- predict ----------------------------------------------------------------------------------
-__device__ void ukf_predict_warp(UkfSmem& s, const UkfParams& p, double T, int lane) {
+__device__ __noinline__ void ukf_predict_warp(UkfSmem& s, const UkfParams& p, double T, int lane) {
     const int k = 9, n = 21, npts = 43;
     const UtW w = ut_weights(n, p);
     const double sc = sqrt(w.c);
@@ -311,7 +312,7 @@ __device__ void ukf_predict_warp(UkfSmem& s, const UkfParams& p, double T, int l
 }
 
 // ---- correct ----------------------------------------------------------------------------------
-__device__ void ukf_correct_warp(UkfSmem& s, const UkfParams& p, int mtype, const double* meas, int lane) {
+__device__ __noinline__ void ukf_correct_warp(UkfSmem& s, const UkfParams& p, int mtype, const double* meas, int lane) {
     if (mtype == ROFTB_MEAS_NONE) return;
     const bool has_v = (mtype == ROFTB_MEAS_VELOCITY || mtype == ROFTB_MEAS_POSE_VELOCITY);
     const bool has_p = (mtype == ROFTB_MEAS_POSE || mtype == ROFTB_MEAS_POSE_VELOCITY);
