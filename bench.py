@@ -407,9 +407,10 @@ def latency_block(api, dev, local, frames=300):
     import numpy as np
     r = Runner(api, dev, local, 1, 12, 0.25, 6, 1, "f32", "auto", width=640, height=480, intr=(617.0, 617.0, 312.0, 241.0))
     seq = r.seq
-    hd = [seq.depth[i].cpu().numpy() for i in range(r.F + 1)]
-    hf = [seq.flow[i].cpu().numpy() for i in range(r.F + 1)]
-    hm = [seq.mask[i].cpu().numpy() for i in range(r.F + 1)]
+    # pinned host buffers, like the e2e measurement (a caller that hands over pageable memory pays the driver's staging copy)
+    hd = [seq.depth[i].cpu().pin_memory() for i in range(r.F + 1)]
+    hf = [seq.flow[i].cpu().pin_memory() for i in range(r.F + 1)]
+    hm = [seq.mask[i].cpu().pin_memory() for i in range(r.F + 1)]
     lat = []
     for step in range(frames + 20):
         f = r.frame_of(step); s = r.stale(step)
@@ -421,7 +422,7 @@ def latency_block(api, dev, local, frames=300):
             lat.append((time.perf_counter() - t0) * 1e3)
         r.step_i += 1
     lat = np.sort(np.array(lat))
-    return {"workload": "BASELINE configs[2]: 640x480, single track, dense flow, subsampling_radius 1, delay 6, host buffers "
+    return {"workload": "BASELINE configs[2]: 640x480, single track, dense flow, subsampling_radius 1, delay 6, pinned host buffers "
                         "(upload + step + blocking read-back of the beliefs per frame)",
             "frames": int(len(lat)), "p50_ms": float(lat[len(lat) // 2]), "p95_ms": float(lat[int(len(lat) * 0.95)]),
             "mean_ms": float(lat.mean()), "finite": bool(np.isfinite(pm).all() and np.isfinite(vm).all())}
