@@ -450,6 +450,8 @@ def extra_workload(api, dev, local, name, T, peak, accum):
            "value": T / (ms * 1e-3), "unit": "tracked frames/s", "ms_per_step": ms,
            "algorithmic_bytes_per_track_frame": B, "roofline_achieved": gbs, "roofline_frac": gbs / peak,
            "mean_listed_units": float(units.mean()), "mean_valid_pixels": float(cnt.mean()),
+           # dram__bytes_read + dram__bytes_write of ONE velocity-kernel launch of this workload (committed ncu capture), or null
+           "velocity_kernel_traffic": ncu_traffic(f"velocity_{name}", T),
            "finite": bool(np.isfinite(pm).all() and np.isfinite(vm).all())}
     del r
     torch.cuda.empty_cache()
