@@ -69,7 +69,7 @@ def quat_to_axis_angle(q: np.ndarray) -> np.ndarray:
 
 
 def write_sequence(root: str, seq, track: int, object_name: str = "003_cracker_box", flow_set: str = "nvof",
-                   mask_set: str = "gt", pose_set: str = "gt", fx=None, fy=None, cx=None, cy=None) -> None:
+                   mask_set: str = "gt", pose_set: str = "gt", fx=None, fy=None, cx=None, cy=None, mask_format: str = "pgm") -> None:
     """Dump one track of a roft_b200.synthetic.SyntheticSequence as a Fast-YCB-format directory."""
     F = seq.depth.shape[0]
     H, W = seq.depth.shape[2], seq.depth.shape[3]
@@ -80,7 +80,11 @@ def write_sequence(root: str, seq, track: int, object_name: str = "003_cracker_b
             write_depth(os.path.join(root, "depth", f"{k}.float"), seq.depth[k, track].cpu().numpy())
             if k > 0:
                 write_flow(os.path.join(root, "optical_flow", flow_set, f"{k}.float"), seq.flow[k, track].cpu().numpy())
-            write_pgm(os.path.join(root, "masks", mask_set, f"{object_name}_{k}.pgm"), seq.mask[k, track].cpu().numpy())
+            if mask_format == "png":  # the format of the Fast-YCB / HO-3D mask directories (needs OpenCV for the writer only)
+                import cv2
+                cv2.imwrite(os.path.join(root, "masks", mask_set, f"{object_name}_{k}.png"), seq.mask[k, track].cpu().numpy())
+            else:
+                write_pgm(os.path.join(root, "masks", mask_set, f"{object_name}_{k}.pgm"), seq.mask[k, track].cpu().numpy())
             stamp = k * seq.dt
             fd.write(f"{stamp!r} {stamp!r} 0 0 0 1 0 0 0\n")
             p = seq.pose[k, track].numpy()

@@ -2,12 +2,16 @@
 // batched ROFTFilter that forwards every frame to libroft_b200.so through the C ABI.
 #include "roft_host.h"
 
+#include <zlib.h>
+
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iomanip>
 #include <iostream>
+#include <iterator>
 #include <sstream>
 #include <stdexcept>
 
@@ -115,21 +119,90 @@ bool DatasetImageSegmentation::step_frame() {
 }
 std::pair<bool, MaskImage> DatasetImageSegmentation::segmentation(const bool&) { return read_file(std::size_t(head_)); }
 
+// Greyscale PNG -> 8-bit plane, what cv::imread(IMREAD_UNCHANGED) + convertTo(CV_8UC1) give for the masks of the Fast-YCB /
+// HO-3D layouts (DatasetImageSegmentation.cpp:130-132): colour type 0, bit depth 8 or 16 (16-bit samples saturate to 255
+// like cv::saturate_cast), non-interlaced.  zlib does the inflate; the five scanline filters are undone here.
+bool read_png_gray8(const std::string& file_name, MaskImage& out) {
+    std::ifstream in(file_name, std::ios::binary);
+    if (!in) return false;
+    std::vector<unsigned char> file((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (file.size() < 33 || std::memcmp(file.data(), sig, 8) != 0) return false;
+    auto be32 = [&](std::size_t o) { return (std::uint32_t(file[o]) << 24) | (std::uint32_t(file[o + 1]) << 16) | (std::uint32_t(file[o + 2]) << 8) | file[o + 3]; };
+    std::size_t w = 0, h = 0;
+    int depth = 0, colour = -1, interlace = 0;
+    std::vector<unsigned char> idat;
+    for (std::size_t o = 8; o + 12 <= file.size();) {
+        const std::size_t len = be32(o);
+        if (o + 12 + len > file.size()) return false;
+        const std::string type(reinterpret_cast<const char*>(&file[o + 4]), 4);
+        if (type == "IHDR" && len >= 13) {
+            w = be32(o + 8); h = be32(o + 12);
+            depth = file[o + 16]; colour = file[o + 17]; interlace = file[o + 20];
+        } else if (type == "IDAT") {
+            idat.insert(idat.end(), file.begin() + long(o + 8), file.begin() + long(o + 8 + len));
+        } else if (type == "IEND") {
+            break;
+        }
+        o += 12 + len;
+    }
+    if (!w || !h || colour != 0 || (depth != 8 && depth != 16) || interlace != 0) return false;
+    const std::size_t bpp = std::size_t(depth / 8), stride = w * bpp;
+    std::vector<unsigned char> raw((stride + 1) * h);
+    uLongf raw_len = uLongf(raw.size());
+    if (uncompress(raw.data(), &raw_len, idat.data(), uLong(idat.size())) != Z_OK || raw_len != raw.size()) return false;
+    std::vector<unsigned char> prev(stride, 0), cur(stride);
+    out.cols = w; out.rows = h;
+    out.data.resize(w * h);
+    for (std::size_t y = 0; y < h; ++y) {
+        const unsigned char* line = &raw[y * (stride + 1)];
+        const int filter = line[0];
+        for (std::size_t x = 0; x < stride; ++x) {
+            const int a = x >= bpp ? cur[x - bpp] : 0, b = prev[x], cc = x >= bpp ? prev[x - bpp] : 0;
+            int pred = 0;
+            switch (filter) {
+                case 0: pred = 0; break;
+                case 1: pred = a; break;
+                case 2: pred = b; break;
+                case 3: pred = (a + b) / 2; break;
+                case 4: {
+                    const int p = a + b - cc, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - cc);
+                    pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : cc);
+                    break;
+                }
+                default: return false;
+            }
+            cur[x] = static_cast<unsigned char>(line[1 + x] + pred);
+        }
+        for (std::size_t x = 0; x < w; ++x) {
+            const unsigned v = bpp == 1 ? cur[x] : ((unsigned(cur[2 * x]) << 8) | cur[2 * x + 1]);
+            out.data[y * w + x] = static_cast<std::uint8_t>(v > 255u ? 255u : v);
+        }
+        prev.swap(cur);
+    }
+    return true;
+}
+
 std::pair<bool, MaskImage> DatasetImageSegmentation::read_file(std::size_t index) {
     const std::string file_name = dataset_path_ + object_name_ + "_" + compose_file_name(int(index), heading_zeros_) + "." + format_;
-    std::ifstream in(file_name, std::ios::binary);
-    if (!in) {
+    auto fail = [&]() {
         std::cout << "DatasetImageSegmentation::segmentation. Error: cannot load segmentation data for frame " + file_name << std::endl;
-        return {false, MaskImage()};
+        return std::pair<bool, MaskImage>{false, MaskImage()};
+    };
+    MaskImage m;
+    if (format_ == "png") {
+        if (!read_png_gray8(file_name, m) || m.cols != width_ || m.rows != height_) return fail();
+        return {true, std::move(m)};
     }
-    // binary PGM (P5), maxval 255
+    std::ifstream in(file_name, std::ios::binary);
+    if (!in) return fail();
+    // binary PGM (P5), maxval 255 (the format the synthetic sequences of tests / bench are written in)
     std::string magic;
     std::size_t w = 0, h = 0;
     int maxval = 0;
     in >> magic >> w >> h >> maxval;
     in.get();
     if (magic != "P5" || maxval != 255 || w != width_ || h != height_) return {false, MaskImage()};
-    MaskImage m;
     m.cols = w;
     m.rows = h;
     m.data.resize(w * h);
@@ -466,4 +539,13 @@ int rofth_delivered_index(int head, int delay, int head_0, int simulate) {
     return ROFT::DatasetImageSegmentationDelayed::delivered_index(head, delay, head_0, simulate != 0);
 }
 int rofth_is_flow_valid(float fx, float fy) { return ROFT::OpticalFlowUtils::is_flow_valid(fx, fy) ? 1 : 0; }
+// PNG mask -> out[capacity] (row-major 8-bit); returns 0 and the size, -1 on a reader error, -2 if it does not fit
+int rofth_read_png(const char* path, unsigned char* out, unsigned long long capacity, unsigned long long* cols, unsigned long long* rows) {
+    ROFT::MaskImage m;
+    if (!ROFT::read_png_gray8(path, m)) return -1;
+    *cols = m.cols; *rows = m.rows;
+    if (m.data.size() > capacity) return -2;
+    std::memcpy(out, m.data.data(), m.data.size());
+    return 0;
+}
 }

@@ -193,6 +193,9 @@ private:
 };
 
 // ---- the filter -------------------------------------------------------------------------------------------
+// 8-bit plane of a greyscale PNG (colour type 0, 8 or 16 bit, non-interlaced): cv::imread + convertTo(CV_8UC1) for masks
+bool read_png_gray8(const std::string& file_name, struct MaskImage& out);
+
 // Wavefront OBJ triangles (v / f records, polygons fan-triangulated, 1-based or negative indices): the mesh input of the
 // depth renderer.  Stands in for MeshResource + Assimp (SICAD's model loading); throws std::runtime_error.
 void read_obj_mesh(const std::string& path, std::vector<float>& vertices, std::vector<std::int32_t>& faces);

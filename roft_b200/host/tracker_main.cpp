@@ -157,7 +157,7 @@ int main(int argc, char** argv) {
             }
         }
     std::vector<std::string> sequences;
-    std::string object = "003_cracker_box", log_path = ".", flow_set = "nvof", mask_set = "gt", pose_set = "gt", mesh_path;
+    std::string object = "003_cracker_box", log_path = ".", flow_set = "nvof", mask_set = "gt", pose_set = "gt", mesh_path, mask_format = "pgm";
     bool outlier_rejection = false;
     int frames = -1, device = 0;
     double stride = 35.0, fps = 30.0, desired_fps = 5.0;
@@ -169,6 +169,7 @@ int main(int argc, char** argv) {
         else if (a == "--object") object = next();
         else if (a == "--log") log_path = next();
         else if (a == "--mesh") mesh_path = next();
+        else if (a == "--mask-format") mask_format = next();
         else if (a == "--outlier-rejection") outlier_rejection = true;
         else if (a == "--flow-set") flow_set = next();
         else if (a == "--mask-set") mask_set = next();
@@ -185,7 +186,7 @@ int main(int argc, char** argv) {
     }
     if (sequences.empty()) {
         std::cerr << "usage: roft_b200_tracker --sequence <dir> [--sequence <dir> ...] [--object name] [--log dir] [--frames N] "
-                     "[--stride S] [--flow-set s] [--mask-set s] [--pose-set s] [--no-delay] [--no-weight] [--no-resync] [--outlier-rejection --mesh file.obj]" << std::endl;
+                     "[--stride S] [--flow-set s] [--mask-set s] [--pose-set s] [--no-delay] [--no-weight] [--no-resync] [--outlier-rejection --mesh file.obj] [--mask-format pgm|png]" << std::endl;
         return 2;
     }
     try {
@@ -204,11 +205,11 @@ int main(int argc, char** argv) {
             TrackSources s;
             s.camera = std::make_shared<CameraMeasurement>(seq, cam, 0, 0);
             if (delay) {
-                s.segmentation = std::make_shared<DatasetImageSegmentationDelayed>(float(fps), float(desired_fps), true, seq, "pgm", cam.width,
+                s.segmentation = std::make_shared<DatasetImageSegmentationDelayed>(float(fps), float(desired_fps), true, seq, mask_format, cam.width,
                                                                                    cam.height, mask_set, object, 0, 0);
                 s.pose = std::make_shared<DatasetTransformDelayed>(float(fps), float(desired_fps), true, seq + "/" + pose_set + "/poses.txt", 0, 0, 7);
             } else {
-                s.segmentation = std::make_shared<DatasetImageSegmentation>(seq, "pgm", cam.width, cam.height, mask_set, object, 0, 0);
+                s.segmentation = std::make_shared<DatasetImageSegmentation>(seq, mask_format, cam.width, cam.height, mask_set, object, 0, 0);
                 s.pose = std::make_shared<DatasetTransformDelayed>(float(fps), float(fps), false, seq + "/" + pose_set + "/poses.txt", 0, 0, 7);
             }
             s.flow = std::make_shared<DatasetImageOpticalFlow>(seq, flow_set, cam.width, cam.height, 0, 0);

@@ -326,11 +326,12 @@ def test_tracker_executable_with_outlier_rejection(hostlib, tmp_path):
     seq = sequence(cfg, 1, F, target_coverage=0.3, corrupt=False)
     seq.pose[6, 0, :3] += torch.tensor([0.0, 0.07, 0.06], dtype=seq.pose.dtype)
     root = str(tmp_path / "seq0")
-    dataset_io.write_sequence(root, seq, 0, fx=cfg.fx, fy=cfg.fy, cx=cfg.cx, cy=cfg.cy)
+    dataset_io.write_sequence(root, seq, 0, fx=cfg.fx, fy=cfg.fy, cx=cfg.cx, cy=cfg.cy, mask_format="png")  # masks as PNG, like Fast-YCB
     verts, faces = cuboid_mesh(seq.half[0].numpy())
     dataset_io.write_obj(str(tmp_path / "box.obj"), verts, faces)
     out = subprocess.run([os.path.join(HOST, "roft_b200_tracker"), "--sequence", root, "--log", str(tmp_path), "--stride", "4",
-                          "--desired-fps", "10", "--outlier-rejection", "--mesh", str(tmp_path / "box.obj")], capture_output=True, text=True)
+                          "--desired-fps", "10", "--outlier-rejection", "--mesh", str(tmp_path / "box.obj"), "--mask-format", "png"],
+                         capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     pose_log = np.loadtxt(tmp_path / "pose_estimate.txt")
     x0 = np.zeros(13)
@@ -349,5 +350,35 @@ def test_tracker_executable_with_outlier_rejection(hostlib, tmp_path):
     assert 1 in orc.or_selected and 0 in orc.or_selected, orc.or_selected
     # a missing mesh is an error, not a silent fallback
     bad = subprocess.run([os.path.join(HOST, "roft_b200_tracker"), "--sequence", root, "--log", str(tmp_path), "--outlier-rejection",
-                          "--mesh", str(tmp_path / "nope.obj")], capture_output=True, text=True)
+                          "--mesh", str(tmp_path / "nope.obj"), "--mask-format", "png"], capture_output=True, text=True)
     assert bad.returncode != 0 and "cannot open" in (bad.stdout + bad.stderr)
+
+
+def test_png_mask_reader_matches_opencv(hostlib, tmp_path):
+    """read_png_gray8 = cv::imread(IMREAD_UNCHANGED) + convertTo(CV_8UC1) (DatasetImageSegmentation.cpp:130-132) on 8- and
+    16-bit greyscale PNGs written by OpenCV at several compression levels (all five scanline filters occur)."""
+    import cv2
+    rng = np.random.default_rng(7)
+    hostlib.rofth_read_png.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_void_p]
+    cases = []
+    m = np.zeros((90, 160), np.uint8); m[20:70, 40:120] = 255; cases.append(m)                     # a Mask R-CNN style mask
+    cases.append(rng.integers(0, 256, (33, 47)).astype(np.uint8))                                   # noise, odd size
+    g = (np.add.outer(np.arange(64), np.arange(96)) * 2 % 256).astype(np.uint8); cases.append(g)   # gradient (sub / up / paeth filters)
+    cases.append((rng.integers(0, 600, (40, 50))).astype(np.uint16))                                # 16 bit: saturates to 255
+    for k, img in enumerate(cases):
+        for level in (0, 3, 9):
+            p = str(tmp_path / f"m{k}_{level}.png")
+            assert cv2.imwrite(p, img, [cv2.IMWRITE_PNG_COMPRESSION, level])
+            exp = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+            exp = np.clip(exp, 0, 255).astype(np.uint8)
+            out = np.zeros(img.size, np.uint8)
+            c = ctypes.c_ulonglong(0); r = ctypes.c_ulonglong(0)
+            assert hostlib.rofth_read_png(p.encode(), out.ctypes.data, out.size, ctypes.byref(c), ctypes.byref(r)) == 0
+            assert (r.value, c.value) == img.shape and np.array_equal(out.reshape(img.shape), exp)
+    # colour PNGs / garbage are refused, not misread
+    p = str(tmp_path / "rgb.png")
+    cv2.imwrite(p, rng.integers(0, 256, (8, 8, 3)).astype(np.uint8))
+    out = np.zeros(64 * 3, np.uint8); c = ctypes.c_ulonglong(0); r = ctypes.c_ulonglong(0)
+    assert hostlib.rofth_read_png(p.encode(), out.ctypes.data, out.size, ctypes.byref(c), ctypes.byref(r)) == -1
+    (tmp_path / "bad.png").write_bytes(b"not a png at all")
+    assert hostlib.rofth_read_png(str(tmp_path / "bad.png").encode(), out.ctypes.data, out.size, ctypes.byref(c), ctypes.byref(r)) == -1
