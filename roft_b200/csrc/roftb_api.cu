@@ -357,6 +357,11 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
         // velocity kernel: shared-memory / cluster attributes are per device; one scratch slot per cluster that can
         // be resident at once
         int max_clusters = 0;
+        if (ukf_prepare_device()) {
+            g_create_error = "cannot configure the UKF kernel";
+            roftb_destroy(ctx);
+            return -1;
+        }
         if (velocity_prepare_device(ctx->g, ctx->n_units, &max_clusters)) {
             g_create_error = std::string("velocity kernel set-up failed: ") + cudaGetErrorString(cudaGetLastError());
             roftb_destroy(ctx);

@@ -237,6 +237,7 @@ struct UkfArgs {
     int32_t* resume; double* cand_mean; double* cand_cov;
 };
 int launch_ukf(const UkfArgs& a, cudaStream_t s);
+int ukf_prepare_device();
 
 // depth rasteriser (render.cu): n_items poses of ONE mesh -> n_items tiles of w x h pixels
 struct RenderArgs {

@@ -464,20 +464,19 @@ __device__ __noinline__ void ukf_correct_warp(UkfSmem& s, const UkfParams& p, in
     __syncwarp();
 }
 
-// One track (one warp) per block: 27 KB of shared memory and 32 threads, to be resident BESIDE the two CTAs per SM of
+// One warp per track, 27 KB of shared memory per track, to be resident BESIDE the two CTAs per SM of
 // the velocity kernel so that the latency-bound pose filter runs in the issue slots the streaming kernel leaves idle
 // instead of after it.  What decides that is the register file of an SM SUB-PARTITION (16384 registers): two velocity
 // CTAs put four warps of R registers x 32 lanes there, and a pose warp of U x 32 fits beside them only if
 // 4 * 32 R + 32 U <= 16384.  Left to itself ptxas gives this kernel 164 registers; next to it the second velocity CTA
 // of every SM it touches cannot start (measured: 33 instead of 71 clusters in flight while a pose kernel runs, and a
 // re-sync replay of ~1 ms halves the occupancy of a whole step).  Capped at 128 (no spills) it pairs with R = 96.
-constexpr int kUkfWarps = 1;
 struct UkfWarpSmem { UkfSmem s; double meas[16]; };
 
-template <int REGS>
+template <int REGS, int WARPS>
 __global__ void __maxnreg__(REGS) k_ukf_batch(UkfArgs a) {
     extern __shared__ __align__(16) unsigned char ukf_smem_raw[];
-    const int t = blockIdx.x * kUkfWarps + (threadIdx.x >> 5);
+    const int t = blockIdx.x * WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= a.n_tracks) return;
     const int nops = a.n_ops[t];
@@ -571,19 +570,47 @@ __global__ void __maxnreg__(REGS) k_ukf_batch(UkfArgs a) {
 
 }  // namespace
 
+// Tracks (warps) per CTA.  While a pose warp is resident in an SM sub-partition the second velocity CTA of that SM cannot
+// start (see above), so the question is how many SMs the pose kernel touches: one track per CTA spreads 256 tracks over
+// all 148 SMs, four per CTA (one warp per sub-partition, 108 KB of shared memory) over 64.  Measured on B200 at 256
+// tracks: 53 instead of 33 velocity clusters in flight while the previous step's pose kernel runs, 1.093 instead of
+// 1.117 ms per step.  (Eight per CTA would need 216 KB of shared memory and evict both velocity CTAs.)  ROFTB_UKF_WARPS=1|4.
+static int ukf_warps() {
+    static const int v = [] { const char* e = getenv("ROFTB_UKF_WARPS"); return (e && atoi(e) < 4) ? 1 : 4; }();
+    return v;
+}
+
 int launch_ukf(const UkfArgs& a, cudaStream_t s) {
-    const int smem = (int)sizeof(UkfWarpSmem) * kUkfWarps;  // (below the 48 KB that need no opt-in)
-    static_assert(sizeof(UkfWarpSmem) * kUkfWarps <= 48 * 1024, "k_ukf_batch would need the shared-memory opt-in per device");
     static const int regs = [] { const char* e = getenv("ROFTB_UKF_REGS"); return e ? atoi(e) : 128; }();
-    const int grid = (a.n_tracks + kUkfWarps - 1) / kUkfWarps;
-    if (regs >= 168)
-        ROFTB_LAUNCH(k_ukf_batch<168>, grid, 32 * kUkfWarps, smem, s, a);
-    else if (regs >= 128)
-        ROFTB_LAUNCH(k_ukf_batch<128>, grid, 32 * kUkfWarps, smem, s, a);
-    else
-        ROFTB_LAUNCH(k_ukf_batch<96>, grid, 32 * kUkfWarps, smem, s, a);
+    const int w = ukf_warps();
+    const int smem = (int)sizeof(UkfWarpSmem) * w;
+    const int grid = (a.n_tracks + w - 1) / w;
+    if (w == 4) {
+        if (regs >= 168)
+            ROFTB_LAUNCH((k_ukf_batch<168, 4>), grid, 128, smem, s, a);
+        else if (regs >= 128)
+            ROFTB_LAUNCH((k_ukf_batch<128, 4>), grid, 128, smem, s, a);
+        else
+            ROFTB_LAUNCH((k_ukf_batch<96, 4>), grid, 128, smem, s, a);
+    } else {
+        if (regs >= 168)
+            ROFTB_LAUNCH((k_ukf_batch<168, 1>), grid, 32, smem, s, a);
+        else if (regs >= 128)
+            ROFTB_LAUNCH((k_ukf_batch<128, 1>), grid, 32, smem, s, a);
+        else
+            ROFTB_LAUNCH((k_ukf_batch<96, 1>), grid, 32, smem, s, a);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
+// per device (called from roftb_create after cudaSetDevice): the four-track CTAs need the shared-memory opt-in
+int ukf_prepare_device() {
+    static_assert(sizeof(UkfWarpSmem) <= 48 * 1024, "one track per CTA must fit the default shared-memory limit");
+    const int bytes = (int)sizeof(UkfWarpSmem) * 4;
+    cudaError_t e = cudaFuncSetAttribute(k_ukf_batch<168, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ukf_batch<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ukf_batch<96, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return e == cudaSuccess ? 0 : -1;
+}
 
 }  // namespace roftb
