@@ -80,6 +80,7 @@ struct roftb_ctx {
         bool stage_done_used[3] = {false, false, false}, unstage_done_used = false;
         cudaStream_t stream = nullptr;      // snapshot copies
     } orj;
+    double* ukf_warm = nullptr;                      // [T][2][145] warm start of the UKF's Jacobi decompositions
     float* mesh_vertices = nullptr;                  // outlier-rejection mesh (roftb_set_mesh): device [n][3]
     int32_t* mesh_faces = nullptr;
     int mesh_nv = 0, mesh_nf = 0;
@@ -407,6 +408,7 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     CKC(dalloc(&ctx->p_cov, (size_t)T * 144));
     CKC(dalloc(&ctx->pb_mean, (size_t)T * 13));
     CKC(dalloc(&ctx->pb_cov, (size_t)T * 144));
+    CKC(dalloc(&ctx->ukf_warm, (size_t)T * 290));
     CKC(dalloc(&ctx->vel_hist, (size_t)T * kHistRing * 6));
     if (cfg->outlier_rejection) {
         auto& oj = ctx->orj;
@@ -496,7 +498,7 @@ void roftb_destroy(roftb_ctx* ctx) {
     void* dptrs[] = {ctx->mask_state[0], ctx->mask_state[1], ctx->mask_state[2], ctx->mask_occ[0], ctx->mask_occ[1], ctx->mask_occ[2],
                      ctx->winner, ctx->scratch.nu, ctx->scratch.dp, ctx->scratch.r, ctx->scratch.hist, ctx->scratch.chunk_cnt,
                      ctx->scratch.part, ctx->scratch.track_sel, ctx->scratch.sel_part, ctx->scratch.slot_bitmap, ctx->scratch.track_slot, ctx->scratch.chunk_aux,
-                     ctx->wl_units, ctx->wl_pixels, ctx->phase_clock, ctx->span_clock, ctx->mesh_vertices, ctx->mesh_faces, ctx->mesh_scale, ctx->vel_order, ctx->vel_ticket, ctx->order_units,
+                     ctx->wl_units, ctx->wl_pixels, ctx->phase_clock, ctx->span_clock, ctx->mesh_vertices, ctx->mesh_faces, ctx->mesh_scale, ctx->ukf_warm, ctx->vel_order, ctx->vel_ticket, ctx->order_units,
                      ctx->wt_count2, ctx->wt_list, ctx->wt_n, ctx->nl_count, ctx->nl_list, ctx->nl_n, ctx->stat, ctx->plan, ctx->fbuf, ctx->v_mean,
                      ctx->v_cov, ctx->p_mean, ctx->p_cov, ctx->pb_mean, ctx->pb_cov, ctx->vel_hist, ctx->q_diag,
                      ctx->d_count, ctx->d_lambda, ctx->d_eta, ctx->d_wctl, ctx->d_vctl, ctx->d_ops, ctx->d_nops,
@@ -731,6 +733,7 @@ int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mea
     CK(cudaMemcpy(ctx->v_mean, vm.data(), vm.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->v_cov, vc.data(), vc.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMemset(ctx->vel_hist, 0, sizeof(double) * T * kHistRing * 6));
+    CK(cudaMemset(ctx->ukf_warm, 0, sizeof(double) * T * 290));  // use counters 0: the first decompositions start cold
     CK(cudaMemset(ctx->mask_state[0], 0, (size_t)T * ctx->HW));
     CK(cudaMemset(ctx->mask_state[1], 0, (size_t)T * ctx->HW));
     CK(cudaMemset(ctx->mask_state[2], 0, (size_t)T * ctx->HW));
@@ -1166,6 +1169,8 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
         a.mean = ctx->p_mean; a.cov = ctx->p_cov; a.buf_mean = ctx->pb_mean; a.buf_cov = ctx->pb_cov;
         a.vel_hist = ctx->vel_hist; a.hist_ring = kHistRing;
         a.span_clock = span ? span + 8 : nullptr;
+        static const bool warm_on = [] { const char* e = getenv("ROFTB_UKF_WARM"); return !e || atoi(e) != 0; }();
+        a.warm = warm_on ? ctx->ukf_warm : nullptr;
         auto& oj = ctx->orj;
         if (cfg.outlier_rejection) {
             a.resume = oj.resume; a.cand_mean = oj.cand_mean; a.cand_cov = oj.cand_cov;

@@ -235,6 +235,7 @@ struct UkfArgs {
     unsigned long long* span_clock;                         // diagnostics (may be null): [first start, last end]
     // outlier rejection (all null when off): per-track op index to start from (-1: nothing left), candidates [T][2][13|144]
     int32_t* resume; double* cand_mean; double* cand_cov;
+    double* warm;   // [T][2][145] eigenvectors of the last covariance square roots (+ use counter), may be null: cold Jacobi
 };
 int launch_ukf(const UkfArgs& a, cudaStream_t s);
 int ukf_prepare_device();

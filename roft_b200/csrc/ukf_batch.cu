@@ -84,8 +84,9 @@ __device__ __forceinline__ void quat_diff(const double* a, const double* b, doub
 // round-robin ("chess tournament") ordering: the n/2 index pairs of one round are disjoint, so their rotations
 // commute and are applied together - 11 dependent rounds per sweep for n = 12 instead of 66 dependent rotations.
 // Same per-pair rotation rule and relative threshold as the cyclic sweep; converged when a whole sweep rotates nothing.
-__device__ void jacobi_warp(UkfSmem& s, int n, int lane) {
-    for (int i = lane; i < 144; i += 32) s.V[i / 12][i % 12] = (i / 12 == i % 12) ? 1.0 : 0.0;
+__device__ void jacobi_warp(UkfSmem& s, int n, int lane, bool keep_v = false) {
+    if (!keep_v)
+        for (int i = lane; i < 144; i += 32) s.V[i / 12][i % 12] = (i / 12 == i % 12) ? 1.0 : 0.0;
     __syncwarp();
     const int ne = n + (n & 1);  // players (a dummy index n sits out when n is odd)
     const int np = ne >> 1;      // pairs per round
@@ -179,9 +180,46 @@ __device__ void jacobi_warp(UkfSmem& s, int n, int lane) {
     }
 }
 
-// out = sc * U sqrt(max(S,0)) for the n x n matrix currently in s.A
-__device__ void cov_sqrt_warp(UkfSmem& s, int n, double sc, double (*out)[12], int lane) {
-    jacobi_warp(s, n, lane);
+// out = sc * U sqrt(max(S,0)) for the n x n matrix currently in s.A.
+// `warm` (12 x 12 matrices only; may be null): eigenvectors found for this track's previous matrix of the same kind
+// (posterior before a prediction / prior before a correction).  Consecutive covariances are close, so B = W^T A W is
+// nearly diagonal and the sweeps that a cold start spends on the bulk of the off-diagonal mass are skipped; the
+// decomposition reached is the same up to rounding (and up to the basis of a degenerate eigenspace, which the unscented
+// transform does not see to second order).  Every 64th use starts cold again so that the accumulated product of
+// rotations cannot drift away from orthogonality.  warm[144] = counter.
+__device__ void cov_sqrt_warp(UkfSmem& s, int n, double sc, double (*out)[12], int lane, double* warm = nullptr) {
+    bool keep = false;
+    if (warm && n == 12) {
+        const int uses = (int)warm[144];
+        keep = uses > 0 && (uses & 63) != 0;
+        if (keep) {
+            for (int i = lane; i < 144; i += 32) s.V[i / 12][i % 12] = warm[i];
+            __syncwarp();
+            for (int i = lane; i < 144; i += 32) {  // K = A W
+                const int r = i / 12, c = i % 12;
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) v = fma(s.A[r][k], s.V[k][c], v);
+                s.K[r][c] = v;
+            }
+            __syncwarp();
+            for (int i = lane; i < 78; i += 32) {  // A <- W^T K, upper triangle mirrored (exactly symmetric)
+                int r = 0, c = i;
+                while (c >= 12 - r) { c -= 12 - r; ++r; }
+                c += r;
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) v = fma(s.V[k][r], s.K[k][c], v);
+                s.A[r][c] = v;
+                s.A[c][r] = v;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) warm[144] = (double)(uses + 1);
+    }
+    jacobi_warp(s, n, lane, keep);
+    if (warm && n == 12)
+        for (int i = lane; i < 144; i += 32) warm[i] = s.V[i / 12][i % 12];
     for (int i = lane; i < n * n; i += 32) {
         const int r = i / n, c = i % n;
         out[r][c] = sc * s.V[r][c] * sqrt(fmax(s.A[c][c], 0.0));
@@ -249,13 +287,13 @@ __device__ __forceinline__ void make_sigma_point(const UkfSmem& s, int i, int n,
 }
 
 // ---- predict ----------------------------------------------------------------------------------
-__device__ __noinline__ void ukf_predict_warp(UkfSmem& s, const UkfParams& p, double T, int lane) {
+__device__ __noinline__ void ukf_predict_warp(UkfSmem& s, const UkfParams& p, double T, int lane, double* warm = nullptr) {
     const int k = 9, n = 21, npts = 43;
     const UtW w = ut_weights(n, p);
     const double sc = sqrt(w.c);
     for (int i = lane; i < 144; i += 32) s.A[i / 12][i % 12] = s.P[i / 12][i % 12];
     __syncwarp();
-    cov_sqrt_warp(s, 12, sc, s.AP, lane);
+    cov_sqrt_warp(s, 12, sc, s.AP, lane, warm);
     // Q(T), CartesianQuaternionModel.cpp:127-141
     for (int i = lane; i < 144; i += 32) s.A[i / 12][i % 12] = 0.0;
     __syncwarp();
@@ -312,7 +350,7 @@ __device__ __noinline__ void ukf_predict_warp(UkfSmem& s, const UkfParams& p, do
 }
 
 // ---- correct ----------------------------------------------------------------------------------
-__device__ __noinline__ void ukf_correct_warp(UkfSmem& s, const UkfParams& p, int mtype, const double* meas, int lane) {
+__device__ __noinline__ void ukf_correct_warp(UkfSmem& s, const UkfParams& p, int mtype, const double* meas, int lane, double* warm = nullptr) {
     if (mtype == ROFTB_MEAS_NONE) return;
     const bool has_v = (mtype == ROFTB_MEAS_VELOCITY || mtype == ROFTB_MEAS_POSE_VELOCITY);
     const bool has_p = (mtype == ROFTB_MEAS_POSE || mtype == ROFTB_MEAS_POSE_VELOCITY);
@@ -323,7 +361,7 @@ __device__ __noinline__ void ukf_correct_warp(UkfSmem& s, const UkfParams& p, in
     const double sc = sqrt(w.c);
     for (int i = lane; i < 144; i += 32) s.A[i / 12][i % 12] = s.P[i / 12][i % 12];
     __syncwarp();
-    cov_sqrt_warp(s, 12, sc, s.AP, lane);
+    cov_sqrt_warp(s, 12, sc, s.AP, lane, warm);
     // R = blkdiag(R_velocity, R_pose) (CartesianQuaternionMeasurement.cpp:49-61)
     for (int i = lane; i < 144; i += 32) s.A[i / 12][i % 12] = 0.0;
     __syncwarp();
@@ -487,6 +525,7 @@ __global__ void __maxnreg__(REGS) k_ukf_batch(UkfArgs a) {
     double* meas = wsm.meas;
     double* gm = a.mean + (long long)t * 13;
     double* gc = a.cov + (long long)t * 144;
+    double* wv = a.warm ? a.warm + (long long)t * 290 : nullptr;  // [2][144 eigenvectors + use counter]
     const int o_first = a.resume ? a.resume[t] : 0;
     if (o_first < 0 || o_first >= nops) {  // (second launch of a step: this track had no render-and-compare test)
         if (a.resume && lane == 0) a.resume[t] = -1;
@@ -500,7 +539,7 @@ __global__ void __maxnreg__(REGS) k_ukf_batch(UkfArgs a) {
         const UkfOp* op = a.ops + (long long)t * a.max_ops + o;
         const int kind = op->kind;
         if (kind == kOpPredict) {
-            ukf_predict_warp(s, a.p, op->dt, lane);
+            ukf_predict_warp(s, a.p, op->dt, lane, wv);
         } else if (kind == kOpCorrect) {
             if (lane < 13) {
                 double v = op->meas[lane];
@@ -509,7 +548,7 @@ __global__ void __maxnreg__(REGS) k_ukf_batch(UkfArgs a) {
                 meas[lane] = v;
             }
             __syncwarp();
-            ukf_correct_warp(s, a.p, op->meas_type, meas, lane);
+            ukf_correct_warp(s, a.p, op->meas_type, meas, lane, wv ? wv + 145 : nullptr);
         } else if (kind == kOpCorrectBoth && a.cand_mean) {
             if (lane < 13) {
                 double v = op->meas[lane];
@@ -525,7 +564,7 @@ __global__ void __maxnreg__(REGS) k_ukf_batch(UkfArgs a) {
             if (lane < 13) cm[13 + lane] = s.mean[lane];
             for (int i = lane; i < 144; i += 32) cc[144 + i] = s.P[i / 12][i % 12];
             __syncwarp();
-            ukf_correct_warp(s, a.p, ROFTB_MEAS_POSE_VELOCITY, meas, lane);
+            ukf_correct_warp(s, a.p, ROFTB_MEAS_POSE_VELOCITY, meas, lane, wv ? wv + 145 : nullptr);
             if (lane < 13) {
                 cm[lane] = s.mean[lane];
                 s.mean[lane] = cm[13 + lane];
@@ -535,7 +574,7 @@ __global__ void __maxnreg__(REGS) k_ukf_batch(UkfArgs a) {
                 s.P[i / 12][i % 12] = cc[144 + i];
             }
             __syncwarp();
-            ukf_correct_warp(s, a.p, ROFTB_MEAS_VELOCITY, meas, lane);
+            ukf_correct_warp(s, a.p, ROFTB_MEAS_VELOCITY, meas, lane, wv ? wv + 145 : nullptr);
             if (lane < 13) cm[13 + lane] = s.mean[lane];
             for (int i = lane; i < 144; i += 32) cc[144 + i] = s.P[i / 12][i % 12];
             __syncwarp();
