@@ -55,11 +55,20 @@ struct FineGrainedFilter {
     Gaussian v_pred_belief_{6}, v_corr_belief_{6};
     double sample_time_, last_camera_stamp_ = -1;
     bool pose_resync_;
+    // ROFTFilter.h: outlier rejection members
+    bool outlier_rejection_ = false, outlier_rejection_features_initialized_ = false;
+    double outlier_rejection_gain_ = 1.0;
+    int divider_ = 4;
+    DepthImage buffered_depth_;
+    MaskImage buffered_segmentation_;
+    std::shared_ptr<B200Context> ctx_;
+    std::vector<int> selected_;  // diagnostics: choices of pick_best_alternative
 
     FineGrainedFilter(const Sources& s, const CameraParameters& cam, std::shared_ptr<B200Context> ctx, const double* x0, double sample_time,
                       bool pose_resync, double stride, double max_depth, bool weighting)
-        : sample_time_(sample_time), pose_resync_(pose_resync) {
+        : sample_time_(sample_time), pose_resync_(pose_resync), ctx_(ctx) {
         camera_ = s.camera;
+        divider_ = cam.width == 640 ? 2 : 4;  // ROFTFilter.cpp:191-193
         // ROFTFilter.cpp:118-128: the segmentation source is wrapped in the flow-aided one
         auto of_aided = std::make_shared<ImageSegmentationOFAidedSource<T>>(s.segmentation, s.flow, cam, false, ctx);
         segmentation_ = std::make_shared<ImageSegmentationMeasurement>(of_aided);
@@ -106,6 +115,10 @@ struct FineGrainedFilter {
         double tw[6];
         for (int i = 0; i < 6; ++i) tw[i] = v_corr_belief_.mean()(i, 0);
         velocity_->set_twist(tw, tw + 3);                                                             // :305
+        if (outlier_rejection_ && pose_resync_ && !outlier_rejection_features_initialized_) {          // :313-321
+            if (!buffer_outlier_rejection_features()) throw std::runtime_error("cannot initialize the outlier rejection features");
+            outlier_rejection_features_initialized_ = true;
+        }
         p_prediction_->predict(p_corr_belief_, p_pred_belief_);                                       // :325
         using MM = CartesianQuaternionMeasurement::MeasurementMode;
         if (p_correction_->getMeasurementModel().freeze(MM::Standard)) {                              // :327
@@ -116,10 +129,17 @@ struct FineGrainedFilter {
                     p_corr_belief_ = buffered_belief_copy;
                     while (p_correction_->getMeasurementModel().freeze(MM::PopBufferedMeasurement)) {
                         p_prediction_->predict(p_corr_belief_, p_pred_belief_);
-                        p_correction_->correct(p_pred_belief_, p_corr_belief_);
+                        if (outlier_rejection_ && p_correction_->getMeasurementModel().getMeasurementDescription().total_size() == 13)
+                            p_corr_belief_ = correct_outlier_rejection(p_pred_belief_, true);           // :346-347
+                        else
+                            p_correction_->correct(p_pred_belief_, p_corr_belief_);
                     }
+                    if (outlier_rejection_) buffer_outlier_rejection_features();                       // :352-353
                 } else {
-                    p_correction_->correct(p_pred_belief_, p_corr_belief_);                           // :360
+                    if (outlier_rejection_)
+                        p_corr_belief_ = correct_outlier_rejection(p_pred_belief_, false);              // :357-358
+                    else
+                        p_correction_->correct(p_pred_belief_, p_corr_belief_);                       // :360
                 }
             } else {
                 p_correction_->correct(p_pred_belief_, p_corr_belief_);                               // :364
@@ -129,11 +149,59 @@ struct FineGrainedFilter {
         }
         return true;
     }
+
+    // ROFTFilter.cpp:624-646
+    bool buffer_outlier_rejection_features() {
+        const auto d = camera_->measure();
+        if (!d.first) return false;
+        buffered_depth_ = *d.second;
+        const auto m = segmentation_->measure();
+        if (!m.first) return false;
+        buffered_segmentation_ = bfl::any::any_cast<std::pair<bool, MaskImage>>(m.second).second;
+        return true;
+    }
+
+    // ROFTFilter.cpp:467-621: SICAD render of both alternatives + masked depth L1 + choice, through the C ABI
+    std::pair<bool, Gaussian> pick_best_alternative(const std::vector<Gaussian>& alternatives, bool use_buffered_features) {
+        DepthImage depth;
+        MaskImage segmentation;
+        if (use_buffered_features) {
+            depth = buffered_depth_;
+            segmentation = buffered_segmentation_;
+        } else {
+            const auto d = camera_->measure();
+            if (!d.first) return {false, Gaussian()};
+            depth = *d.second;
+            const auto m = segmentation_->measure();
+            if (!m.first) return {false, Gaussian()};
+            segmentation = bfl::any::any_cast<std::pair<bool, MaskImage>>(m.second).second;
+        }
+        double alts[26];
+        for (int k = 0; k < 2; ++k)
+            for (int i = 0; i < 13; ++i) alts[13 * k + i] = alternatives[k].mean()(i, 0);
+        std::int32_t selected = 0;
+        double lik[2];
+        if (roftb_pick_best_alternative(ctx_->get(), 1, segmentation.data.data(), depth.data.data(), alts, divider_, outlier_rejection_gain_,
+                                        &selected, lik) != 0)
+            return {false, Gaussian()};
+        selected_.push_back(selected);
+        return {true, alternatives[selected]};
+    }
+
+    // ROFTFilter.cpp:649-676
+    Gaussian correct_outlier_rejection(const Gaussian& prediction, bool use_buffered_features) {
+        Gaussian corr_belief_v = prediction, corr_belief_p_v = prediction;
+        p_correction_->correct(prediction, corr_belief_p_v);
+        p_correction_->getMeasurementModel().freeze(CartesianQuaternionMeasurement::MeasurementMode::RepeatOnlyVelocity);
+        p_correction_->correct(prediction, corr_belief_v);
+        const auto best = pick_best_alternative({corr_belief_p_v, corr_belief_v}, use_buffered_features);
+        return best.first ? best.second : corr_belief_p_v;
+    }
 };
 
 template <class T>
 static int run(const std::string& seq, const CameraParameters& cam, int flow_type, std::size_t grid, float scale, int frames, double stride,
-               double fps, double desired_fps, bool resync) {
+               double fps, double desired_fps, bool resync, const std::string& mesh_path) {
     const double cov_flow[2] = {1.0, 1.0};
     const double p_model[6] = {1, 1, 1, 1, 1, 1};
     const double p_meas[12] = {0.1, 0.1, 0.1, 1e-4, 1e-4, 1e-4, 1e-3, 1e-3, 1e-3, 1e-4, 1e-4, 1e-4};
@@ -146,6 +214,14 @@ static int run(const std::string& seq, const CameraParameters& cam, int flow_typ
     if (init.freeze(false)) std::copy(init.transform(), init.transform() + 7, x0.begin() + 6);
 
     FineGrainedFilter<T> fine(make_sources(seq, cam, fps, desired_fps), cam, ctx, x0.data(), 0.033333333333, resync, stride, 2.0, true);
+    const bool outrej = !mesh_path.empty();
+    if (outrej) {  // the fine-grained loop renders through the operators of the same library
+        std::vector<float> mv;
+        std::vector<std::int32_t> mf;
+        read_obj_mesh(mesh_path, mv, mf);
+        if (roftb_set_mesh(ctx->get(), mv.data(), int(mv.size() / 3), mf.data(), int(mf.size() / 3)) != 0) throw std::runtime_error(roftb_last_error(ctx->get()));
+        fine.outlier_rejection_ = true;
+    }
 
     Sources s2 = make_sources(seq, cam, fps, desired_fps);
     TrackSources ts;
@@ -156,7 +232,7 @@ static int run(const std::string& seq, const CameraParameters& cam, int flow_typ
     tracks.push_back(std::move(ts));
     const std::vector<double> p_cov0(12, 1e-3), v_cov0(6, 1e-3), v_q(6, 0.1), v_r{1.0, 1.0};
     ROFTFilter fused(std::move(tracks), p_cov0, std::vector<double>(p_model, p_model + 6), std::vector<double>(p_meas, p_meas + 12), v_cov0, v_q, v_r,
-                     1.0, 2.0, 0.0, 0.033333333333, true, resync, true, true, true, 2.0, stride, false, ".", "");
+                     1.0, 2.0, 0.0, 0.033333333333, true, resync, true, true, true, 2.0, stride, false, ".", "", 0, outrej, true, mesh_path);
     fused.initialization_step();
 
     double worst = 0.0;
@@ -184,6 +260,11 @@ static int run(const std::string& seq, const CameraParameters& cam, int flow_typ
     }
     std::cout << "adapter_check: " << k << " frames, reference call sequence over the adapters == fused batched step, max rel diff " << worst
               << std::endl;
+    if (outrej) {
+        std::cout << "outlier rejection choices:";
+        for (int c : fine.selected_) std::cout << ' ' << c;
+        std::cout << std::endl;
+    }
     return 0;
 }
 
@@ -192,6 +273,7 @@ int main(int argc, char** argv) {
     int frames = -1;
     double stride = 35.0, fps = 30.0, desired_fps = 5.0;
     bool resync = true;
+    std::string mesh_path;  // non-empty: outlier rejection on, in both loops
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         auto next = [&]() -> std::string { return i + 1 < argc ? argv[++i] : std::string(); };
@@ -200,6 +282,7 @@ int main(int argc, char** argv) {
         else if (a == "--stride") stride = std::atof(next().c_str());
         else if (a == "--desired-fps") desired_fps = std::atof(next().c_str());
         else if (a == "--no-resync") resync = false;
+        else if (a == "--mesh") mesh_path = next();
         else { std::cerr << "unknown option " << a << std::endl; return 2; }
     }
     if (seq.empty()) { std::cerr << "usage: adapter_check --sequence <dir> [--frames N] [--stride S] [--desired-fps F] [--no-resync]" << std::endl; return 2; }
@@ -217,8 +300,8 @@ int main(int argc, char** argv) {
         // ROFTFilter.cpp:122-149: the flow element type decides the template argument
         DatasetImageOpticalFlow probe(seq, "nvof", cam.width, cam.height, 0, 0);
         if (probe.get_matrix_type() == ROFTB_FLOW_S16)
-            return run<cv::Vec2s>(seq, cam, ROFTB_FLOW_S16, probe.get_grid_size(), probe.get_scaling_factor(), frames, stride, fps, desired_fps, resync);
-        return run<cv::Vec2f>(seq, cam, ROFTB_FLOW_F32, probe.get_grid_size(), probe.get_scaling_factor(), frames, stride, fps, desired_fps, resync);
+            return run<cv::Vec2s>(seq, cam, ROFTB_FLOW_S16, probe.get_grid_size(), probe.get_scaling_factor(), frames, stride, fps, desired_fps, resync, mesh_path);
+        return run<cv::Vec2f>(seq, cam, ROFTB_FLOW_F32, probe.get_grid_size(), probe.get_scaling_factor(), frames, stride, fps, desired_fps, resync, mesh_path);
     } catch (const std::exception& e) {
         std::cerr << e.what() << std::endl;
         return 1;

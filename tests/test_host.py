@@ -382,3 +382,29 @@ def test_png_mask_reader_matches_opencv(hostlib, tmp_path):
     assert hostlib.rofth_read_png(p.encode(), out.ctypes.data, out.size, ctypes.byref(c), ctypes.byref(r)) == -1
     (tmp_path / "bad.png").write_bytes(b"not a png at all")
     assert hostlib.rofth_read_png(str(tmp_path / "bad.png").encode(), out.ctypes.data, out.size, ctypes.byref(c), ctypes.byref(r)) == -1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resync", [True, False])
+def test_reference_call_sequence_with_outlier_rejection(hostlib, tmp_path, resync):
+    """adapter_check --mesh: ROFTFilter::filtering_step INCLUDING correct_outlier_rejection / pick_best_alternative /
+    buffer_outlier_rejection_features (ROFTFilter.cpp:313-359, 467-676) transcribed over the adapter classes and the
+    render / pick-best operators, against the fused device-side path of roftb_filter_step (cfg.outlier_rejection)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from roft_b200.synthetic import cuboid_mesh
+    cfg = small_cfg(subsampling_radius=4.0, segm_delay=3, pose_delay=3, sample_time=1.0 / 30.0)
+    F = 20
+    seq = sequence(cfg, 1, F, corrupt=False)
+    seq.pose[6, 0, :3] += torch.tensor([0.0, 0.07, 0.06], dtype=seq.pose.dtype)
+    seq.pose[12, 0, :3] += torch.tensor([0.09, 0.0, 0.0], dtype=seq.pose.dtype)
+    root = str(tmp_path / "seq0")
+    dataset_io.write_sequence(root, seq, 0, fx=cfg.fx, fy=cfg.fy, cx=cfg.cx, cy=cfg.cy)
+    dataset_io.write_obj(str(tmp_path / "box.obj"), *cuboid_mesh(seq.half[0].numpy()))
+    args = [os.path.join(HOST, "adapter_check"), "--sequence", root, "--stride", "4", "--desired-fps", "10", "--mesh", str(tmp_path / "box.obj")]
+    out = subprocess.run(args + ([] if resync else ["--no-resync"]), capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert f"adapter_check: {F} frames" in out.stdout, out.stdout
+    choices = out.stdout.split("outlier rejection choices:")[1].split()
+    assert "0" in choices and "1" in choices, out.stdout
