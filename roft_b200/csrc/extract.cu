@@ -185,6 +185,107 @@ __global__ void __launch_bounds__(kThreads) k_extract(ExtractArgs a) {
     }
 }
 
+// ---- buffered features of the render-and-compare pose test, compacted -------------------------------------------
+// ROFTFilter::pick_best_alternative only ever looks at every second non-zero pixel of the (buffered) segmentation, in
+// findNonZero order, and at the depth under it (ROFTFilter.cpp:556-566).  Instead of keeping copies of both planes
+// (5 bytes per pixel of the frame), the features of a track are that list itself: entry k = (linear pixel index, depth
+// bits) of coordinate 2k, depth bits 0 when the depth gate 0 < d < 2 fails (a valid depth is never 0).  ~0.9 MB per
+// track at 25 % coverage instead of 4.6 MB, and the L1 of both rendered alternatives is one pass over it.
+__global__ void __launch_bounds__(kThreads) k_or_features(Geom g, const UkfOp* __restrict__ ops, int max_ops, int bits,
+                                                          const uint8_t* __restrict__ mask, long long mask_stride, int thr,
+                                                          const float* __restrict__ depth, long long depth_stride,
+                                                          const int32_t* __restrict__ rank_prefix, const int32_t* __restrict__ total,
+                                                          int n_warp_tiles, uint2* __restrict__ feat, long long feat_stride,
+                                                          int32_t* __restrict__ n_feat) {
+    const int t = blockIdx.y;
+    if ((ops[(long long)t * max_ops].pad & bits) == 0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) n_feat[t] = (total[t] + 1) >> 1;
+    const uint32_t thr4 = (uint32_t)thr * 0x01010101u;
+    const uint32_t* mq = reinterpret_cast<const uint32_t*>(mask + (long long)t * mask_stride);
+    const float* dp = depth + (long long)t * depth_stride;
+    uint2* out = feat + (long long)t * feat_stride;
+    const int nq = g.HW >> 2;
+    for (int wt = blockIdx.x * (kThreads / 32) + warp; wt < n_warp_tiles; wt += gridDim.x * (kThreads / 32)) {
+        int r = rank_prefix[(long long)t * n_warp_tiles + wt];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = wt * 128 + j * 32 + lane;
+            const uint32_t sel = q < nq ? __vcmpgtu4(__ldg(mq + q), thr4) : 0u;
+            const int cnt = __popc(sel) >> 3;
+            const int incl = warp_scan_incl(cnt, lane);
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            int rank = r + incl - cnt;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (!((sel >> (8 * i)) & 1u)) continue;
+                if ((rank & 1) == 0) {
+                    const int px = (q << 2) + i;
+                    const float d = __ldg(dp + px);
+                    const bool ok = d > 0.f && (double)d < 2.0;
+                    out[rank >> 1] = make_uint2((uint32_t)px, ok ? __float_as_uint(d) : 0u);
+                }
+                ++rank;
+            }
+            r += tot;
+        }
+    }
+}
+
+// stage -> snapshot of the flagged tracks
+__global__ void __launch_bounds__(kThreads) k_or_feat_copy(const UkfOp* __restrict__ ops, int max_ops, int bits,
+                                                           const uint2* __restrict__ src, const int32_t* __restrict__ n_src,
+                                                           uint2* __restrict__ dst, int32_t* __restrict__ n_dst, long long stride) {
+    const int t = blockIdx.y;
+    if ((ops[(long long)t * max_ops].pad & bits) == 0) return;
+    const int n = n_src[t];
+    if (blockIdx.x == 0 && threadIdx.x == 0) n_dst[t] = n;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + (long long)t * stride);
+    uint4* d4 = reinterpret_cast<uint4*>(dst + (long long)t * stride);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n + 1) / 2; i += gridDim.x * blockDim.x) d4[i] = s4[i];
+}
+
+// masked depth L1 of BOTH rendered alternatives over the feature list of every track with a pending test: one block per
+// track, fixed reduction order (deterministic).  err / samples laid out [alternative][track].
+__global__ void __launch_bounds__(1024) k_or_l1(int n_tracks, const int32_t* __restrict__ resume, const uint2* __restrict__ feat,
+                                                const int32_t* __restrict__ n_feat, long long feat_stride,
+                                                const float* __restrict__ rendered, long long tile, int divider, int W,
+                                                double* __restrict__ err, int32_t* __restrict__ samples) {
+    const int t = blockIdx.x;
+    __shared__ double s_e[2][32];
+    __shared__ int s_n[2][32];
+    double e0 = 0.0, e1 = 0.0;
+    int n0 = 0, n1 = 0;
+    if (resume[t] > 0) {
+        const uint2* f = feat + (long long)t * feat_stride;
+        const float* ra = rendered + (long long)t * tile;
+        const float* rb = rendered + ((long long)n_tracks + t) * tile;
+        const int n = n_feat[t], wt = W / divider;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint2 en = f[i];
+            if (en.y == 0u) continue;
+            const float d = __uint_as_float(en.y);
+            const int v = (int)(en.x / (unsigned)W), u = (int)(en.x - (unsigned)v * (unsigned)W);
+            const long long ri = (long long)(v / divider) * wt + u / divider;
+            const float a = __ldg(ra + ri), b = __ldg(rb + ri);
+            if (a != 0.0f) { e0 += (double)fabsf(d - a); ++n0; }   // std::abs(float - float) accumulated in double
+            if (b != 0.0f) { e1 += (double)fabsf(d - b); ++n1; }
+        }
+    }
+    e0 = warp_sum(e0); e1 = warp_sum(e1);
+    n0 = warp_sum(n0); n1 = warp_sum(n1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_e[0][warp] = e0; s_e[1][warp] = e1; s_n[0][warp] = n0; s_n[1][warp] = n1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double e = 0.0;
+        int n = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { e += s_e[threadIdx.x][w]; n += s_n[threadIdx.x][w]; }
+        err[(long long)threadIdx.x * n_tracks + t] = e;
+        samples[(long long)threadIdx.x * n_tracks + t] = n;
+    }
+}
+
 ExtractArgs base_args(const SelectArgs& s) {
     ExtractArgs a;
     memset(&a, 0, sizeof(a));
@@ -239,6 +340,32 @@ int launch_masked_depth_l1(const SelectArgs& s, const float* rendered, long long
     if (launch_mask_rank(s.mask, s.mask_stride, s.thr, s.g.HW, s.n_items, s.wt_count, nullptr, nullptr, st)) return -1;
     const int bx = max(1, min(a.n_warp_tiles / (kThreads / 32), 148 * 4));
     ROFTB_LAUNCH((k_extract<kModeL1, 0>), dim3(bx, s.n_items), kThreads, 0, st, a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// features of the flagged tracks (UkfOp::pad & bits) from a raw mask state plane (thr = 1) and a depth plane; wt_count /
+// total are scratch ([n][n_warp_tiles], [n])
+int launch_or_features(const Geom& g, int n_tracks, const UkfOp* ops, int max_ops, int bits, const uint8_t* mask, long long mask_stride,
+                       int thr, const float* depth, long long depth_stride, int32_t* wt_count, int32_t* total, uint2* feat,
+                       long long feat_stride, int32_t* n_feat, cudaStream_t st) {
+    const int n_warp_tiles = (g.HW + kWarpTilePx - 1) / kWarpTilePx;
+    if (launch_mask_rank(mask, mask_stride, thr, g.HW, n_tracks, wt_count, total, nullptr, st)) return -1;
+    const int bx = max(1, min(n_warp_tiles / (kThreads / 32), max(1, 148 * 8 / n_tracks)));
+    ROFTB_LAUNCH(k_or_features, dim3(bx, n_tracks), kThreads, 0, st, g, ops, max_ops, bits, mask, mask_stride, thr, depth, depth_stride,
+                 wt_count, total, n_warp_tiles, feat, feat_stride, n_feat);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_or_feat_copy(int n_tracks, const UkfOp* ops, int max_ops, int bits, const uint2* src, const int32_t* n_src, uint2* dst,
+                        int32_t* n_dst, long long stride, cudaStream_t st) {
+    ROFTB_LAUNCH(k_or_feat_copy, dim3(max(1, 148 * 4 / n_tracks), n_tracks), kThreads, 0, st, ops, max_ops, bits, src, n_src, dst, n_dst,
+                 stride);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_or_l1(int n_tracks, const int32_t* resume, const uint2* feat, const int32_t* n_feat, long long feat_stride,
+                 const float* rendered, long long tile, int divider, int W, double* err, int32_t* samples, cudaStream_t st) {
+    ROFTB_LAUNCH(k_or_l1, n_tracks, 1024, 0, st, n_tracks, resume, feat, n_feat, feat_stride, rendered, tile, divider, W, err, samples);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -189,29 +189,6 @@ __global__ void k_or_select(int n_tracks, const int32_t* __restrict__ resume, co
     for (int i = threadIdx.x; i < 144; i += blockDim.x) cov[(long long)t * 144 + i] = cand_cov[(long long)t * 288 + 144 + i];
 }
 
-
-// Buffered features of the render-and-compare test (ROFTFilter::buffer_outlier_rejection_features, ROFTFilter.cpp:624-646):
-// the mask state and the depth of the tracks whose first op carries `bits` in UkfOp::pad are copied plane by plane.
-// Two hops: k_or_copy(stage <- live planes) as soon as the step's mask state is final, k_or_copy(snapshot <- stage) on the
-// pose stream before (bit 2) or after (bit 1) the step's test, which may still be reading the previous snapshot.
-__global__ void __launch_bounds__(kThreads) k_or_copy(const UkfOp* __restrict__ ops, int max_ops, int bits,
-                                                      const uint8_t* __restrict__ mask_src, const float* __restrict__ depth_src,
-                                                      long long depth_stride, uint8_t* __restrict__ mask_dst,
-                                                      float* __restrict__ depth_dst, int HW) {
-    const int t = blockIdx.y;
-    if ((ops[(long long)t * max_ops].pad & bits) == 0) return;
-    const uint4* ms = reinterpret_cast<const uint4*>(mask_src + (long long)t * HW);
-    uint4* md = reinterpret_cast<uint4*>(mask_dst + (long long)t * HW);
-    const uint4* ds = reinterpret_cast<const uint4*>(depth_src + (long long)t * depth_stride);
-    uint4* dd = reinterpret_cast<uint4*>(depth_dst + (long long)t * HW);
-    const int n16 = HW >> 4, n4 = HW >> 2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-        if (i < n16) md[i] = ms[i];
-        dd[i] = ds[i];
-    }
-    // (frame sizes are multiples of 16 pixels per track plane: check_geom)
-}
-
 }  // namespace
 
 int launch_render_depth(const RenderArgs& a, void* vertex_scratch, uint32_t* zbuf, float* out, cudaStream_t s) {
@@ -245,14 +222,6 @@ int launch_or_models(int n_tracks, const int32_t* resume, const double* cand_mea
 int launch_or_select(int n_tracks, const int32_t* resume, const int32_t* selected, const double* cand_mean, const double* cand_cov,
                      double* mean, double* cov, cudaStream_t s) {
     ROFTB_LAUNCH(k_or_select, n_tracks, 64, 0, s, n_tracks, resume, selected, cand_mean, cand_cov, mean, cov);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
-
-int launch_or_copy(int n_tracks, const UkfOp* ops, int max_ops, int bits, const uint8_t* mask_src, const float* depth_src,
-                   long long depth_stride, uint8_t* mask_dst, float* depth_dst, int HW, cudaStream_t s) {
-    const int bx = max(1, min((HW / 4 + kThreads - 1) / kThreads, max(1, 148 * 8 / n_tracks)));
-    ROFTB_LAUNCH(k_or_copy, dim3(bx, n_tracks), kThreads, 0, s, ops, max_ops, bits, mask_src, depth_src, depth_stride, mask_dst,
-                 depth_dst, HW);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -70,12 +70,15 @@ struct roftb_ctx {
         double* err = nullptr; int32_t* samples = nullptr;   // [2][T]
         int32_t* selected = nullptr;        // [T]
         int32_t* wt_count = nullptr;        // [T][n_units] rank scratch of the masked L1
-        // features buffered at the previous re-synchronisation (ROFTFilter.cpp:624-646): raw mask state + depth per track.
-        // A refresh goes through a staging copy: stage <- live planes as soon as the step's mask state is final (own
-        // stream; the planes are recycled two steps later), snapshot <- stage on the pose stream, before or after the
-        // step's test, which may still be reading the previous snapshot
-        uint8_t* snap_mask = nullptr; float* snap_depth = nullptr;
-        uint8_t* stage_mask = nullptr; float* stage_depth = nullptr;
+        // features buffered at the previous re-synchronisation (ROFTFilter.cpp:624-646), compacted: per track the list
+        // (pixel index, depth) of every second segmentation pixel (extract.cu: k_or_features).  A refresh goes through a
+        // staging list: stage <- live planes as soon as the step's mask state is final (own stream; the planes are recycled
+        // two steps later), snapshot <- stage on the pose stream, before or after the step's test, which may still be
+        // reading the previous snapshot
+        uint2* feat_snap = nullptr; uint2* feat_stage = nullptr;     // [T][feat_stride]
+        int32_t* n_snap = nullptr; int32_t* n_stage = nullptr;       // [T] entries
+        int32_t* rank_total = nullptr;                               // [T] scratch
+        long long feat_stride = 0;
         cudaEvent_t stage_done[3] = {nullptr, nullptr, nullptr}, unstage_done = nullptr, ops_ready = nullptr;
         bool stage_done_used[3] = {false, false, false}, unstage_done_used = false;
         cudaStream_t stream = nullptr;      // snapshot copies
@@ -429,10 +432,12 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
         CKC(dalloc(&oj.samples, (size_t)2 * T));
         CKC(dalloc(&oj.selected, (size_t)T));
         CKC(dalloc(&oj.wt_count, (size_t)T * ctx->n_units));
-        CKC(dalloc(&oj.snap_mask, (size_t)T * ctx->HW));
-        CKC(dalloc(&oj.snap_depth, (size_t)T * ctx->HW));
-        CKC(dalloc(&oj.stage_mask, (size_t)T * ctx->HW));
-        CKC(dalloc(&oj.stage_depth, (size_t)T * ctx->HW));
+        oj.feat_stride = (long long)((ctx->HW / 2 + 16) & ~(size_t)1);
+        CKC(dalloc(&oj.feat_snap, (size_t)T * oj.feat_stride));
+        CKC(dalloc(&oj.feat_stage, (size_t)T * oj.feat_stride));
+        CKC(dalloc(&oj.n_snap, (size_t)T));
+        CKC(dalloc(&oj.n_stage, (size_t)T));
+        CKC(dalloc(&oj.rank_total, (size_t)T));
         for (int i = 0; i < 3; ++i) CKC(cudaEventCreateWithFlags(&oj.stage_done[i], cudaEventDisableTiming));
         CKC(cudaEventCreateWithFlags(&oj.unstage_done, cudaEventDisableTiming));
         CKC(cudaEventCreateWithFlags(&oj.ops_ready, cudaEventDisableTiming));
@@ -487,7 +492,7 @@ void roftb_destroy(roftb_ctx* ctx) {
         auto& oj = ctx->orj;
         if (oj.stream) { cudaStreamSynchronize(oj.stream); cudaStreamDestroy(oj.stream); }
         void* op[] = {oj.resume, oj.cand_mean, oj.cand_cov, oj.model, oj.vertex_scratch, oj.zbuf, oj.rendered, oj.err, oj.samples,
-                      oj.selected, oj.wt_count, oj.snap_mask, oj.snap_depth, oj.stage_mask, oj.stage_depth};
+                      oj.selected, oj.wt_count, oj.feat_snap, oj.feat_stage, oj.n_snap, oj.n_stage, oj.rank_total};
         for (void* p : op)
             if (p) cudaFree(p);
         for (int i = 0; i < 3; ++i)
@@ -1153,8 +1158,9 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
         CK(cudaStreamWaitEvent(cs, ctx->vel_done_event, 0));
         CK(cudaStreamWaitEvent(cs, ctx->mask_event, 0));
         if (oj.unstage_done_used) CK(cudaStreamWaitEvent(cs, oj.unstage_done, 0));
-        if (launch_or_copy(T, d_ops, kMaxUkfOps, 3, seg_next, d_depth, depth_stride, oj.stage_mask, oj.stage_depth, (int)ctx->HW, cs))
-            return fail(ctx, "launch_or_copy failed");
+        if (launch_or_features(ctx->g, T, d_ops, kMaxUkfOps, 3, seg_next, (long long)ctx->HW, 1, d_depth, depth_stride, oj.wt_count,
+                               oj.rank_total, oj.feat_stage, oj.feat_stride, oj.n_stage, cs))
+            return fail(ctx, "launch_or_features failed");
         const int cur = (int)(ctx->frame_idx % 3);
         CK(cudaEventRecord(oj.stage_done[cur], cs));
         oj.stage_done_used[cur] = true;
@@ -1181,9 +1187,8 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
         const int stage_slot = (int)(ctx->frame_idx % 3);
         if (any_stage_before) {
             CK(cudaStreamWaitEvent(us, oj.stage_done[stage_slot], 0));
-            if (launch_or_copy(T, d_ops, kMaxUkfOps, 2, oj.stage_mask, oj.stage_depth, (long long)ctx->HW, oj.snap_mask, oj.snap_depth,
-                               (int)ctx->HW, us))
-                return fail(ctx, "launch_or_copy failed");
+            if (launch_or_feat_copy(T, d_ops, kMaxUkfOps, 2, oj.feat_stage, oj.n_stage, oj.feat_snap, oj.n_snap, oj.feat_stride, us))
+                return fail(ctx, "launch_or_feat_copy failed");
         }
         if (any_or) {
             // ROFTFilter::pick_best_alternative (ROFTFilter.cpp:467-621) on the buffered features, all on this stream
@@ -1199,18 +1204,9 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
             ra.w = ctx->g.W / dv; ra.h = ctx->g.H / dv;
             ra.scale = ctx->mesh_scale; ra.n_scale = T;
             if (launch_render_depth(ra, oj.vertex_scratch, oj.zbuf, oj.rendered, us)) return fail(ctx, "launch_render_depth failed");
-            CK(cudaMemsetAsync(oj.err, 0, sizeof(double) * 2 * T, us));
-            CK(cudaMemsetAsync(oj.samples, 0, sizeof(int32_t) * 2 * T, us));
-            SelectArgs sa;
-            memset(&sa, 0, sizeof(sa));
-            sa.g = ctx->g; sa.n_items = T;
-            sa.mask = oj.snap_mask; sa.mask_stride = (long long)ctx->HW; sa.thr = 1;  // the state holds raw values: threshold(> 1) on load
-            sa.depth = oj.snap_depth; sa.depth_stride = (long long)ctx->HW;
-            sa.wt_count = oj.wt_count;
-            for (int k = 0; k < 2; ++k)
-                if (launch_masked_depth_l1(sa, oj.rendered + (size_t)k * T * tile, (long long)tile, dv, oj.err + (size_t)k * T,
-                                           oj.samples + (size_t)k * T, us))
-                    return fail(ctx, "launch_masked_depth_l1 failed");
+            if (launch_or_l1(T, oj.resume, oj.feat_snap, oj.n_snap, oj.feat_stride, oj.rendered, (long long)tile, dv, ctx->g.W, oj.err,
+                             oj.samples, us))
+                return fail(ctx, "launch_or_l1 failed");
             if (launch_pick_best(T, oj.err, oj.samples, cfg.outlier_rejection_gain, oj.selected, nullptr, us)) return fail(ctx, "launch_pick_best failed");
             if (launch_or_select(T, oj.resume, oj.selected, oj.cand_mean, oj.cand_cov, ctx->p_mean, ctx->p_cov, us))
                 return fail(ctx, "launch_or_select failed");
@@ -1218,9 +1214,8 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
         }
         if (any_stage_after) {
             CK(cudaStreamWaitEvent(us, oj.stage_done[stage_slot], 0));
-            if (launch_or_copy(T, d_ops, kMaxUkfOps, 1, oj.stage_mask, oj.stage_depth, (long long)ctx->HW, oj.snap_mask, oj.snap_depth,
-                               (int)ctx->HW, us))
-                return fail(ctx, "launch_or_copy failed");
+            if (launch_or_feat_copy(T, d_ops, kMaxUkfOps, 1, oj.feat_stage, oj.n_stage, oj.feat_snap, oj.n_snap, oj.feat_stride, us))
+                return fail(ctx, "launch_or_feat_copy failed");
         }
         if (any_stage) {
             CK(cudaEventRecord(oj.unstage_done, us));

@@ -254,8 +254,13 @@ size_t render_vertex_scratch_bytes(int n_items, int n_vertices);
 int launch_render_depth(const RenderArgs& a, void* vertex_scratch, uint32_t* zbuf, float* out, cudaStream_t s);
 int launch_pick_best(int n, const double* err, const int32_t* samples, double gain, int32_t* selected, double* likelihoods,
                      cudaStream_t s);
-int launch_or_copy(int n_tracks, const UkfOp* ops, int max_ops, int bits, const uint8_t* mask_src, const float* depth_src,
-                   long long depth_stride, uint8_t* mask_dst, float* depth_dst, int HW, cudaStream_t s);
+int launch_or_features(const Geom& g, int n_tracks, const UkfOp* ops, int max_ops, int bits, const uint8_t* mask, long long mask_stride,
+                       int thr, const float* depth, long long depth_stride, int32_t* wt_count, int32_t* total, uint2* feat,
+                       long long feat_stride, int32_t* n_feat, cudaStream_t st);
+int launch_or_feat_copy(int n_tracks, const UkfOp* ops, int max_ops, int bits, const uint2* src, const int32_t* n_src, uint2* dst,
+                        int32_t* n_dst, long long stride, cudaStream_t st);
+int launch_or_l1(int n_tracks, const int32_t* resume, const uint2* feat, const int32_t* n_feat, long long feat_stride,
+                 const float* rendered, long long tile, int divider, int W, double* err, int32_t* samples, cudaStream_t st);
 int launch_or_models(int n_tracks, const int32_t* resume, const double* cand_mean, float* model, cudaStream_t s);
 int launch_or_select(int n_tracks, const int32_t* resume, const int32_t* selected, const double* cand_mean, const double* cand_cov,
                      double* mean, double* cov, cudaStream_t s);
