@@ -292,6 +292,33 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
     unsigned long long* clk = (a.phase_clock && rank == 0 && tid == 0) ? a.phase_clock + (long long)t * 8 : nullptr;
     if (clk) clk[0] = global_timer();
     if (rank == 0) span_stamp(a.span_clock, false);
+    // scratch slot: rank 0 claims one bit of the pool bitmap right away - the atomic's round trip overlaps the table and
+    // worklist set-up below (the slot is published to the other CTAs at cluster barrier #1)
+    if (c.enable && rank == 0 && tid == 0) {
+        int sl = -1;
+        while (sl < 0) {
+            for (int w = 0; w < a.sc.n_slot_words && sl < 0; ++w) {
+                uint32_t cur = *reinterpret_cast<volatile uint32_t*>(a.sc.slot_bitmap + w);
+                while (~cur) {
+                    const int bit = __ffs(~cur) - 1;
+                    const uint32_t old = atomicOr(a.sc.slot_bitmap + w, 1u << bit);
+                    if (!(old & (1u << bit))) { sl = w * 32 + bit; break; }
+                    cur = old | (1u << bit);
+                }
+            }
+        }
+        s_misc[0] = sl;
+        a.sc.track_slot[t] = sl;
+    }
+    // flags of the destination plane's previous content (lazy clear below): in flight during the worklist set-up
+    uint4 pre_of = make_uint4(0u, 0u, 0u, 0u);
+    const int pre_gi = (int)rank * kVtThreads + tid;
+    bool pre_ok = false;
+    if (do_sc) {
+        const uint8_t* of0 = a.occ_dst + (long long)t * a.n_units;
+        pre_ok = ((reinterpret_cast<uintptr_t>(of0) & 15) == 0) && pre_gi * 16 + 16 <= a.n_units;
+        if (pre_ok) pre_of = __ldcg(reinterpret_cast<const uint4*>(of0) + pre_gi);
+    }
 
     float* s_xh = reinterpret_cast<float*>(smem + a.smem_tab);
     float* s_yh = s_xh + W;
@@ -364,7 +391,7 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
             const int ub = gi * 16;
             uint32_t w[4] = {0u, 0u, 0u, 0u};
             if (vec && ub + 16 <= a.n_units) {
-                const uint4 v4 = *reinterpret_cast<const uint4*>(of + ub);
+                const uint4 v4 = (pre_ok && gi == pre_gi) ? pre_of : *reinterpret_cast<const uint4*>(of + ub);
                 w[0] = v4.x; w[1] = v4.y; w[2] = v4.z; w[3] = v4.w;
                 if (v4.x | v4.y | v4.z | v4.w) *reinterpret_cast<uint4*>(of + ub) = make_uint4(0u, 0u, 0u, 0u);
             } else {
@@ -388,21 +415,7 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
     int slot = -1;
     if (c.enable) {
         if (rank == 0) {
-            if (tid == 0) {
-                int sl = -1;
-                while (sl < 0) {
-                    for (int w = 0; w < a.sc.n_slot_words && sl < 0; ++w) {
-                        uint32_t cur = *reinterpret_cast<volatile uint32_t*>(a.sc.slot_bitmap + w);
-                        while (~cur) {
-                            const int bit = __ffs(~cur) - 1;
-                            const uint32_t old = atomicOr(a.sc.slot_bitmap + w, 1u << bit);
-                            if (!(old & (1u << bit))) { sl = w * 32 + bit; break; }
-                            cur = old | (1u << bit);
-                        }
-                    }
-                }
-                s_misc[0] = sl;
-                a.sc.track_slot[t] = sl;
+            if (tid == 0) {  // (the slot itself was claimed at the top of the kernel)
                 if (a.wl_units) a.wl_units[t] = n_list;
                 if (a.wl_pixels) a.wl_pixels[t] = 0;
             }
