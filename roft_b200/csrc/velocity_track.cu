@@ -1109,21 +1109,18 @@ __global__ void __maxnreg__(REGS) k_velocity_track(const __grid_constant__ VtArg
                 const long long off = (long long)c * chunk_stride + (lo - s_base[c]);
                 const float2* nup = nu_t + off;
                 const uint2* dpp = dp_t + off;
-                float2 A[PF];
-                uint2 D[PF];
+                // two register sets alternate (no copies): while one trip is accumulated the next is in flight
+                float2 A[PF], B[PF];
+                uint2 D[PF], E[PF];
                 fetch(nup, dpp, lane, n, A, D);
 #pragma unroll 1
-                for (int k = lane; k < n; k += 32 * PF) {
-                    float2 An[PF];
-                    uint2 Dn[PF];
-                    fetch(nup, dpp, k + 32 * PF, n, An, Dn);
+                for (int k = lane; k < n; k += 64 * PF) {
+                    fetch(nup, dpp, k + 32 * PF, n, B, E);
 #pragma unroll
                     for (int u = 0; u < PF; ++u) accum(A[u].x, A[u].y, D[u].x, D[u].y, k + 32 * u < n);
+                    fetch(nup, dpp, k + 64 * PF, n, A, D);
 #pragma unroll
-                    for (int u = 0; u < PF; ++u) {
-                        A[u] = An[u];
-                        D[u] = Dn[u];
-                    }
+                    for (int u = 0; u < PF; ++u) accum(B[u].x, B[u].y, E[u].x, E[u].y, k + 32 * PF + 32 * u < n);
                 }
                 lo = ce;
                 ++c;
