@@ -48,7 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc compilation of roft_b200 failed")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    # (the arch on the link line keeps nvcc from adding a default sm_52 stub image to the library)
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     return LIB
 
