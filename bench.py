@@ -432,7 +432,7 @@ def extra_workload(api, dev, local, name, T, peak, accum):
     """Short device-resident run of another workload (reported beside the headline, never instead of it)."""
     import numpy as np
     import torch
-    wl = WORKLOADS[name]
+    wl = WORKLOADS[name.split("@")[0]]  # "c4@512": the c4 workload at 512 tracks per GPU
     r = Runner(api, dev, local, T, 6, wl["coverage"], wl["delay"], wl["stride"], wl["fmt"], accum,
                outlier_rejection=wl.get("outlier_rejection", False))
 
@@ -451,7 +451,7 @@ def extra_workload(api, dev, local, name, T, peak, accum):
            "algorithmic_bytes_per_track_frame": B, "roofline_achieved": gbs, "roofline_frac": gbs / peak,
            "mean_listed_units": float(units.mean()), "mean_valid_pixels": float(cnt.mean()),
            # dram__bytes_read + dram__bytes_write of ONE velocity-kernel launch of this workload (committed ncu capture), or null
-           "velocity_kernel_traffic": ncu_traffic(f"velocity_{name}", T),
+           "velocity_kernel_traffic": ncu_traffic(f"velocity_{name.split('@')[0]}", T),
            "finite": bool(np.isfinite(pm).all() and np.isfinite(vm).all())}
     del r
     torch.cuda.empty_cache()
@@ -622,9 +622,9 @@ def run_own(args):
         extras = {}
         del r, trk
         torch.cuda.empty_cache()
-        for name in ("c2", "c5", "full", "ref"):
+        for name in ("c2", "c5", "full", "ref", "c4@512"):
             try:
-                extras[name] = extra_workload(api, dev, local, name, T, peak, args.accum)
+                extras[name] = extra_workload(api, dev, local, name, int(name.split("@")[1]) if "@" in name else T, peak, args.accum)
             except Exception as e:
                 extras[name] = {"error": repr(e)}
         try:
