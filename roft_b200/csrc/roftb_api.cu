@@ -10,8 +10,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <deque>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "roftb_internal.cuh"
@@ -47,8 +51,79 @@ struct TrackHost {
 
 }  // namespace
 
+// Pipelined parts: a context of many tracks is run as two (to four) complete sub-contexts (own streams, events, control
+// rings, state) over consecutive pieces of the track range.  Tracks never interact, so the halves are independent
+// pipelines - and the tail of one half's velocity launch, its epilogue and the launch latencies of its next step overlap
+// the other half's bulk instead of leaving the GPU partly idle (16 % of a step at 256 tracks).  The second
+// half's host work (control blocks, ~25 CUDA calls per step) runs on a worker thread.
+constexpr int kMaxParts = 4;
+struct PartWorker {  // one host thread per extra part: runs that part's share of an API call
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<int()> task;
+    bool has_task = false, done = false, quit = false;
+    int result = 0;
+    void post(const std::function<int()>& f) {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            task = f;
+            has_task = true;
+            done = false;
+        }
+        cv.notify_all();
+    }
+    int wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return done; });
+        return result;
+    }
+    void loop() {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv.wait(lk, [&] { return has_task || quit; });
+            if (quit) break;
+            std::function<int()> t = std::move(task);
+            has_task = false;
+            lk.unlock();
+            const int r = t();
+            lk.lock();
+            result = r;
+            done = true;
+            cv.notify_all();
+        }
+    }
+    void stop() {
+        if (!th.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            quit = true;
+        }
+        cv.notify_all();
+        th.join();
+    }
+};
+struct Composite {
+    int n = 0;                                   // parts
+    roftb_ctx* sub[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};
+    int first[kMaxParts] = {0, 0, 0, 0}, count[kMaxParts] = {0, 0, 0, 0};
+    cudaEvent_t join_ev[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};
+    PartWorker worker[kMaxParts];                // [0] unused: part 0 runs on the caller's thread
+    // f(part) for every part at once
+    int run_all(const std::function<int(int)>& f) {
+        for (int h = 1; h < n; ++h) worker[h].post([&f, h] { return f(h); });
+        int rc = f(0);
+        for (int h = 1; h < n; ++h) {
+            const int r = worker[h].wait();
+            if (!rc) rc = r;
+        }
+        return rc;
+    }
+};
+
 struct roftb_ctx {
     roftb_config cfg;
+    Composite* comp = nullptr;   // non-null: this context only fans out to two half contexts
     Geom g;
     int T = 0;
     size_t HW = 0;
@@ -257,9 +332,9 @@ const char* roftb_last_error(const roftb_ctx* ctx) { return ctx ? ctx->err.c_str
 
 int64_t roftb_kernel_launches(const roftb_ctx* ctx) { return ctx ? (int64_t)(g_launch_count.load() - ctx->launches0) : 0; }
 
-void* roftb_stream(roftb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+void* roftb_stream(roftb_ctx* ctx) { return ctx ? (void*)(ctx->comp ? ctx->comp->sub[0]->stream : ctx->stream) : nullptr; }
 
-int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
+static int create_single(const roftb_config* cfg, roftb_ctx** out) {
     if (!cfg || !out) { g_create_error = "null argument"; return -2; }
     *out = nullptr;
     std::string err;
@@ -476,8 +551,78 @@ int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
     return 0;
 }
 
+int roftb_create(const roftb_config* cfg, roftb_ctx** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return -2; }
+    // ROFTB_PARTS: number of pipelined part contexts (1 = none); default: 2 from 64 tracks
+    const char* eh = getenv("ROFTB_PARTS");
+    int parts = eh ? atoi(eh) : (cfg->n_tracks >= 64 ? 2 : 1);
+    parts = std::max(1, std::min(parts, std::min(kMaxParts, cfg->n_tracks)));
+    if (parts < 2) return create_single(cfg, out);
+    *out = nullptr;
+    roftb_ctx* ctx = new roftb_ctx();
+    ctx->cfg = *cfg;
+    ctx->T = cfg->n_tracks;
+    ctx->dev = cfg->device;
+    ctx->launches0 = g_launch_count;
+    ctx->comp = new Composite();
+    Composite& c = *ctx->comp;
+    c.n = parts;
+    for (int h = 0, at = 0; h < parts; ++h) {
+        c.first[h] = at;
+        c.count[h] = cfg->n_tracks / parts + (h < cfg->n_tracks % parts ? 1 : 0);
+        at += c.count[h];
+    }
+    for (int h = 0; h < parts; ++h) {
+        roftb_config sc = *cfg;
+        sc.n_tracks = c.count[h];
+        if (create_single(&sc, &c.sub[h]) != 0) {
+            roftb_destroy(ctx);
+            return -1;
+        }
+    }
+    fill_geom(ctx);
+    ctx->HW = (size_t)ctx->g.HW;
+    ctx->flow_elems = (size_t)ctx->g.Wf * ctx->g.Hf * 2;
+    if (cudaSetDevice(ctx->dev) != cudaSuccess) {
+        g_create_error = "cudaSetDevice failed";
+        roftb_destroy(ctx);
+        return -1;
+    }
+    for (int h = 1; h < parts; ++h) {
+        if (cudaEventCreateWithFlags(&c.join_ev[h], cudaEventDisableTiming) != cudaSuccess) {
+            g_create_error = "cannot create the join events of the part contexts";
+            roftb_destroy(ctx);
+            return -1;
+        }
+        PartWorker* w = &c.worker[h];
+        w->th = std::thread([w] { w->loop(); });
+    }
+    *out = ctx;
+    return 0;
+}
+
+// error of a half context -> the composite's
+static int comp_fail(roftb_ctx* ctx, int rc) {
+    if (rc) {
+        for (int h = 0; h < ctx->comp->n; ++h)
+            if (ctx->comp->sub[h] && !ctx->comp->sub[h]->err.empty()) { ctx->err = ctx->comp->sub[h]->err; break; }
+    }
+    return rc;
+}
+
 void roftb_destroy(roftb_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->comp) {
+        Composite* c = ctx->comp;
+        for (int h = 1; h < kMaxParts; ++h) c->worker[h].stop();
+        for (int h = 0; h < kMaxParts; ++h) {
+            roftb_destroy(c->sub[h]);
+            if (c->join_ev[h]) cudaEventDestroy(c->join_ev[h]);
+        }
+        delete c;
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->dev);
     // nothing may still be running on any of the streams when the buffers go away
     for (cudaStream_t st : {ctx->copy_stream, ctx->prep_stream, ctx->stream, ctx->aux_stream, ctx->mask_stream, ctx->ukf_stream,
@@ -546,6 +691,11 @@ void roftb_destroy(roftb_ctx* ctx) {
 
 int roftb_sync(roftb_ctx* ctx) {
     if (!ctx) return -2;
+    if (ctx->comp) {
+        int rc = 0;
+        for (int h = 0; h < ctx->comp->n; ++h) rc |= roftb_sync(ctx->comp->sub[h]);
+        return comp_fail(ctx, rc);
+    }
     CK(cudaSetDevice(ctx->dev));
     CK(cudaStreamSynchronize(ctx->copy_stream));
     CK(cudaStreamSynchronize(ctx->prep_stream));
@@ -557,6 +707,17 @@ int roftb_sync(roftb_ctx* ctx) {
 
 int roftb_join(roftb_ctx* ctx) {
     if (!ctx) return -2;
+    if (ctx->comp) {  // everything of EVERY part before whatever is recorded on roftb_stream (= the first part's) next
+        Composite& c = *ctx->comp;
+        for (int h = c.n - 1; h >= 0; --h)
+            if (roftb_join(c.sub[h])) return comp_fail(ctx, -1);
+        CK(cudaSetDevice(ctx->dev));
+        for (int h = 1; h < c.n; ++h) {
+            CK(cudaEventRecord(c.join_ev[h], c.sub[h]->stream));
+            CK(cudaStreamWaitEvent(c.sub[0]->stream, c.join_ev[h], 0));
+        }
+        return 0;
+    }
     CK(cudaSetDevice(ctx->dev));
     CK(cudaEventRecord(ctx->join_event, ctx->ukf_stream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->join_event, 0));
@@ -591,6 +752,23 @@ static void prof_collect(roftb_ctx* ctx, int slot) {
 
 int roftb_profile(roftb_ctx* ctx, int32_t enable, double* ms_per_step, int64_t* steps) {
     if (!ctx) return -2;
+    if (ctx->comp) {  // phase times: mean over the parts (they run side by side)
+        Composite& c = *ctx->comp;
+        double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+        int64_t s0 = 0;
+        int rc = 0;
+        for (int h = 0; h < c.n; ++h) {
+            double m[7] = {0, 0, 0, 0, 0, 0, 0};
+            int64_t sh = 0;
+            rc |= roftb_profile(c.sub[h], enable, m, &sh);
+            for (int j = 0; j < 7; ++j) acc[j] += m[j] / c.n;
+            if (h == 0) s0 = sh;
+        }
+        if (ms_per_step)
+            for (int j = 0; j < 7; ++j) ms_per_step[j] = acc[j];
+        if (steps) *steps = s0;
+        return comp_fail(ctx, rc);
+    }
     CK(cudaSetDevice(ctx->dev));
     for (int i = 0; i < kCtlRing; ++i) prof_collect(ctx, i);
     if (ms_per_step) {
@@ -711,6 +889,13 @@ int roftb_profile(roftb_ctx* ctx, int32_t enable, double* ms_per_step, int64_t* 
 // ---------------------------------------------------------------------------------------------
 int roftb_filter_init(roftb_ctx* ctx, const double* p_mean0, const double* v_mean0) {
     if (!ctx) return -2;
+    if (ctx->comp) {
+        Composite& c = *ctx->comp;
+        int rc = 0;
+        for (int h = 0; h < c.n; ++h)
+            rc |= roftb_filter_init(c.sub[h], p_mean0 ? p_mean0 + (size_t)c.first[h] * 13 : nullptr, v_mean0 ? v_mean0 + (size_t)c.first[h] * 6 : nullptr);
+        return comp_fail(ctx, rc);
+    }
     const int T = ctx->T;
     CK(cudaSetDevice(ctx->dev));
     CK(cudaStreamSynchronize(ctx->prep_stream));
@@ -817,6 +1002,25 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f);
 
 int roftb_filter_step(roftb_ctx* ctx, const roftb_frame* f) {
     if (!ctx || !f) return -2;
+    if (ctx->comp) {  // the parts step side by side: the same frame with every per-track pointer shifted
+        Composite& c = *ctx->comp;
+        roftb_frame fr[kMaxParts];
+        const size_t fb = ctx->g.flow_s16 ? 2 : 4;
+        for (int h = 0; h < c.n; ++h) {
+            const size_t o = (size_t)c.first[h];
+            fr[h] = *f;
+            if (f->depth) fr[h].depth = f->depth + o * (size_t)f->depth_track_stride;
+            if (f->flow) fr[h].flow = reinterpret_cast<const char*>(f->flow) + o * (size_t)f->flow_track_stride * fb;
+            if (f->mask) fr[h].mask = f->mask + o * (size_t)f->mask_track_stride;
+            if (f->flow_valid) fr[h].flow_valid = f->flow_valid + o;
+            if (f->mask_valid) fr[h].mask_valid = f->mask_valid + o;
+            if (f->pose) fr[h].pose = f->pose + o * 7;
+            if (f->pose_valid) fr[h].pose_valid = f->pose_valid + o;
+            if (f->dt) fr[h].dt = f->dt + o;
+        }
+        const int rc = c.run_all([&](int h) { return roftb_filter_step(c.sub[h], &fr[h]); });
+        return comp_fail(ctx, rc);
+    }
     if (ctx->poisoned) return fail(ctx, "roftb_filter_step: a previous step failed; call roftb_filter_init first");
     const long long idx0 = ctx->frame_idx;
     const int rc = filter_step_impl(ctx, f);
@@ -1242,6 +1446,16 @@ static int filter_step_impl(roftb_ctx* ctx, const roftb_frame* f) {
 
 int roftb_get_state(roftb_ctx* ctx, double* p_mean, double* p_cov, double* v_mean, double* v_cov) {
     if (!ctx) return -2;
+    if (ctx->comp) {
+        Composite& c = *ctx->comp;
+        int rc = 0;
+        for (int h = 0; h < c.n; ++h) {
+            const size_t o = (size_t)c.first[h];
+            rc |= roftb_get_state(c.sub[h], p_mean ? p_mean + o * 13 : nullptr, p_cov ? p_cov + o * 144 : nullptr, v_mean ? v_mean + o * 6 : nullptr,
+                                  v_cov ? v_cov + o * 36 : nullptr);
+        }
+        return comp_fail(ctx, rc);
+    }
     const size_t T = ctx->T;
     CK(cudaSetDevice(ctx->dev));
     cudaStream_t s = ctx->stream;
@@ -1257,6 +1471,15 @@ int roftb_get_state(roftb_ctx* ctx, double* p_mean, double* p_cov, double* v_mea
 
 int roftb_get_mask(roftb_ctx* ctx, uint8_t* raw, uint8_t* thresholded) {
     if (!ctx) return -2;
+    if (ctx->comp) {
+        Composite& c = *ctx->comp;
+        int rc = 0;
+        for (int h = 0; h < c.n; ++h) {
+            const size_t o = (size_t)c.first[h] * ctx->HW;
+            rc |= roftb_get_mask(c.sub[h], raw ? raw + o : nullptr, thresholded ? thresholded + o : nullptr);
+        }
+        return comp_fail(ctx, rc);
+    }
     const size_t n = (size_t)ctx->T * ctx->HW;
     CK(cudaSetDevice(ctx->dev));
     cudaStream_t s = ctx->stream;
@@ -1274,6 +1497,15 @@ int roftb_get_mask(roftb_ctx* ctx, uint8_t* raw, uint8_t* thresholded) {
 
 int roftb_get_velocity_info(roftb_ctx* ctx, int32_t* count, double* lambda, double* eta) {
     if (!ctx) return -2;
+    if (ctx->comp) {
+        Composite& c = *ctx->comp;
+        int rc = 0;
+        for (int h = 0; h < c.n; ++h) {
+            const size_t o = (size_t)c.first[h];
+            rc |= roftb_get_velocity_info(c.sub[h], count ? count + o : nullptr, lambda ? lambda + o * 36 : nullptr, eta ? eta + o * 6 : nullptr);
+        }
+        return comp_fail(ctx, rc);
+    }
     const size_t T = ctx->T;
     CK(cudaSetDevice(ctx->dev));
     cudaStream_t s = ctx->stream;
@@ -1286,6 +1518,12 @@ int roftb_get_velocity_info(roftb_ctx* ctx, int32_t* count, double* lambda, doub
 
 int roftb_get_worklist(roftb_ctx* ctx, int32_t* units, int32_t* pixels) {
     if (!ctx) return -2;
+    if (ctx->comp) {
+        Composite& c = *ctx->comp;
+        int rc = 0;
+        for (int h = 0; h < c.n; ++h) rc |= roftb_get_worklist(c.sub[h], units ? units + c.first[h] : nullptr, pixels ? pixels + c.first[h] : nullptr);
+        return comp_fail(ctx, rc);
+    }
     if (ctx->frame_idx == 0) return fail(ctx, "roftb_get_worklist: no step yet");
     const size_t T = ctx->T;
     CK(cudaSetDevice(ctx->dev));
@@ -1330,6 +1568,7 @@ extern "C" {
 
 int roftb_mask_sync(roftb_ctx* ctx, int32_t n_masks, const uint8_t* mask, const void* flows, int32_t n_flows,
                     int32_t zero_origin, uint8_t* out_raw, uint8_t* out_thr) {
+    if (ctx && ctx->comp) return comp_fail(ctx, roftb_mask_sync(ctx->comp->sub[0], n_masks, mask, flows, n_flows, zero_origin, out_raw, out_thr));  // operators run on the first half context
     if (!ctx || !mask || n_masks <= 0 || n_flows < 0 || n_flows > kMaxChain || (n_flows > 0 && !flows))
         return ctx ? fail(ctx, "roftb_mask_sync: bad argument") : -2;
     CK(cudaSetDevice(ctx->dev));
@@ -1452,11 +1691,13 @@ static int velocity_operator(roftb_ctx* ctx, int32_t n, const uint8_t* mask, con
 
 int roftb_flow_velocity(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, const float* depth, const void* flow,
                         const double* x_pred, const double* dt, double* lambda, double* eta, int32_t* count) {
+    if (ctx && ctx->comp) return comp_fail(ctx, roftb_flow_velocity(ctx->comp->sub[0], n_items, mask, depth, flow, x_pred, dt, lambda, eta, count));  // operators run on the first half context
     return velocity_operator(ctx, n_items, mask, depth, flow, x_pred, dt, nullptr, nullptr, lambda, eta, count, false);
 }
 
 int roftb_velocity_kf(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, const float* depth, const void* flow,
                       const double* dt, double* x, double* P, int32_t* count) {
+    if (ctx && ctx->comp) return comp_fail(ctx, roftb_velocity_kf(ctx->comp->sub[0], n_items, mask, depth, flow, dt, x, P, count));  // operators run on the first half context
     if (!x || !P) return ctx ? fail(ctx, "roftb_velocity_kf: x and P are required") : -2;
     return velocity_operator(ctx, n_items, mask, depth, flow, nullptr, dt, x, P, nullptr, nullptr, count, true);
 }
@@ -1483,6 +1724,7 @@ static int ukf_operator(roftb_ctx* ctx, int32_t n, double* mean, double* cov, co
 }
 
 int roftb_ukf_predict(roftb_ctx* ctx, int32_t n_items, double* mean, double* cov, const double* dt) {
+    if (ctx && ctx->comp) return comp_fail(ctx, roftb_ukf_predict(ctx->comp->sub[0], n_items, mean, cov, dt));  // operators run on the first half context
     if (!ctx || n_items <= 0 || !mean || !cov) return ctx ? fail(ctx, "roftb_ukf_predict: bad argument") : -2;
     std::vector<UkfOp> ops(n_items);
     for (int i = 0; i < n_items; ++i) {
@@ -1494,6 +1736,7 @@ int roftb_ukf_predict(roftb_ctx* ctx, int32_t n_items, double* mean, double* cov
 }
 
 int roftb_ukf_correct(roftb_ctx* ctx, int32_t n_items, double* mean, double* cov, const double* meas, const int32_t* meas_type) {
+    if (ctx && ctx->comp) return comp_fail(ctx, roftb_ukf_correct(ctx->comp->sub[0], n_items, mean, cov, meas, meas_type));  // operators run on the first half context
     if (!ctx || n_items <= 0 || !mean || !cov || !meas || !meas_type) return ctx ? fail(ctx, "roftb_ukf_correct: bad argument") : -2;
     std::vector<UkfOp> ops(n_items);
     for (int i = 0; i < n_items; ++i) {
@@ -1522,6 +1765,7 @@ static void fill_select(roftb_ctx* ctx, SelectArgs& a, TmpBuf& tb, int32_t n, co
 
 int roftb_flow_measurement_export(roftb_ctx* ctx, const uint8_t* mask, const float* depth, const void* flow, double dt,
                                   int32_t capacity, double* z, double* H, int32_t* n_valid) {
+    if (ctx && ctx->comp) return comp_fail(ctx, roftb_flow_measurement_export(ctx->comp->sub[0], mask, depth, flow, dt, capacity, z, H, n_valid));  // operators run on the first half context
     if (!ctx || !mask || !depth || !flow || capacity < 0 || !n_valid) return ctx ? fail(ctx, "export: bad argument") : -2;
     CK(cudaSetDevice(ctx->dev));
     cudaStream_t s = ctx->stream;
@@ -1543,6 +1787,7 @@ int roftb_flow_measurement_export(roftb_ctx* ctx, const uint8_t* mask, const flo
 
 int roftb_masked_points(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, const float* depth, double max_depth,
                         int32_t capacity, double* points, int32_t* count) {
+    if (ctx && ctx->comp) return comp_fail(ctx, roftb_masked_points(ctx->comp->sub[0], n_items, mask, depth, max_depth, capacity, points, count));  // operators run on the first half context
     if (!ctx || n_items <= 0 || !mask || !depth || capacity < 0 || !count) return ctx ? fail(ctx, "masked_points: bad argument") : -2;
     CK(cudaSetDevice(ctx->dev));
     cudaStream_t s = ctx->stream;
@@ -1562,6 +1807,7 @@ int roftb_masked_points(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, co
 
 int roftb_masked_depth_l1(roftb_ctx* ctx, int32_t n_items, const uint8_t* mask, const float* depth, const float* rendered,
                           int32_t divider, double* err_sum, int32_t* samples) {
+    if (ctx && ctx->comp) return comp_fail(ctx, roftb_masked_depth_l1(ctx->comp->sub[0], n_items, mask, depth, rendered, divider, err_sum, samples));  // operators run on the first half context
     if (!ctx || n_items <= 0 || !mask || !depth || !rendered || divider <= 0 || !err_sum || !samples)
         return ctx ? fail(ctx, "masked_depth_l1: bad argument") : -2;
     CK(cudaSetDevice(ctx->dev));
@@ -1646,6 +1892,11 @@ int render_tiles(roftb_ctx* ctx, TmpBuf& tb, int n_items, const double* poses7, 
 extern "C" {
 
 int roftb_set_mesh(roftb_ctx* ctx, const float* vertices, int32_t n_vertices, const int32_t* faces, int32_t n_faces) {
+    if (ctx && ctx->comp) {
+        int rc = 0;
+        for (int h = 0; h < ctx->comp->n; ++h) rc |= roftb_set_mesh(ctx->comp->sub[h], vertices, n_vertices, faces, n_faces);
+        return comp_fail(ctx, rc);
+    }
     if (!ctx || !vertices || !faces || n_vertices <= 0 || n_faces <= 0) return ctx ? fail(ctx, "roftb_set_mesh: bad argument") : -2;
     for (int64_t i = 0; i < (int64_t)n_faces * 3; ++i)
         if (faces[i] < 0 || faces[i] >= n_vertices) return fail(ctx, "roftb_set_mesh: face index out of range");
@@ -1670,6 +1921,11 @@ int roftb_set_mesh(roftb_ctx* ctx, const float* vertices, int32_t n_vertices, co
 
 int roftb_set_mesh_scale(roftb_ctx* ctx, const float* scale) {
     if (!ctx) return -2;
+    if (ctx->comp) {
+        int rc = 0;
+        for (int h = 0; h < ctx->comp->n; ++h) rc |= roftb_set_mesh_scale(ctx->comp->sub[h], scale ? scale + (size_t)ctx->comp->first[h] * 3 : nullptr);
+        return comp_fail(ctx, rc);
+    }
     CK(cudaSetDevice(ctx->dev));
     CK(cudaStreamSynchronize(ctx->ukf_stream));
     if (!scale) {
@@ -1683,6 +1939,7 @@ int roftb_set_mesh_scale(roftb_ctx* ctx, const float* scale) {
 }
 
 int roftb_render_depth(roftb_ctx* ctx, int32_t n_items, const double* poses7, int32_t divider, float* out_depth) {
+    if (ctx && ctx->comp) return comp_fail(ctx, roftb_render_depth(ctx->comp->sub[0], n_items, poses7, divider, out_depth));  // operators run on the first half context
     if (!ctx || n_items <= 0 || !poses7 || divider <= 0 || !out_depth) return ctx ? fail(ctx, "roftb_render_depth: bad argument") : -2;
     if (!ctx->mesh_nv) return fail(ctx, "roftb_render_depth: no mesh (roftb_set_mesh)");
     if (ctx->g.W % divider || ctx->g.H % divider) return fail(ctx, "roftb_render_depth: divider must divide the frame size");
@@ -1699,6 +1956,7 @@ int roftb_render_depth(roftb_ctx* ctx, int32_t n_items, const double* poses7, in
 
 int roftb_pick_best_alternative(roftb_ctx* ctx, int32_t n_items, const uint8_t* segmentation, const float* depth,
                                 const double* alternatives, int32_t divider, double gain, int32_t* selected, double* likelihoods) {
+    if (ctx && ctx->comp) return comp_fail(ctx, roftb_pick_best_alternative(ctx->comp->sub[0], n_items, segmentation, depth, alternatives, divider, gain, selected, likelihoods));  // operators run on the first half context
     if (!ctx || n_items <= 0 || !segmentation || !depth || !alternatives || divider <= 0 || !selected || !(gain != 0.0))
         return ctx ? fail(ctx, "roftb_pick_best_alternative: bad argument") : -2;
     if (!ctx->mesh_nv) return fail(ctx, "roftb_pick_best_alternative: no mesh (roftb_set_mesh)");

@@ -618,3 +618,42 @@ def test_filter_loop_with_outlier_rejection_matches_oracle(api, resync):
         trk2.step(np.stack([f.depth for f in frs]), flow, mask, pose=pose, pose_valid=pv)
     pm2, vm2 = trk2.state()
     assert rel(pm2, pm) < 1e-9 and rel(vm2, vm) < 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("parts", [2, 3])
+def test_pipelined_part_contexts_match_oracle(api, monkeypatch, parts):
+    """ROFTB_PARTS: a context run as 2-3 complete part contexts over consecutive pieces of the track range (the default from
+    64 tracks: one part's launch tail overlaps the other's bulk).  Same frame-by-frame parity as the single context, with
+    and without the render-and-compare test, and every per-track read-back (state, masks, counts) in track order."""
+    import torch
+    from roft_b200.synthetic import cuboid_mesh
+    monkeypatch.setenv("ROFTB_PARTS", str(parts))
+    cfg = small_cfg(subsampling_radius=2.0, use_pose_resync=True, segm_delay=3, pose_delay=3)
+    _run_filter_loop(api, cfg, "f32", 5, 12)
+    cfg = small_cfg(subsampling_radius=2.0, use_pose_resync=True, segm_delay=3, pose_delay=3, outlier_rejection=True,
+                    outlier_rejection_divider=2)
+    T, F = 4, 14
+    seq = sequence(cfg, T, F)
+    seq.pose[6, 3, :3] += torch.tensor([0.08, 0.0, 0.0], dtype=seq.pose.dtype)
+    verts, faces = cuboid_mesh(seq.half[0].numpy())
+    x0 = np.zeros((T, 13)); x0[:, 6:] = seq.pose[0].numpy()
+    trk = make_tracker(api, cfg, T, "f32")
+    trk.set_mesh(verts, faces)
+    trk.init(x0)
+    oracles = [o.RoftFilterOracle(cfg, x0[t], mesh=(verts, faces)) for t in range(T)]
+    for k in range(F):
+        frs = [frame_inputs(seq, cfg, k, t) for t in range(T)]
+        mask = np.stack([f.mask for f in frs]) if frs[0].mask is not None else None
+        pose = np.stack([f.pose if f.pose is not None else np.zeros(7) for f in frs])
+        pv = np.array([f.pose is not None for f in frs], np.uint8)
+        flow = np.stack([f.flow for f in frs]) if k > 0 else None
+        trk.step(np.stack([f.depth for f in frs]), flow, mask, pose=pose, pose_valid=pv)
+        pm, vm = trk.state()
+        units, pixels = trk.worklist()
+        assert units.shape == (T,) and (k < 2 or (units > 0).all())
+        for t in range(T):
+            ep, ev = oracles[t].step(frs[t])
+            assert rel(vm[t], ev) < TOL or np.linalg.norm(vm[t] - ev) < 1e-9, (k, t)
+            assert rel(pm[t, :9], ep[:9]) < TOL and quat_close(pm[t, 9:], ep[9:]) < TOL, (k, t, oracles[t].or_selected)
+    assert 1 in sum((orc.or_selected for orc in oracles), [])
