@@ -117,6 +117,9 @@ typedef struct roftb_frame {
 
 /* ---- context ------------------------------------------------------------------------- */
 void roftb_config_default(roftb_config* cfg);
+/* From 64 tracks on the context is built as two pipelined part contexts over the halves of the track range (DESIGN.md 6;
+ * ROFTB_PARTS overrides) and owns one internal host thread; results do not depend on it.  A context is still to be used
+ * from one host thread at a time. */
 int roftb_create(const roftb_config* cfg, roftb_ctx** out);
 void roftb_destroy(roftb_ctx* ctx);
 const char* roftb_last_error(const roftb_ctx* ctx); /* ctx may be NULL: last create() error */
