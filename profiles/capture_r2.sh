@@ -3,6 +3,8 @@
 # Numbers printed by a run under ncu are never bench values; only shares and per-kernel counters are used.
 set -u
 mkdir -p gpurun_out
+# (ROFTB_PARTS=1: one launch per step over all 256 tracks; capture_r2_parts.sh holds the launch list of the default, two part contexts)
+export ROFTB_PARTS=1
 B="python bench.py --no-cpu --no-e2e --no-sweep --no-parity --steps 12 --warmup 12"
 # launch list: per-launch durations of the repo's own kernels (cold cache, serialised), two mask periods
 if [ "${1:-all}" != "full" ]; then

@@ -20,8 +20,8 @@ def short(name):
     return name.split("(")[0].replace("void ", "").replace("roftb::<unnamed>::", "").replace("unnamed>::", "")
 
 
-def launches():
-    rows = list(csv.reader(open(os.path.join(src, "r02_launches.csv" if os.path.exists(os.path.join(src, "r02_launches.csv")) else "r02_launches_256tracks.csv"))))
+def launches(name="r02_launches", parts=1, out_name="r02_launches_256tracks.txt", note=""):
+    rows = list(csv.reader(open(os.path.join(src, name + ".csv" if os.path.exists(os.path.join(src, name + ".csv")) else name + "_256tracks.csv"))))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     h = rows[hi]
     ki, vi, ui = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
@@ -33,14 +33,14 @@ def launches():
             seq.append((short(r[ki]), v))
     # one mask period = from one k_tile_count (a delivery) to the next
     starts = [i for i, (n, _) in enumerate(seq) if n == "k_tile_count"]
-    period = seq[starts[0]:starts[1]] if len(starts) >= 2 else seq
+    period = seq[starts[0]:starts[parts]] if len(starts) > parts else seq  # (every part context delivers in the same step)
     d = collections.OrderedDict()
     for n, v in period:
         d.setdefault(n, []).append(v)
     tot = sum(v for _, v in period)
-    n_steps = sum(1 for n, _ in period if n.startswith("k_velocity_track"))
-    with open(os.path.join(out, "r02_launches_256tracks.txt"), "w") as f:
-        f.write("ncu --metrics gpu__time_duration.sum --clock-control none (profiles/capture_r2.sh), bench.py default workload, 256 tracks\n")
+    n_steps = sum(1 for n, _ in period if n.startswith("k_velocity_track")) // parts
+    with open(os.path.join(out, out_name), "w") as f:
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none (profiles/capture_r2.sh), bench.py default workload, 256 tracks" + note + "\n")
         f.write(f"one mask period = {n_steps} steps, {len(period)} launches, {tot:.1f} us serialised and cold = {tot / n_steps:.1f} us per step\n\n")
         f.write(f"{'kernel':36s} {'launches':>8s} {'mean us':>10s} {'min':>9s} {'max':>9s} {'share':>7s}\n")
         for n, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
@@ -123,6 +123,10 @@ def source():
 
 
 if __name__ == "__main__":
-    launches()
-    full()
-    source()
+    if os.path.exists(os.path.join(src, "r02_launches.csv")) or os.path.exists(os.path.join(src, "r02_launches_256tracks.csv")):
+        launches()
+        full()
+        source()
+    if os.path.exists(os.path.join(src, "r02_launches_parts2.csv")) or os.path.exists(os.path.join(src, "r02_launches_parts2_256tracks.csv")):
+        launches("r02_launches_parts2", 2, "r02_launches_parts2_256tracks.txt",
+                 "; default build: two pipelined part contexts of 128 tracks, every kernel launched once per part and step")
